@@ -1,0 +1,53 @@
+// Host-side translation of the C-ABI descriptors into the device structs.
+// The track tables restate RadiusArclengthTrack.get_track_key_pts / get_curvature_casadi_fn /
+// get_tangent_angle_casadi_fn (DGSQP/tracks/radius_arclength_track.py:361-408,199-225).
+#pragma once
+#include "../../include/dgsqp_b200.h"
+#include "racing_game.cuh"
+#include "sqp_v1.cuh"
+
+static inline int dg_fill_game(const dgsqp_racing_game* g, GameDesc* G) {
+  if (!g || g->M < 2 || g->M > DG_MAX_AGENTS || g->N < 2 || g->N > 64) return -1;
+  if (g->track_nseg < 1 || g->track_nseg > DG_MAX_SEGS) return -1;
+  G->M = g->M; G->N = g->N;
+  G->veh.Lr = g->L_r; G->veh.L = g->L_f + g->L_r; G->veh.c_da = g->c_da; G->veh.c_dr = g->c_dr; G->veh.c_s = g->c_s;
+  G->veh.inv_m = 1.0 / g->mass; G->veh.dt = g->dt;
+  for (int i = 0; i < 2; ++i) {
+    G->w_u[i] = g->input_weight[i]; G->w_du[i] = g->rate_weight[i];
+    G->u_ub[i] = g->u_ub[i]; G->u_lb[i] = g->u_lb[i]; G->rate_ub[i] = g->rate_ub[i]; G->rate_lb[i] = g->rate_lb[i];
+  }
+  G->c_prog = g->comp_weights[0]; G->c_comp = g->comp_weights[1];
+  G->half_width = g->half_width;
+  for (int a = 0; a < DG_MAX_AGENTS; ++a) G->obs_r[a] = g->obs_r[a];
+  TrackTable& T = G->trk;
+  T.nseg = g->track_nseg;
+  T.cum_len[0] = 0.0; T.cum_ang[0] = 0.0;
+  for (int i = 0; i < T.nseg; ++i) {
+    double len = g->track_seg_len[i], cv = g->track_seg_curv[i];
+    if (!(len > 0.0)) return -1;
+    T.curv[i] = cv;
+    T.cum_len[i + 1] = T.cum_len[i] + len;
+    T.cum_ang[i + 1] = cv == 0.0 ? T.cum_ang[i] : T.cum_ang[i] + len * cv;
+  }
+  T.L = T.cum_len[T.nseg];
+  for (int i = 0; i < T.nseg; ++i) {
+    T.slope[i] = (T.cum_ang[i + 1] - T.cum_ang[i]) / (T.cum_len[i + 1] - T.cum_len[i]);
+    if (i + 1 < T.nseg) T.brk[i] = T.cum_len[i + 1];
+  }
+  return 0;
+}
+
+static inline int dg_fill_params(const dgsqp_params* p, SolverParams* P) {
+  if (!p || p->line_search_iters < 1 || p->sqp_iters < 1 || !(p->mu_vio_thresh >= 0.0)) return -1;
+  P->reg = p->reg; P->p_tol = p->p_tol; P->d_tol = p->d_tol; P->beta = p->beta; P->tau = p->tau;
+  P->eig_floor = 1e-10;            // DGSQP.py:1294
+  P->merit_max = 1e6;              // DGSQP.py:1174
+  P->diverge_tol = 1e5;            // DGSQP.py:383
+  P->line_search_iters = p->line_search_iters; P->sqp_iters = p->sqp_iters; P->nonmono_ls = p->nonmono_ls;
+  P->merit_l1 = p->merit_function == 0; P->conv_approx = p->conv_approx;
+  P->rel_tol_req = 3;              // DGSQP.py:56
+  P->t_hat = 5;                    // DGSQP.py:1179
+  P->dbg_l0_perturb = 0.0;
+  P->mu_vio_thresh = p->mu_vio_thresh;
+  return 0;
+}

@@ -1,0 +1,145 @@
+// Dual initialisation  l0 = max(0, -lsqr(G G', G q))   (DGSQP/solvers/DGSQP.py:320-326).
+//
+// The reference calls SciPy's LSQR (Paige & Saunders) with its defaults atol = btol = 1e-6,
+// conlim = 1e8, iter_lim = 2*m, damp = 0, x0 = None on the singular m x m matrix G G'.  The
+// early-stopped Krylov iterate is not a closed form, so the recurrences and the ORDER of the
+// stopping tests are restated here after scipy/sparse/linalg/_isolve/lsqr.py:329-560.
+#pragma once
+#include "racing_game.cuh"
+
+struct LsqrBuf {
+  double* u;   // m
+  double* v;   // m
+  double* w;   // m
+  double* x;   // m
+  double* tn;  // n  scratch (G' v)
+  double* tm;  // m  scratch (A v)
+};
+
+DG_DEV void sym_ortho(double a, double b, double& cs, double& sn, double& r) {
+  if (b == 0.0) { cs = a > 0.0 ? 1.0 : (a < 0.0 ? -1.0 : 0.0); sn = 0.0; r = fabs(a); }
+  else if (a == 0.0) { cs = 0.0; sn = b > 0.0 ? 1.0 : -1.0; r = fabs(b); }
+  else if (fabs(b) > fabs(a)) {
+    double tau = a / b;
+    sn = (b > 0.0 ? 1.0 : -1.0) / sqrt(1.0 + tau * tau);
+    cs = sn * tau; r = b / sn;
+  } else {
+    double tau = b / a;
+    cs = (a > 0.0 ? 1.0 : -1.0) / sqrt(1.0 + tau * tau);
+    sn = cs * tau; r = a / cs;
+  }
+}
+
+// out = G (G' in)
+DG_DEV void lsqr_A(Cta& c, const Dims& D, const EvalBuf& E, const LsqrBuf& L, const double* in, double* out) {
+  game_GT_times(c, D, E, in, L.tn);
+  game_G_times(c, D, E, L.tn, out);
+}
+
+DG_DEV double vec_norm(Cta& c, int len, const double* v) {
+  double p = 0.0;
+  DG_FOR(i, len) p += v[i] * v[i];
+  return sqrt(c.sum(p));
+}
+
+// l_out[m] = max(0, -x_lsqr).  Returns the iteration count.
+DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D, const EvalBuf& E, const LsqrBuf& L, const double* qv, double* l_out) {
+  const int m = D.m;
+  const double atol = 1e-6, btol = 1e-6, conlim = 1e8, eps = 2.220446049250313e-16;
+  const int iter_lim = 2 * m;
+  const double ctol = 1.0 / conlim;
+  int itn = 0, istop = 0;
+  double anorm = 0, acond = 0, ddnorm = 0, res2 = 0, xnorm = 0, xxnorm = 0, z = 0, cs2 = -1, sn2 = 0;
+  // b = G q -> u
+  game_G_times(c, D, E, qv, L.u);
+  DG_FOR(i, m) L.x[i] = 0.0;
+  double bnorm = vec_norm(c, m, L.u);
+  double beta = bnorm, alfa = 0.0;
+  if (beta > 0.0) {
+    c.sync();
+    DG_FOR(i, m) L.u[i] *= 1.0 / beta;
+    c.sync();
+    lsqr_A(c, D, E, L, L.u, L.v);
+    alfa = vec_norm(c, m, L.v);
+  } else {
+    DG_FOR(i, m) L.v[i] = 0.0;
+  }
+  c.sync();
+  if (alfa > 0.0) { DG_FOR(i, m) L.v[i] *= 1.0 / alfa; }
+  c.sync();
+  DG_FOR(i, m) L.w[i] = L.v[i];
+  double rhobar = alfa, phibar = beta;
+  double arnorm = alfa * beta;
+  if (arnorm != 0.0) {
+    while (itn < iter_lim) {
+      ++itn;
+      // u = A v - alfa u
+      lsqr_A(c, D, E, L, L.v, L.tm);
+      DG_FOR(i, m) L.u[i] = L.tm[i] - alfa * L.u[i];
+      c.sync();
+      beta = vec_norm(c, m, L.u);
+      if (beta > 0.0) {
+        c.sync();
+        DG_FOR(i, m) L.u[i] *= 1.0 / beta;
+        c.sync();
+        anorm = sqrt(anorm * anorm + alfa * alfa + beta * beta);
+        lsqr_A(c, D, E, L, L.u, L.tm);
+        DG_FOR(i, m) L.v[i] = L.tm[i] - beta * L.v[i];
+        c.sync();
+        alfa = vec_norm(c, m, L.v);
+        c.sync();
+        if (alfa > 0.0) { DG_FOR(i, m) L.v[i] *= 1.0 / alfa; }
+        c.sync();
+      }
+      double rhobar1 = rhobar, psi = 0.0;
+      double cs, sn, rho;
+      sym_ortho(rhobar1, beta, cs, sn, rho);
+      double theta = sn * alfa;
+      rhobar = -cs * alfa;
+      double phi = cs * phibar;
+      phibar = sn * phibar;
+      double tau = sn * phi;
+      double t1 = phi / rho, t2 = -theta / rho;
+      double dpart = 0.0;
+      DG_FOR(i, m) {
+        double wi = L.w[i];
+        double dk = (1.0 / rho) * wi;
+        dpart += dk * dk;
+        L.x[i] += t1 * wi;
+        L.w[i] = L.v[i] + t2 * wi;
+      }
+      double dkn = sqrt(c.sum(dpart));
+      ddnorm += dkn * dkn;
+      double delta = sn2 * rho, gambar = -cs2 * rho, rhs = phi - delta * z, zbar = rhs / gambar;
+      xnorm = sqrt(xxnorm + zbar * zbar);
+      double gamma = sqrt(gambar * gambar + theta * theta);
+      cs2 = gambar / gamma; sn2 = theta / gamma; z = rhs / gamma;
+      xxnorm += z * z;
+      acond = anorm * sqrt(ddnorm);
+      double res1 = phibar * phibar;
+      res2 += psi * psi;
+      double rnorm = sqrt(res1 + res2);
+      arnorm = alfa * fabs(tau);
+      double test1 = rnorm / bnorm;
+      double test2 = arnorm / (anorm * rnorm + eps);
+      double test3 = 1.0 / (acond + eps);
+      double tt1 = test1 / (1.0 + anorm * xnorm / bnorm);
+      double rtol = btol + atol * anorm * xnorm / bnorm;
+#ifdef DG_LSQR_DEBUG
+      printf("%3d rnorm %.6e test1 %.6e rtol %.6e test2 %.3e anorm %.6e acond %.4e xnorm %.6e alfa %.6e beta %.6e\n", itn, rnorm, test1, rtol, test2, anorm, acond, xnorm, alfa, beta);
+#endif
+      if (itn >= iter_lim) istop = 7;
+      if (1.0 + test3 <= 1.0) istop = 6;
+      if (1.0 + test2 <= 1.0) istop = 5;
+      if (1.0 + tt1 <= 1.0) istop = 4;
+      if (test3 <= ctol) istop = 3;
+      if (test2 <= atol) istop = 2;
+      if (test1 <= rtol) istop = 1;
+      if (istop != 0) break;
+    }
+  }
+  c.sync();
+  DG_FOR(i, m) { double v = -L.x[i]; l_out[i] = v > 0.0 ? v : 0.0; }
+  c.sync();
+  return itn;
+}

@@ -1,0 +1,562 @@
+// Racing dynamic game on device: rollout, derivatives, constraints and the condensed game-KKT data.
+//
+// Replaces, for the racing games of the reference (scripts/DGSQP_ALGAMES_monte_carlo_chicane.py,
+// ..._curve.py, DGSQP_monte_carlo_agents.py), the CasADi functions evaluated by
+// DGSQP._evaluate (DGSQP/solvers/DGSQP.py:509-533):
+//   evaluate_dynamics (:598-601), evaluate_jacobian_A/B (:607-612), evaluate_hessian_E/F/G (:621-628),
+//   f_Du_x (:642-650), f_Cxu (:804-821), f_Du_C (:824-826), f_q (:673-676,898-899), f_Q (:679-727,829-934).
+// The constraint Jacobian G is never materialised: it is kept as the sensitivity rows of the states
+// the constraints read (x, y, e_y) and applied matrix-free (G v, G' w, single rows on demand).
+#pragma once
+#include "cta.cuh"
+#include "model_bicycle_gen.cuh"
+
+#define DG_MAX_AGENTS 4
+#define DG_MAX_SEGS 8
+#define DG_NQA 6
+#define DG_NUA 2
+#define DG_MAX_NQ (DG_NQA * DG_MAX_AGENTS)
+#define DG_MAX_PAIRS 6
+
+struct TrackTable {
+  int nseg;
+  double L;
+  double brk[DG_MAX_SEGS];        // nseg-1 interior breakpoints
+  double curv[DG_MAX_SEGS];       // curvature per segment
+  double cum_len[DG_MAX_SEGS + 1];
+  double cum_ang[DG_MAX_SEGS + 1];
+  double slope[DG_MAX_SEGS];      // tangent-angle slope per segment
+};
+
+struct GameDesc {
+  int M, N;
+  BicycleParams veh;
+  TrackTable trk;
+  double w_u[2], w_du[2], c_prog, c_comp;
+  double u_ub[2], u_lb[2];
+  double rate_ub[2], rate_lb[2];   // per-second rates; constraint uses dt*rate
+  double half_width;
+  double obs_r[DG_MAX_AGENTS];
+};
+
+struct Dims {
+  int M, N, nq, nu, n, m, P, nc0, nck, ncN, twoN;
+};
+
+DG_HD Dims make_dims(int M, int N) {
+  Dims d;
+  d.M = M; d.N = N; d.nq = DG_NQA * M; d.nu = DG_NUA * M; d.n = d.nu * N;
+  d.P = M * (M - 1) / 2;
+  d.nc0 = 8 * M; d.nck = d.P + 10 * M; d.ncN = d.P + 2 * M;
+  d.m = d.nc0 + (N - 1) * d.nck + d.ncN;
+  d.twoN = 2 * N;
+  return d;
+}
+
+// ---- constraint row layout (DGSQP.py:730-821): stage major; [shared, agent0(...), agent1(...)] ----
+enum { K_COLL = 0, K_RATE = 1, K_INUB = 2, K_INLB = 3, K_STUB = 4, K_STLB = 5 };
+
+DG_DEV int row_off(const Dims& D, int k) { return k == 0 ? 0 : D.nc0 + (k - 1) * D.nck; }
+DG_DEV int row_coll(const Dims& D, int k, int p) { return row_off(D, k) + p; }                        // k>=1
+DG_DEV int row_agent(const Dims& D, int k, int a) {
+  return k == 0 ? 8 * a : (k < D.N ? row_off(D, k) + D.P + 10 * a : row_off(D, k) + D.P + 2 * a);
+}
+DG_DEV int row_rate(const Dims& D, int k, int a, int r) { return row_agent(D, k, a) + r; }             // k<N
+DG_DEV int row_inub(const Dims& D, int k, int a, int c) { return row_agent(D, k, a) + 4 + c; }         // k<N
+DG_DEV int row_inlb(const Dims& D, int k, int a, int c) { return row_agent(D, k, a) + 6 + c; }         // k<N
+DG_DEV int row_stub(const Dims& D, int k, int a) { return row_agent(D, k, a) + (k < D.N ? 8 : 0); }    // k>=1
+DG_DEV int row_stlb(const Dims& D, int k, int a) { return row_agent(D, k, a) + (k < D.N ? 9 : 1); }    // k>=1
+
+DG_DEV void pair_ij(int M, int p, int& i, int& j) {
+  i = 0;
+  int rem = p;
+  while (rem >= M - 1 - i) { rem -= M - 1 - i; ++i; }
+  j = i + 1 + rem;
+}
+
+DG_DEV void decode_row(const Dims& D, int r, int& k, int& kind, int& a, int& b) {
+  int w;
+  if (r < D.nc0) { k = 0; w = r; }
+  else { k = 1 + (r - D.nc0) / D.nck; if (k > D.N) k = D.N; w = r - row_off(D, k); }
+  if (k >= 1) {
+    if (w < D.P) { kind = K_COLL; pair_ij(D.M, w, a, b); return; }
+    w -= D.P;
+  }
+  if (k < D.N) {
+    int per = k == 0 ? 8 : 10;
+    a = w / per; w -= a * per;
+    if (w < 4) { kind = K_RATE; b = w; }
+    else if (w < 6) { kind = K_INUB; b = w - 4; }
+    else if (w < 8) { kind = K_INLB; b = w - 6; }
+    else if (w == 8) { kind = K_STUB; b = 5; }
+    else { kind = K_STLB; b = 5; }
+  } else {
+    a = w / 2; w -= a * 2;
+    kind = w == 0 ? K_STUB : K_STLB; b = 5;
+  }
+}
+
+DG_DEV int uidx(const Dims& D, int a, int k, int c) { return a * D.twoN + 2 * k + c; }
+
+// ---- track look-ups (radius_arclength_track.py:199-225; CasADi pw_const / pw_lin / fmod) ----
+DG_DEV void track_eval(const TrackTable& T, double s, double& kappa, double& psit, double& dpsit) {
+  double sb = fmod(fmod(s, T.L) + T.L, T.L);
+  double kap = T.curv[0];
+  double l_prev = T.cum_ang[0] + T.slope[0] * (sb - T.cum_len[0]);
+  double ps = l_prev, dp = T.slope[0];
+  for (int i = 0; i + 1 < T.nseg; ++i) {
+    double ind = sb >= T.brk[i] ? 1.0 : 0.0;
+    kap += (T.curv[i + 1] - T.curv[i]) * ind;
+    double l_next = T.cum_ang[i + 1] + T.slope[i + 1] * (sb - T.cum_len[i + 1]);
+    ps += (l_next - l_prev) * ind;
+    dp += (T.slope[i + 1] - T.slope[i]) * ind;
+    l_prev = l_next;
+  }
+  kappa = kap; psit = ps; dpsit = dp;
+}
+
+// Per-CTA workspace views (global memory unless noted)
+struct EvalBuf {
+  double* x;     // (N+1)*nq
+  double* AB;    // N*M*48      d fd / d [q;u]  per (k,a)
+  double* T2;    // N*M*90      second derivatives per (k,a)
+  double* S;     // M*N*3*2N    sensitivity rows (x, y, e_y) of stages 1..N wrt own inputs
+  double* g;     // m
+  double* q;     // n   [grad_{u^a} J^a]_a
+  double* gtl;   // n   G' l
+  double* cst;   // (M+1)*(N+1)*nq  costates: f<M of J^f, f==M of l'C
+  double* Hc;    // (M+1)*N*M*15    sum_i p_i * T2[i]
+  double* Vbuf;  // 2*nq*nq  DP value-function Hessian (double buffered)
+  double* Q;     // n*n raw game Hessian (row major)
+  double* Wrow;  // n*nq  running rows of Dxu_Q in the Hessian DP
+  double* tmpS;  // M*N*3   state-row products for G v
+  double* cf;    // M*N*3   per (a,k) coefficients for G' w
+};
+
+// x_{k+1} = x_k + dt f(x_k,u_k): agents are dynamically decoupled, thread a rolls out agent a.
+DG_DEVN void game_rollout(Cta& c, const GameDesc& G, const Dims& D, const double* u, const double* x0, double* x) {
+  DG_FOR(a, D.M) {
+    double qk[DG_NQA];
+    for (int i = 0; i < DG_NQA; ++i) { qk[i] = x0[a * DG_NQA + i]; x[a * DG_NQA + i] = qk[i]; }
+    for (int k = 0; k < D.N; ++k) {
+      double kap, ps, dp, dq[DG_NQA];
+      track_eval(G.trk, qk[4], kap, ps, dp);
+      bicycle_fd_raw(qk, u + uidx(D, a, k, 0), G.veh, kap, ps, dp, qk[2] > 0 ? 1.0 : -1.0, dq);
+      for (int i = 0; i < DG_NQA; ++i) { qk[i] += dq[i]; x[(k + 1) * D.nq + a * DG_NQA + i] = qk[i]; }
+    }
+  }
+}
+
+DG_DEVN void game_linearize(Cta& c, const GameDesc& G, const Dims& D, const double* u, const EvalBuf& E, bool second) {
+  DG_FOR(t, D.N * D.M) {
+    int k = t / D.M, a = t - k * D.M;
+    const double* qk = E.x + k * D.nq + a * DG_NQA;
+    double kap, ps, dp;
+    track_eval(G.trk, qk[4], kap, ps, dp);
+    double sg = qk[2] > 0 ? 1.0 : -1.0;
+    bicycle_jac(qk, u + uidx(D, a, k, 0), G.veh, kap, ps, dp, sg, E.AB + t * 48);
+    if (second) bicycle_hess(qk, u + uidx(D, a, k, 0), G.veh, kap, ps, dp, sg, E.T2 + t * 90);
+  }
+}
+
+// f_Cxu: one thread per row
+DG_DEVN void game_constraints(Cta& c, const GameDesc& G, const Dims& D, const double* u, const double* up,
+                              const double* x, double* g) {
+  DG_FOR(r, D.m) {
+    int k, kind, a, b;
+    decode_row(D, r, k, kind, a, b);
+    double val;
+    if (kind == K_COLL) {
+      double dx = x[k * D.nq + a * DG_NQA] - x[k * D.nq + b * DG_NQA];
+      double dy = x[k * D.nq + a * DG_NQA + 1] - x[k * D.nq + b * DG_NQA + 1];
+      double rr = G.obs_r[a] + G.obs_r[b];
+      val = rr * rr - (dx * dx + dy * dy);
+    } else if (kind == K_RATE) {
+      int cc = b >> 1;
+      double uk = u[uidx(D, a, k, cc)];
+      double um = k == 0 ? up[a * DG_NUA + cc] : u[uidx(D, a, k - 1, cc)];
+      double du = uk - um;
+      val = (b & 1) == 0 ? du - G.veh.dt * G.rate_ub[cc] : G.veh.dt * G.rate_lb[cc] - du;
+    } else if (kind == K_INUB) val = u[uidx(D, a, k, b)] - G.u_ub[b];
+    else if (kind == K_INLB) val = G.u_lb[b] - u[uidx(D, a, k, b)];
+    else if (kind == K_STUB) val = x[k * D.nq + a * DG_NQA + b] - G.half_width;
+    else val = -G.half_width - x[k * D.nq + a * DG_NQA + b];
+    g[r] = val;
+  }
+}
+
+// Sensitivity rows (f_Du_x restricted to x, y, e_y): thread per input column (a, j).
+DG_DEVN void game_sens(Cta& c, const Dims& D, const EvalBuf& E) {
+  const int twoN = D.twoN;
+  DG_FOR(t, D.M * twoN) {
+    int a = t / twoN, j = t - a * twoN, kj = j >> 1, cc = j & 1;
+    double s6[DG_NQA];
+    const double* AB = E.AB + (kj * D.M + a) * 48;
+    for (int i = 0; i < DG_NQA; ++i) s6[i] = AB[i * 8 + 6 + cc];
+    for (int k = 1; k <= D.N; ++k) {
+      double* Sk = E.S + ((a * D.N + (k - 1)) * 3) * twoN + j;
+      if (k <= kj) { Sk[0] = 0.0; Sk[twoN] = 0.0; Sk[2 * twoN] = 0.0; continue; }
+      if (k > kj + 1) {
+        const double* Ak = E.AB + ((k - 1) * D.M + a) * 48;
+        double t6[DG_NQA];
+        for (int i = 0; i < DG_NQA; ++i) {
+          double acc = 0.0;
+          for (int jj = 0; jj < DG_NQA; ++jj) acc += Ak[i * 8 + jj] * s6[jj];
+          t6[i] = acc;
+        }
+        for (int i = 0; i < DG_NQA; ++i) s6[i] = t6[i];
+      }
+      Sk[0] = s6[0]; Sk[twoN] = s6[1]; Sk[2 * twoN] = s6[5];
+    }
+  }
+}
+
+DG_DEV double sens_dot(const Dims& D, const EvalBuf& E, int a, int k, int row, const double* va) {
+  const double* Sk = E.S + ((a * D.N + (k - 1)) * 3 + row) * D.twoN;
+  double acc = 0.0;
+  for (int j = 0; j < 2 * k; ++j) acc += Sk[j] * va[j];
+  return acc;
+}
+
+// y = G v   (v in R^n agent-major, y in R^m).  Two phases with one sync.
+DG_DEVN void game_G_times(Cta& c, const Dims& D, const EvalBuf& E, const double* v, double* y) {
+  c.sync();
+  DG_FOR(t, D.M * D.N * 3) {
+    int a = t / (D.N * 3), rem = t - a * D.N * 3, k1 = rem / 3, row = rem - k1 * 3;
+    E.tmpS[t] = sens_dot(D, E, a, k1 + 1, row, v + a * D.twoN);
+  }
+  c.sync();
+  DG_FOR(r, D.m) {
+    int k, kind, a, b;
+    decode_row(D, r, k, kind, a, b);
+    double val;
+    if (kind == K_COLL) {
+      double dx = E.x[k * D.nq + a * DG_NQA] - E.x[k * D.nq + b * DG_NQA];
+      double dy = E.x[k * D.nq + a * DG_NQA + 1] - E.x[k * D.nq + b * DG_NQA + 1];
+      const double* ta = E.tmpS + (a * D.N + (k - 1)) * 3;
+      const double* tb = E.tmpS + (b * D.N + (k - 1)) * 3;
+      val = -2.0 * (dx * (ta[0] - tb[0]) + dy * (ta[1] - tb[1]));
+    } else if (kind == K_RATE) {
+      int cc = b >> 1;
+      double dv = v[uidx(D, a, k, cc)] - (k > 0 ? v[uidx(D, a, k - 1, cc)] : 0.0);
+      val = (b & 1) == 0 ? dv : -dv;
+    } else if (kind == K_INUB) val = v[uidx(D, a, k, b)];
+    else if (kind == K_INLB) val = -v[uidx(D, a, k, b)];
+    else if (kind == K_STUB) val = E.tmpS[(a * D.N + (k - 1)) * 3 + 2];
+    else val = -E.tmpS[(a * D.N + (k - 1)) * 3 + 2];
+    y[r] = val;
+  }
+  c.sync();
+}
+
+// per (a,k>=1) coefficients of the state rows in  G' w:  cf = [c_x, c_y, c_ey]
+DG_DEV void game_state_coefs(Cta& c, const Dims& D, const EvalBuf& E, const double* w, double* cf) {
+  DG_FOR(t, D.M * D.N) {
+    int a = t / D.N, k = t - a * D.N + 1;
+    double cx = 0.0, cy = 0.0;
+    for (int p = 0; p < D.P; ++p) {
+      int i, j;
+      pair_ij(D.M, p, i, j);
+      if (i != a && j != a) continue;
+      double dx = E.x[k * D.nq + i * DG_NQA] - E.x[k * D.nq + j * DG_NQA];
+      double dy = E.x[k * D.nq + i * DG_NQA + 1] - E.x[k * D.nq + j * DG_NQA + 1];
+      double wl = w[row_coll(D, k, p)] * (i == a ? -2.0 : 2.0);
+      cx += wl * dx; cy += wl * dy;
+    }
+    cf[t * 3] = cx; cf[t * 3 + 1] = cy;
+    cf[t * 3 + 2] = w[row_stub(D, k, a)] - w[row_stlb(D, k, a)];
+  }
+}
+
+// input-dependent (sparse) rows of G' w at input (a,k,cc)
+DG_DEV double game_GT_direct(const Dims& D, const double* w, int a, int k, int cc) {
+  double v = w[row_rate(D, k, a, 2 * cc)] - w[row_rate(D, k, a, 2 * cc + 1)];
+  if (k + 1 < D.N) v -= w[row_rate(D, k + 1, a, 2 * cc)] - w[row_rate(D, k + 1, a, 2 * cc + 1)];
+  v += w[row_inub(D, k, a, cc)] - w[row_inlb(D, k, a, cc)];
+  return v;
+}
+
+// y = G' w  (w in R^m, y in R^n)
+DG_DEVN void game_GT_times(Cta& c, const Dims& D, const EvalBuf& E, const double* w, double* y) {
+  c.sync();
+  game_state_coefs(c, D, E, w, E.cf);
+  c.sync();
+  DG_FOR(t, D.n) {
+    int a = t / D.twoN, j = t - a * D.twoN, kj = j >> 1, cc = j & 1;
+    double acc = game_GT_direct(D, w, a, kj, cc);
+    for (int k = kj + 1; k <= D.N; ++k) {
+      const double* Sk = E.S + ((a * D.N + (k - 1)) * 3) * D.twoN + j;
+      const double* cf = E.cf + (a * D.N + (k - 1)) * 3;
+      acc += cf[0] * Sk[0] + cf[1] * Sk[D.twoN] + cf[2] * Sk[2 * D.twoN];
+    }
+    y[t] = acc;
+  }
+  c.sync();
+}
+
+// dense row r of G into out[n] (all threads cooperate)
+DG_DEVN void game_G_row(Cta& c, const Dims& D, const EvalBuf& E, int r, double* out) {
+  int k, kind, a, b;
+  decode_row(D, r, k, kind, a, b);
+  DG_FOR(t, D.n) {
+    int ta = t / D.twoN, j = t - ta * D.twoN, kj = j >> 1, cc = j & 1;
+    double val = 0.0;
+    if (kind == K_COLL) {
+      if ((ta == a || ta == b) && kj < k) {
+        double dx = E.x[k * D.nq + a * DG_NQA] - E.x[k * D.nq + b * DG_NQA];
+        double dy = E.x[k * D.nq + a * DG_NQA + 1] - E.x[k * D.nq + b * DG_NQA + 1];
+        const double* Sk = E.S + ((ta * D.N + (k - 1)) * 3) * D.twoN + j;
+        double sg = ta == a ? -2.0 : 2.0;
+        val = sg * (dx * Sk[0] + dy * Sk[D.twoN]);
+      }
+    } else if (kind == K_RATE) {
+      if (ta == a && cc == (b >> 1)) {
+        double sg = (b & 1) == 0 ? 1.0 : -1.0;
+        if (kj == k) val = sg;
+        else if (kj == k - 1) val = -sg;
+      }
+    } else if (kind == K_INUB) { if (ta == a && kj == k && cc == b) val = 1.0; }
+    else if (kind == K_INLB) { if (ta == a && kj == k && cc == b) val = -1.0; }
+    else {
+      if (ta == a && kj < k) {
+        double sv = E.S[((ta * D.N + (k - 1)) * 3 + 2) * D.twoN + j];
+        val = kind == K_STUB ? sv : -sv;
+      }
+    }
+    out[t] = val;
+  }
+  c.sync();
+}
+
+// terminal-cost gradient entries of agent f wrt joint x_N:  -c_prog*s_f + sum_b c_comp*atan(s_b - s_f)
+DG_DEV double term_grad(const GameDesc& G, const Dims& D, const double* xN, int f, int idx) {
+  int blk = idx / DG_NQA, comp = idx - blk * DG_NQA;
+  if (comp != 4) return 0.0;
+  double sf = xN[f * DG_NQA + 4];
+  if (blk == f) {
+    double v = -G.c_prog;
+    for (int b = 0; b < D.M; ++b) if (b != f) { double dd = xN[b * DG_NQA + 4] - sf; v -= G.c_comp / (1.0 + dd * dd); }
+    return v;
+  }
+  double dd = xN[blk * DG_NQA + 4] - sf;
+  return G.c_comp / (1.0 + dd * dd);
+}
+
+DG_DEV double term_hess(const GameDesc& G, const Dims& D, const double* xN, int f, int i1, int i2) {
+  int b1 = i1 / DG_NQA, c1 = i1 - b1 * DG_NQA, b2 = i2 / DG_NQA, c2 = i2 - b2 * DG_NQA;
+  if (c1 != 4 || c2 != 4) return 0.0;
+  double sf = xN[f * DG_NQA + 4];
+  double v = 0.0;
+  for (int b = 0; b < D.M; ++b) {
+    if (b == f) continue;
+    double dd = xN[b * DG_NQA + 4] - sf;
+    double d2 = -2.0 * G.c_comp * dd / ((1.0 + dd * dd) * (1.0 + dd * dd));
+    // contributes +d2 at (b,b),(f,f), -d2 at (f,b),(b,f)
+    if (b1 == b && b2 == b) v += d2;
+    if (b1 == f && b2 == f) v += d2;
+    if ((b1 == f && b2 == b) || (b1 == b && b2 == f)) v -= d2;
+  }
+  return v;
+}
+
+// d(l'C)/dx_k entry idx (state-dependent rows), k>=1
+DG_DEV double con_lx(const Dims& D, const double* x, const double* l, int k, int idx) {
+  int a = idx / DG_NQA, comp = idx - a * DG_NQA;
+  if (comp == 5) return l[row_stub(D, k, a)] - l[row_stlb(D, k, a)];
+  if (comp > 1) return 0.0;
+  double v = 0.0;
+  for (int p = 0; p < D.P; ++p) {
+    int i, j;
+    pair_ij(D.M, p, i, j);
+    if (i != a && j != a) continue;
+    double dd = x[k * D.nq + i * DG_NQA + comp] - x[k * D.nq + j * DG_NQA + comp];
+    v += l[row_coll(D, k, p)] * (i == a ? -2.0 : 2.0) * dd;
+  }
+  return v;
+}
+
+// d2(l'C)/dx_k^2 entry (collision rows only), k>=1
+DG_DEV double con_lxx(const Dims& D, const double* l, int k, int i1, int i2) {
+  int a1 = i1 / DG_NQA, c1 = i1 - a1 * DG_NQA, a2 = i2 / DG_NQA, c2 = i2 - a2 * DG_NQA;
+  if (c1 > 1 || c1 != c2) return 0.0;
+  double v = 0.0;
+  for (int p = 0; p < D.P; ++p) {
+    int i, j;
+    pair_ij(D.M, p, i, j);
+    double lp = l[row_coll(D, k, p)];
+    if (a1 == a2) { if (a1 == i || a1 == j) v += -2.0 * lp; }
+    else if ((a1 == i && a2 == j) || (a1 == j && a2 == i)) v += 2.0 * lp;
+  }
+  return v;
+}
+
+// Costate chains  p_k = l_x,k + A_k' p_{k+1}:  thread per (function f, agent block b).
+// f < M: cost of agent f (state cost only at the terminal stage); f == M: l'C.
+DG_DEVN void game_costates(Cta& c, const GameDesc& G, const Dims& D, const EvalBuf& E, const double* l) {
+  DG_FOR(t, (D.M + 1) * D.M) {
+    int f = t / D.M, b = t - f * D.M;
+    double p[DG_NQA];
+    double* out = E.cst + f * (D.N + 1) * D.nq;
+    const double* xN = E.x + D.N * D.nq;
+    for (int i = 0; i < DG_NQA; ++i) {
+      p[i] = f < D.M ? term_grad(G, D, xN, f, b * DG_NQA + i) : con_lx(D, E.x, l, D.N, b * DG_NQA + i);
+      out[D.N * D.nq + b * DG_NQA + i] = p[i];
+    }
+    for (int k = D.N - 1; k >= 0; --k) {
+      const double* Ak = E.AB + (k * D.M + b) * 48;
+      double pn[DG_NQA];
+      for (int j = 0; j < DG_NQA; ++j) {
+        double acc = (f == D.M && k >= 1) ? con_lx(D, E.x, l, k, b * DG_NQA + j) : 0.0;
+        for (int i = 0; i < DG_NQA; ++i) acc += Ak[i * 8 + j] * p[i];
+        pn[j] = acc;
+      }
+      for (int i = 0; i < DG_NQA; ++i) { p[i] = pn[i]; out[k * D.nq + b * DG_NQA + i] = pn[i]; }
+    }
+  }
+}
+
+// q (cost gradient, f_q) and G'l from the costates: thread per input (a,k,cc)
+DG_DEVN void game_gradients(Cta& c, const GameDesc& G, const Dims& D, const EvalBuf& E, const double* u,
+                            const double* up, const double* l) {
+  DG_FOR(t, D.n) {
+    int a = t / D.twoN, j = t - a * D.twoN, k = j >> 1, cc = j & 1;
+    const double* Bk = E.AB + (k * D.M + a) * 48;
+    const double* pJ = E.cst + a * (D.N + 1) * D.nq + (k + 1) * D.nq + a * DG_NQA;
+    const double* pC = E.cst + D.M * (D.N + 1) * D.nq + (k + 1) * D.nq + a * DG_NQA;
+    double bj = 0.0, bc = 0.0;
+    for (int i = 0; i < DG_NQA; ++i) { bj += Bk[i * 8 + 6 + cc] * pJ[i]; bc += Bk[i * 8 + 6 + cc] * pC[i]; }
+    double uk = u[t];
+    double um = k == 0 ? up[a * DG_NUA + cc] : u[t - 2];
+    double val = G.w_u[cc] * uk + G.w_du[cc] * (uk - um);
+    if (k + 1 < D.N) val -= G.w_du[cc] * (u[t + 2] - uk);
+    E.q[t] = val + bj;
+    E.gtl[t] = game_GT_direct(D, l, a, k, cc) + bc;
+  }
+}
+
+// Hc[f][k][a][0..14] = sum_i p^f_{k+1}[a,i] * T2[k][a][i][:]
+DG_DEVN void game_contract(Cta& c, const Dims& D, const EvalBuf& E) {
+  DG_FOR(t, (D.M + 1) * D.N * D.M * 15) {
+    int e = t % 15, r = t / 15;
+    int a = r % D.M; r /= D.M;
+    int k = r % D.N, f = r / D.N;
+    const double* p = E.cst + f * (D.N + 1) * D.nq + (k + 1) * D.nq + a * DG_NQA;
+    const double* T = E.T2 + (k * D.M + a) * 90;
+    double acc = 0.0;
+    for (int i = 0; i < DG_NQA; ++i) acc += p[i] * T[i * 15 + e];
+    E.Hc[t] = acc;
+  }
+}
+
+DG_DEV int tri5(int r, int cc) { return r * 5 - (r * (r - 1)) / 2 + (cc - r); }
+
+// second-derivative contraction entries:  state indices 2..5 <-> act 0..3, delta <-> act 4
+DG_DEV double hc_xx(const double* hc, int i, int j) {
+  if (i < 2 || j < 2) return 0.0;
+  int r = i - 2, cc = j - 2;
+  return r <= cc ? hc[tri5(r, cc)] : hc[tri5(cc, r)];
+}
+DG_DEV double hc_ux(const double* hc, int cu, int j) { return (cu == 1 && j >= 2) ? hc[tri5(j - 2, 4)] : 0.0; }
+DG_DEV double hc_uu(const double* hc, int c1, int c2) { return (c1 == 1 && c2 == 1) ? hc[14] : 0.0; }
+
+// Game Hessian Q (f_Q): backward DP per function (M costs, then l'C), rows = threads.
+//   row block a of Q = grad_{u^a} grad_u (J^a + l'C)       (DGSQP.py:920-934)
+DG_DEVN void game_hessian(Cta& c, const GameDesc& G, const Dims& D, const EvalBuf& E, const double* l) {
+  const int n = D.n, nq = D.nq, N = D.N, M = D.M;
+  DG_FOR(t, n * n) E.Q[t] = 0.0;
+  c.sync();
+  for (int f = 0; f <= M; ++f) {
+    const double* cst = E.cst + f * (N + 1) * nq;
+    const double* xN = E.x + N * nq;
+    // V_N
+    double* Vcur = E.Vbuf;
+    double* Vnext = E.Vbuf + nq * nq;
+    DG_FOR(t, nq * nq) {
+      int i1 = t / nq, i2 = t - i1 * nq;
+      Vcur[t] = f < M ? term_hess(G, D, xN, f, i1, i2) : con_lxx(D, l, N, i1, i2);
+    }
+    c.sync();
+    // rows handled by this thread: r = stage-major (k_r, a_r, c_r); its running row of Dxu_Q lives in
+    // E.Wrow[r] and is only ever touched by the owning thread.
+    for (int k = N - 1; k >= 0; --k) {
+      for (int r = c.tid; r < n; r += c.nt) {
+        int kr = r / D.nu, ar = (r - kr * D.nu) >> 1, cr = r & 1;
+        int rowQ = uidx(D, ar, kr, cr);
+        double* wr = E.Wrow + r * nq;
+        if (kr > k) {
+          // existing row: Duu(row r, cols of stage k) = w . B_k ; then w <- w A_k
+          for (int b = 0; b < M; ++b) {
+            const double* ABk = E.AB + (k * M + b) * 48;
+            for (int cc = 0; cc < 2; ++cc) {
+              double val = 0.0;
+              for (int i = 0; i < DG_NQA; ++i) val += wr[b * DG_NQA + i] * ABk[i * 8 + 6 + cc];
+              if (f < M && kr == k + 1 && b == ar && ar == f && cc == cr) val -= G.w_du[cc];
+              int colQ = uidx(D, b, k, cc);
+              if (f == M) { E.Q[rowQ * n + colQ] += val; E.Q[colQ * n + rowQ] += val; }
+              else {
+                if (ar == f) E.Q[rowQ * n + colQ] += val;
+                if (b == f) E.Q[colQ * n + rowQ] += val;
+              }
+            }
+            double tn[DG_NQA];
+            for (int j = 0; j < DG_NQA; ++j) {
+              double acc = 0.0;
+              for (int i = 0; i < DG_NQA; ++i) acc += wr[b * DG_NQA + i] * ABk[i * 8 + j];
+              tn[j] = acc;
+            }
+            for (int j = 0; j < DG_NQA; ++j) wr[b * DG_NQA + j] = tn[j];
+          }
+        } else if (kr == k) {
+          // new row (k, ar, cr):  t = B[:, (ar,cr)]' V[ar-block rows, :]
+          const double* ABa = E.AB + (k * M + ar) * 48;
+          const double* hc = E.Hc + ((f * N + k) * M + ar) * 15;
+          double tv[DG_MAX_NQ];
+          for (int j = 0; j < nq; ++j) {
+            double acc = 0.0;
+            for (int i = 0; i < DG_NQA; ++i) acc += ABa[i * 8 + 6 + cr] * Vcur[(ar * DG_NQA + i) * nq + j];
+            tv[j] = acc;
+          }
+          // same-stage block A1 = luu + B'VB + F.p
+          for (int b = 0; b < M; ++b) {
+            const double* ABb = E.AB + (k * M + b) * 48;
+            for (int cc = 0; cc < 2; ++cc) {
+              double val = 0.0;
+              for (int i = 0; i < DG_NQA; ++i) val += tv[b * DG_NQA + i] * ABb[i * 8 + 6 + cc];
+              if (b == ar) {
+                val += hc_uu(hc, cr, cc);
+                if (f < M && ar == f && cc == cr) val += G.w_u[cc] + G.w_du[cc] + (k + 1 < N ? G.w_du[cc] : 0.0);
+              }
+              if (f == M || ar == f) E.Q[rowQ * n + uidx(D, b, k, cc)] += val;
+            }
+          }
+          // w = t A_k + (G.p)[(ar,cr), ar-block]
+          for (int b = 0; b < M; ++b) {
+            const double* ABb = E.AB + (k * M + b) * 48;
+            for (int j = 0; j < DG_NQA; ++j) {
+              double acc = b == ar ? hc_ux(hc, cr, j) : 0.0;
+              for (int i = 0; i < DG_NQA; ++i) acc += tv[b * DG_NQA + i] * ABb[i * 8 + j];
+              wr[b * DG_NQA + j] = acc;
+            }
+          }
+        }
+      }
+      // V_k = lxx_k + A'VA + E.p   (into the other buffer)
+      DG_FOR(t, nq * nq) {
+        int i1 = t / nq, i2 = t - i1 * nq, b1 = i1 / DG_NQA, b2 = i2 / DG_NQA, c1 = i1 - b1 * DG_NQA, c2 = i2 - b2 * DG_NQA;
+        const double* A1 = E.AB + (k * M + b1) * 48;
+        const double* A2 = E.AB + (k * M + b2) * 48;
+        double acc = (f == M && k >= 1) ? con_lxx(D, l, k, i1, i2) : 0.0;
+        if (b1 == b2) acc += hc_xx(E.Hc + ((f * N + k) * M + b1) * 15, c1, c2);
+        for (int i = 0; i < DG_NQA; ++i) {
+          double rowacc = 0.0;
+          for (int j = 0; j < DG_NQA; ++j) rowacc += Vcur[(b1 * DG_NQA + i) * nq + b2 * DG_NQA + j] * A2[j * 8 + c2];
+          acc += A1[i * 8 + c1] * rowacc;
+        }
+        Vnext[t] = acc;
+      }
+      c.sync();
+      double* tmp = Vcur; Vcur = Vnext; Vnext = tmp;
+    }
+    c.sync();
+  }
+}

@@ -1,0 +1,365 @@
+// DG-SQP v1 outer loop for ONE game instance, executed by one CTA.
+//
+// Restates DGSQP.solve (DGSQP/solvers/DGSQP.py:302-507) with its helpers _get_mu (:559-585), the
+// merit functions f_phi / f_dphi / f_dstat_norm (:962-979), _line_search_3 (:1057-1081) and
+// _watchdog_line_search_4 (:1174-1288).  Everything -- rollout, KKT assembly, eigen-projection,
+// QP, merit, step acceptance, convergence tests -- runs on device; the host only launches.
+#pragma once
+#include "racing_game.cuh"
+#include "linalg.cuh"
+#include "qp_gi.cuh"
+#include "lsqr.cuh"
+
+enum { ST_CONV_ABS = 0, ST_CONV_REL = 1, ST_MAX_IT = 2, ST_DIVERGED = 3, ST_QP_FAIL = 4, ST_TIME_LIMIT = 5 };
+
+struct SolverParams {
+  double reg, p_tol, d_tol, beta, tau, eig_floor, merit_max, diverge_tol;
+  double mu_vio_thresh;    // _get_mu's `thresh` (DGSQP.py:560); see DESIGN.md deviation D2
+  double dbg_l0_perturb;   // test hook (sensitivity studies): relative perturbation of the dual initialisation; 0 in production
+  int line_search_iters, sqp_iters, nonmono_ls, merit_l1, conv_approx, rel_tol_req, t_hat;
+};
+
+struct SqpBuf {
+  double *u, *l, *u_im1, *l_im1;
+  double *du, *dl, *s, *ds;          // step of the outer iteration (kept for the watchdog fallback)
+  double *u_t, *l_t, *du_t, *dl_t, *s_t, *ds_t;
+  double *u_c, *l_c;                 // candidate point
+  double *Gdu, *tn, *tn2;
+  double *Hm;
+  double *up;                        // nu (zeros: v1 resets u_prev every solve, DGSQP.py:305)
+};
+
+struct Workspace { EvalBuf E; LinBuf B; QpBuf Q; LsqrBuf L; SqpBuf S; };
+
+// Carve one CTA's workspace out of a flat double array; returns the number of doubles used.
+// Called with base == nullptr to measure.
+DG_HD size_t carve_workspace(const Dims& D, double* base, Workspace& W) {
+  size_t off = 0;
+  const size_t n = D.n, m = D.m, nq = D.nq, N = D.N, M = D.M;
+#define CARVE(ptr, cnt) do { (ptr) = base ? base + off : nullptr; off += (((size_t)(cnt)) + 1) & ~(size_t)1; } while (0)
+  CARVE(W.E.x, (N + 1) * nq); CARVE(W.E.AB, N * M * 48); CARVE(W.E.T2, N * M * 90);
+  CARVE(W.E.S, M * N * 3 * 2 * N); CARVE(W.E.g, m); CARVE(W.E.q, n); CARVE(W.E.gtl, n);
+  CARVE(W.E.cst, (M + 1) * (N + 1) * nq); CARVE(W.E.Hc, (M + 1) * N * M * 15); CARVE(W.E.Vbuf, 2 * nq * nq);
+  CARVE(W.E.Q, n * n); CARVE(W.E.Wrow, n * nq); CARVE(W.E.tmpS, M * N * 3); CARVE(W.E.cf, M * N * 3);
+  CARVE(W.B.W, n * n); CARVE(W.B.dg, n); CARVE(W.B.od, n); CARVE(W.B.tau, n); CARVE(W.B.pv, n); CARVE(W.B.wv, n);
+  CARVE(W.B.lam, n); CARVE(W.B.Z, DG_EIG_CHUNK * n); CARVE(W.B.itw, DG_EIG_CHUNK * 5 * n);
+  W.Q.Jm = W.B.W;                       // the tridiagonalisation workspace is free once H is formed
+  CARVE(W.Q.Rm, n * n); CARVE(W.Q.xq, n); CARVE(W.Q.dv, n); CARVE(W.Q.zv, n); CARVE(W.Q.rv, n); CARVE(W.Q.npv, n);
+  CARVE(W.Q.hv, n); CARVE(W.Q.wv, n); CARVE(W.Q.lam_act, n); CARVE(W.Q.sl, m); CARVE(W.Q.lam, m);
+  { double* t; CARVE(t, (n + 1) / 2 + 1); W.Q.act = (int*)t; CARVE(t, (m + 1) / 2 + 1); W.Q.is_act = (int*)t; }
+  CARVE(W.L.u, m); CARVE(W.L.v, m); CARVE(W.L.w, m); CARVE(W.L.x, m); CARVE(W.L.tn, n); CARVE(W.L.tm, m);
+  CARVE(W.S.u, n); CARVE(W.S.l, m); CARVE(W.S.u_im1, n); CARVE(W.S.l_im1, m);
+  CARVE(W.S.du, n); CARVE(W.S.dl, m); CARVE(W.S.s, m); CARVE(W.S.ds, m);
+  CARVE(W.S.u_t, n); CARVE(W.S.l_t, m); CARVE(W.S.du_t, n); CARVE(W.S.dl_t, m); CARVE(W.S.s_t, m); CARVE(W.S.ds_t, m);
+  CARVE(W.S.u_c, n); CARVE(W.S.l_c, m); CARVE(W.S.Gdu, m); CARVE(W.S.tn, n); CARVE(W.S.tn2, n);
+  CARVE(W.S.Hm, n * n); CARVE(W.S.up, D.nu);
+#undef CARVE
+  return off;
+}
+
+struct SolveCtx {
+  const GameDesc* G;
+  const SolverParams* P;
+  Dims D;
+  Workspace W;
+  const double* x0;
+  // counters (uniform across threads)
+  int n_evals_full, n_evals_grad, n_gi_iters, n_neg_max;
+};
+
+// _evaluate(u, l, hessian=True)
+DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l) {
+  const Dims& D = X.D; const EvalBuf& E = X.W.E;
+  c.sync();
+  game_rollout(c, *X.G, D, u, X.x0, E.x);
+  c.sync();
+  game_linearize(c, *X.G, D, u, E, true);
+  c.sync();
+  game_constraints(c, *X.G, D, u, X.W.S.up, E.x, E.g);
+  game_costates(c, *X.G, D, E, l);
+  game_sens(c, D, E);
+  c.sync();
+  game_contract(c, D, E);
+  game_gradients(c, *X.G, D, E, u, X.W.S.up, l);
+  c.sync();
+  game_hessian(c, *X.G, D, E, l);
+  ++X.n_evals_full;
+}
+
+// _evaluate(u, l, hessian=False): x, g, q, G'l only (sensitivities optional)
+DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l, bool with_sens) {
+  const Dims& D = X.D; const EvalBuf& E = X.W.E;
+  c.sync();
+  game_rollout(c, *X.G, D, u, X.x0, E.x);
+  c.sync();
+  game_linearize(c, *X.G, D, u, E, false);
+  c.sync();
+  game_constraints(c, *X.G, D, u, X.W.S.up, E.x, E.g);
+  game_costates(c, *X.G, D, E, l);
+  if (with_sens) game_sens(c, D, E);
+  c.sync();
+  game_gradients(c, *X.G, D, E, u, X.W.S.up, l);
+  c.sync();
+  ++X.n_evals_grad;
+}
+
+// phi at the currently evaluated point:  1/2 |q+G'l|^2 + 1/2 (l.g)^2 + mu * sum(g - (s + alpha*ds))
+DG_DEV double merit_here(Cta& c, SolveCtx& X, const double* l, const double* s, const double* ds, double alpha,
+                         double mu) {
+  const Dims& D = X.D; const EvalBuf& E = X.W.E;
+  double p1 = 0.0, p2 = 0.0, p3 = 0.0;
+  DG_FOR(i, D.n) { double d = E.q[i] + E.gtl[i]; p1 += d * d; }
+  DG_FOR(r, D.m) { p2 += l[r] * E.g[r]; p3 += E.g[r] - (s[r] + (ds ? alpha * ds[r] : 0.0)); }
+  double dd = c.sum(p1), lg = c.sum(p2), vio = c.sum(p3);
+  double val = 0.5 * (dd + lg * lg);
+  if (X.P->merit_l1) val += mu * vio;
+  return val;
+}
+
+// After a QP at the currently (fully) evaluated point (u_b, l_b): fills dl, s, ds, Gdu and returns
+// phi, dphi (and mu when compute_mu) -- f_phi / f_dphi / _get_mu.
+DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du, const double* l_hat,
+                        double* dl, double* s, double* ds, bool compute_mu, double& mu, double& phi, double& dphi) {
+  const Dims& D = X.D; const EvalBuf& E = X.W.E; SqpBuf& S = X.W.S;
+  const int n = D.n, m = D.m;
+  game_G_times(c, D, E, du, S.Gdu);
+  DG_FOR(r, m) {
+    dl[r] = l_hat[r] - l_b[r];
+    double sv = E.g[r] < 0.0 ? E.g[r] : 0.0;
+    s[r] = sv;
+    ds[r] = E.g[r] + S.Gdu[r] - sv;
+  }
+  c.sync();
+  game_GT_times(c, D, E, dl, S.tn2);
+  // tn = Q du (raw, unsymmetrised Q -- DGSQP.py:416 passes Q_i)
+  DG_FOR(i, n) {
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) acc += E.Q[i * n + j] * du[j];
+    S.tn[i] = acc;
+  }
+  double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0, p5 = 0.0, p6 = 0.0;
+  DG_FOR(i, n) { double d = E.q[i] + E.gtl[i]; p1 += d * d; p2 += d * (S.tn[i] + S.tn2[i]); }
+  DG_FOR(r, m) {
+    p3 += l_b[r] * E.g[r]; p4 += l_b[r] * S.Gdu[r]; p5 += dl[r] * E.g[r]; p6 += E.g[r] - s[r];
+  }
+  double dd = c.sum(p1), dQ = c.sum(p2), lg = c.sum(p3), lGdu = c.sum(p4), dlg = c.sum(p5), vio = c.sum(p6);
+  double dstat = dQ + lg * (lGdu + dlg);
+  if (compute_mu) {
+    mu = 0.0;
+    if (X.P->merit_l1 && vio > X.P->mu_vio_thresh) mu = fabs(dstat) / ((1.0 - 0.5) * vio);
+  }
+  phi = 0.5 * (dd + lg * lg);
+  dphi = dstat;
+  if (X.P->merit_l1) { phi += mu * vio; dphi -= mu * vio; }
+}
+
+// _solve_qp at the currently evaluated point.  Result in W.Q.xq / W.Q.lam.  Returns 0 on success.
+DG_DEVN int solve_qp_here(Cta& c, SolveCtx& X) {
+  const Dims& D = X.D;
+  int nneg = nearest_pd(c, D.n, X.W.E.Q, X.W.S.Hm, X.W.B, X.P->eig_floor, X.P->reg, X.P->conv_approx != 0);
+  if (nneg > X.n_neg_max) X.n_neg_max = nneg;
+  int it = 0, na = 0;
+  int st = qp_solve_gi(c, D, X.W.E, X.W.S.Hm, X.W.E.q, X.W.Q, &it, &na);
+  X.n_gi_iters += it;
+  return st;
+}
+
+// _line_search_3: base (u,du,l,dl,s,ds) with phi0/dphi0; result left in (u_c, l_c); returns phi_trial
+DG_DEVN double line_search_3(Cta& c, SolveCtx& X, const double* u, const double* du, const double* l, const double* dl,
+                             const double* s, const double* ds, double phi0, double dphi0, double mu) {
+  const Dims& D = X.D; SqpBuf& S = X.W.S;
+  double alpha = 1.0, phi_t = 0.0;
+  for (int i = 0; i < X.P->line_search_iters; ++i) {
+    c.sync();
+    DG_FOR(j, D.n) S.u_c[j] = u[j] + alpha * du[j];
+    DG_FOR(r, D.m) S.l_c[r] = l[r] + alpha * dl[r];
+    eval_grad(c, X, S.u_c, S.l_c, false);
+    phi_t = merit_here(c, X, S.l_c, s, ds, alpha, mu);
+    if (phi_t <= phi0 + X.P->beta * alpha * dphi0) break;
+    alpha *= X.P->tau;
+  }
+  return phi_t;
+}
+
+DG_DEV void vcopy(Cta& c, int len, double* dst, const double* src) { DG_FOR(i, len) dst[i] = src[i]; }
+
+// _watchdog_line_search_4.  On return the accepted iterate is in (S.u, S.l); returns extra QP count.
+DG_DEVN int watchdog_4(Cta& c, SolveCtx& X, double phi_k, double dphi_k, double mu) {
+  const Dims& D = X.D; SqpBuf& S = X.W.S; const SolverParams& P = *X.P;
+  const int n = D.n, m = D.m;
+  int qp = 0;
+  const double target = phi_k + P.beta * dphi_k;
+  // relaxed (full) step
+  c.sync();
+  DG_FOR(j, n) S.u_c[j] = S.u[j] + S.du[j];
+  DG_FOR(r, m) S.l_c[r] = S.l[r] + S.dl[r];
+  eval_grad(c, X, S.u_c, S.l_c, false);
+  double phi1 = merit_here(c, X, S.l_c, S.s, S.ds, 1.0, mu);
+#ifdef DG_TRACE
+  if (c.tid == 0) printf("      full step phi1 %.12e  (accept %d)\n", phi1, (int)(phi1 <= target));
+#endif
+  if (phi1 <= target) { c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync(); return qp; }
+  bool fail = false;
+  c.sync();
+  vcopy(c, n, S.u_t, S.u_c); vcopy(c, m, S.l_t, S.l_c);
+  for (int t = 0; t < P.t_hat; ++t) {
+    eval_full(c, X, S.u_t, S.l_t);
+    int st = solve_qp_here(c, X);
+    ++qp;
+    if (st != 0) { fail = true; break; }
+    c.sync();
+    vcopy(c, n, S.du_t, X.W.Q.xq);
+    double mu_d = mu, ph, dph;
+    step_merit(c, X, S.l_t, S.du_t, X.W.Q.lam, S.dl_t, S.s_t, S.ds_t, false, mu_d, ph, dph);
+    c.sync();
+    DG_FOR(j, n) S.u_c[j] = S.u_t[j] + S.du_t[j];
+    DG_FOR(r, m) S.l_c[r] = X.W.Q.lam[r];
+    eval_grad(c, X, S.u_c, S.l_c, false);
+    double phi_n = merit_here(c, X, S.l_c, S.s_t, S.ds_t, 1.0, mu);
+    if (phi_n > P.merit_max) break;
+    if (phi_n <= target) { c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync(); return qp; }
+    c.sync();
+    vcopy(c, n, S.u_t, S.u_c); vcopy(c, m, S.l_t, S.l_c);
+  }
+  // insist on merit decrease
+  double phi_n = 0.0;
+  {
+    eval_full(c, X, S.u_t, S.l_t);
+    int st = solve_qp_here(c, X);
+    ++qp;
+    if (st != 0) fail = true;
+    else {
+      c.sync();
+      vcopy(c, n, S.du_t, X.W.Q.xq);
+      double mu_d = mu, ph, dph;
+      step_merit(c, X, S.l_t, S.du_t, X.W.Q.lam, S.dl_t, S.s_t, S.ds_t, false, mu_d, ph, dph);
+      phi_n = line_search_3(c, X, S.u_t, S.du_t, S.l_t, S.dl_t, S.s_t, S.ds_t, ph, dph, mu);
+    }
+  }
+  if (!fail) {
+    if (phi_n <= target) { c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync(); return qp; }
+    else if (phi_n > phi_k) fail = true;
+    else {
+      c.sync();
+      vcopy(c, n, S.u_t, S.u_c); vcopy(c, m, S.l_t, S.l_c);
+      eval_full(c, X, S.u_t, S.l_t);
+      int st = solve_qp_here(c, X);
+      if (st != 0) {
+        line_search_3(c, X, S.u, S.du, S.l, S.dl, S.s, S.ds, phi_k, dphi_k, mu);
+        c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync();
+        return qp;
+      }
+      ++qp;
+      c.sync();
+      vcopy(c, n, S.du_t, X.W.Q.xq);
+      double mu_d = mu, ph, dph;
+      step_merit(c, X, S.l_t, S.du_t, X.W.Q.lam, S.dl_t, S.s_t, S.ds_t, false, mu_d, ph, dph);
+      line_search_3(c, X, S.u_t, S.du_t, S.l_t, S.dl_t, S.s_t, S.ds_t, ph, dph, mu);
+      c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync();
+      return qp;
+    }
+  }
+  // fail: search along the original step
+  line_search_3(c, X, S.u, S.du, S.l, S.dl, S.s, S.ds, phi_k, dphi_k, mu);
+  c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync();
+  return qp;
+}
+
+struct SolveOut {
+  double* u;      // n
+  double* l;      // m
+  double* x;      // (N+1)*nq
+  double* cost;   // M
+  double* cond;   // 3: p_feas, comp, stat
+  int* num_iters; int* status; int* qp_solves;
+  int* diag;      // 4: full evals, grad evals, GI iterations, max #negative eigenvalues  (may be null)
+  double* l_init; // m  (may be null): dual initialisation
+};
+
+// l_ws: optional dual warm start (nullptr = the reference's LSQR initialisation, DGSQP.py:312-326)
+DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double* l_ws, const SolveOut& O) {
+  const Dims& D = X.D; SqpBuf& S = X.W.S; const EvalBuf& E = X.W.E; const SolverParams& P = *X.P;
+  const int n = D.n, m = D.m;
+  X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = 0;
+  DG_FOR(j, n) S.u[j] = u_ws[j];
+  DG_FOR(r, m) S.l[r] = 0.0;
+  DG_FOR(j, D.nu) S.up[j] = 0.0;
+  c.sync();
+  // dual initialisation (DGSQP.py:320-326)
+  if (l_ws) {
+    DG_FOR(r, m) S.l[r] = l_ws[r];
+    c.sync();
+  } else {
+    eval_grad(c, X, S.u, S.l, true);
+    lsqr_dual_init(c, D, E, X.W.L, E.q, S.l);
+  }
+  if (P.dbg_l0_perturb != 0.0) {
+    DG_FOR(r, m) S.l[r] *= 1.0 + P.dbg_l0_perturb * (2.0 * (double)((r * 2654435761u) % 1000u) / 1000.0 - 1.0);
+    c.sync();
+  }
+  if (O.l_init) { DG_FOR(r, m) O.l_init[r] = S.l[r]; }
+  int sqp_it = 0, rel_its = 0, total_qp = 0, status = ST_MAX_IT;
+  double p_feas = 0.0, comp = 0.0, stat = 0.0;
+  while (true) {
+    eval_full(c, X, S.u, S.l);
+    double a1 = -1e300, a2 = 0.0, a3 = 0.0;
+    DG_FOR(r, m) { a1 = fmax(a1, E.g[r]); a2 = fmax(a2, fabs(E.g[r] * S.l[r])); }
+    DG_FOR(j, n) a3 = fmax(a3, fabs(E.q[j] + E.gtl[j]));
+    p_feas = fmax(0.0, c.max(a1)); comp = c.max(a2); stat = c.max(a3);
+    c.sync();
+    vcopy(c, n, S.u_im1, S.u); vcopy(c, m, S.l_im1, S.l);
+    if (stat > P.diverge_tol) { status = ST_DIVERGED; break; }
+    if (p_feas < P.p_tol && comp < P.d_tol && stat < P.d_tol) { status = ST_CONV_ABS; break; }
+    int st = solve_qp_here(c, X);
+    ++total_qp;
+    if (st != 0) { status = ST_QP_FAIL; break; }
+    c.sync();
+    vcopy(c, n, S.du, X.W.Q.xq);
+    double mu = 0.0, phi_k, dphi_k;
+    step_merit(c, X, S.l, S.du, X.W.Q.lam, S.dl, S.s, S.ds, true, mu, phi_k, dphi_k);
+#ifdef DG_TRACE
+    if (c.tid == 0) printf("it %2d pf %.6e comp %.6e stat %.6e | mu %.12e phi_k %.12e dphi_k %.12e target %.12e\n", sqp_it, p_feas, comp, stat, mu, phi_k, dphi_k, phi_k + P.beta * dphi_k);
+#endif
+    if (P.nonmono_ls) total_qp += watchdog_4(c, X, phi_k, dphi_k, mu);
+    else {
+      line_search_3(c, X, S.u, S.du, S.l, S.dl, S.s, S.ds, phi_k, dphi_k, mu);
+      c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync();
+    }
+    double q1 = 0.0, q2 = 0.0;
+    DG_FOR(j, n) { double d = S.u[j] - S.u_im1[j]; q1 += d * d; }
+    DG_FOR(r, m) { double d = S.l[r] - S.l_im1[r]; q2 += d * d; }
+    double nu_ = sqrt(c.sum(q1)), nl_ = sqrt(c.sum(q2));
+    if (nu_ < P.p_tol / 2 && nl_ < P.d_tol / 2) {
+      ++rel_its;
+      if (rel_its >= P.rel_tol_req && p_feas < P.p_tol) { status = ST_CONV_REL; break; }
+    } else rel_its = 0;
+    ++sqp_it;
+    if (sqp_it >= P.sqp_iters) { status = ST_MAX_IT; break; }
+  }
+  // outputs: x_bar = evaluate_dynamics(u), costs f_J  (DGSQP.py:476-498)
+  c.sync();
+  game_rollout(c, *X.G, D, S.u, X.x0, E.x);
+  c.sync();
+  DG_FOR(j, n) O.u[j] = S.u[j];
+  DG_FOR(r, m) O.l[r] = S.l[r];
+  DG_FOR(j, (D.N + 1) * D.nq) O.x[j] = E.x[j];
+  DG_FOR(a, D.M) {
+    double J = 0.0;
+    for (int k = 0; k < D.N; ++k)
+      for (int cc = 0; cc < 2; ++cc) {
+        double uk = S.u[uidx(D, a, k, cc)];
+        double um = k == 0 ? S.up[a * 2 + cc] : S.u[uidx(D, a, k - 1, cc)];
+        J += 0.5 * X.G->w_u[cc] * uk * uk + 0.5 * X.G->w_du[cc] * (uk - um) * (uk - um);
+      }
+    const double* xN = E.x + D.N * D.nq;
+    J += -X.G->c_prog * xN[a * DG_NQA + 4];
+    for (int b = 0; b < D.M; ++b) if (b != a) J += X.G->c_comp * atan(xN[b * DG_NQA + 4] - xN[a * DG_NQA + 4]);
+    O.cost[a] = J;
+  }
+  if (c.tid == 0) {
+    O.cond[0] = p_feas; O.cond[1] = comp; O.cond[2] = stat;
+    *O.num_iters = sqp_it; *O.status = status; *O.qp_solves = total_qp;
+    if (O.diag) { O.diag[0] = X.n_evals_full; O.diag[1] = X.n_evals_grad; O.diag[2] = X.n_gi_iters; O.diag[3] = X.n_neg_max; }
+  }
+  c.sync();
+}

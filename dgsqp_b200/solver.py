@@ -1,0 +1,233 @@
+"""Host-side DG-SQP solver class over the CUDA C-ABI.
+
+Mirrors the surface the reference's Monte-Carlo drivers use on ``DGSQP.solvers.DGSQP.DGSQP``
+(``DGSQP/solvers/DGSQP.py``): ``set_warm_start`` (:271-281), ``solve`` (:302-507), ``step``
+(:283-297), ``get_prediction`` (:299-300) and the attributes ``q_pred``, ``u_pred``, ``l_pred``,
+``n_c``, ``N``, ``M`` -- plus ``solve_batch``, which is the reason this package exists: thousands of
+independent instances in one launch.  All arithmetic happens in ``libdgsqp_b200.so``; this module
+only marshals buffers.  There is no CPU fallback.
+"""
+import array
+import copy
+import ctypes as C
+import time
+from typing import List, Optional
+
+import numpy as np
+
+from . import _abi
+from .games import RacingGame, params_to_struct, NQA, NUA
+from .solver_types import DGSQPParams, DGSQPV2Params
+from .types import VehicleState, VehiclePrediction
+
+
+class BatchResult:
+    """Arrays returned by :meth:`DGSQP.solve_batch` (NumPy for host calls, torch CUDA tensors for
+    device calls).  ``msg`` decodes ``status`` into the reference's strings."""
+
+    def __init__(self, u, l, x, cost, cond, num_iters, status, qp_solves, elapsed):
+        self.u, self.l, self.x, self.cost, self.cond = u, l, x, cost, cond
+        self.num_iters, self.status, self.qp_solves, self.elapsed = num_iters, status, qp_solves, elapsed
+
+    @property
+    def msg(self):
+        st = self.status.cpu().numpy() if hasattr(self.status, "cpu") else self.status
+        return [_abi.STATUS_MSG[int(s)] for s in st]
+
+    @property
+    def converged(self):
+        return self.status <= 1
+
+
+class DGSQP:
+    def __init__(self, game: RacingGame, params: DGSQPParams = None, print_method=print, device: int = 0):
+        if params is None:
+            params = DGSQPParams()
+        if isinstance(params, DGSQPV2Params):
+            raise NotImplementedError("the v2 step policy (DGSQPV2Params) is not implemented yet; use DGSQPParams")
+        if params.N != game.N:
+            raise ValueError("params.N = %i but the game was built for N = %i" % (params.N, game.N))
+        if params.qp_solver != "osqp" or params.qp_interface != "casadi":
+            raise ValueError(f"Unsupported QP interface {params.qp_interface}/{params.qp_solver}")
+        if params.hessian_approximation != "none":
+            raise ValueError(f"Hessian approximation method {params.hessian_approximation} not implmented")
+        self.game, self.params = game, params
+        self.print_method = (lambda s: None) if print_method is None else print_method
+        self.M, self.N = game.M, game.N
+        self.n_u, self.n_q = game.n_u, game.n_q
+        self.n_c = game.n_c
+        self.num_qa_d = [NQA] * self.M
+        self.num_ua_d = [NUA] * self.M
+        self.num_ua_el = [self.N * NUA] * self.M
+        self.solver_name = params.solver_name
+
+        self._lib = _abi.load()
+        gs, ps = game.to_struct(), params_to_struct(params)
+        self._h = C.c_void_p()
+        _abi.check(self._lib.dgsqp_create(C.byref(gs), C.byref(ps), int(device), C.byref(self._h)))
+        dims = (C.c_int32 * 4)()
+        _abi.check(self._lib.dgsqp_dims(self._h, dims))
+        assert (dims[0], dims[1], dims[2], dims[3]) == (game.n_q, game.n_u, game.n, game.m)
+        self.device = device
+
+        self.q_pred = np.zeros((self.N + 1, self.n_q))
+        self.u_pred = np.zeros((self.N, self.n_u))
+        self.l_pred = np.zeros(game.m)
+        self.u_prev = np.zeros(self.n_u)
+        self.u_ws = np.zeros(self.N * self.n_u)
+        self.l_ws = None
+        self.state_input_predictions = [VehiclePrediction() for _ in range(self.M)]
+        self.initialized = True
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.dgsqp_destroy(h)
+            self._h = None
+
+    # ------------------------------------------------------------------ reference surface
+    def initialize(self):
+        pass
+
+    def set_warm_start(self, u_ws: np.ndarray, l_ws: np.ndarray = None):
+        if u_ws.shape[0] != self.N or u_ws.shape[1] != self.n_u:
+            raise RuntimeError('Warm start state sequence of shape (%i,%i) is incompatible with required shape (%i,%i)'
+                               % (u_ws.shape[0], u_ws.shape[1], self.N, self.n_u))
+        self.u_ws = self.stage_to_agent_major(np.asarray(u_ws, dtype=np.float64)[None])[0]
+        self.l_ws = l_ws
+
+    def stage_to_agent_major(self, u_ws):
+        """[B, N, n_u] (agent column blocks) -> [B, n] agent-major (DGSQP.py:275-280)."""
+        B = u_ws.shape[0]
+        return np.ascontiguousarray(u_ws.reshape(B, self.N, self.M, NUA).transpose(0, 2, 1, 3).reshape(B, -1))
+
+    def agent_to_stage_major(self, u):
+        """[B, n] agent-major -> [B, N, n_u] (DGSQP.py:477-482)."""
+        B = u.shape[0]
+        return u.reshape(B, self.M, self.N, NUA).transpose(0, 2, 1, 3).reshape(B, self.N, self.n_u)
+
+    def solve(self, states: List[VehicleState], parameters: np.ndarray = np.array([])):
+        t0 = time.time()
+        self.u_prev = np.zeros(self.n_u)
+        x0 = self.game.state2q(states)
+        res = self.solve_batch(x0[None], self.u_ws[None])
+        msg = res.msg[0]
+        self.q_pred = res.x[0].reshape(self.N + 1, self.n_q)
+        self.u_pred = self.agent_to_stage_major(res.u)[0]
+        self.l_pred = res.l[0]
+        dur = time.time() - t0
+        self.print_method(self.solver_name)
+        self.print_method(f'Solve status: {msg}')
+        self.print_method(f'Solve iters: {int(res.num_iters[0])}')
+        self.print_method(f'Solve time: {dur:.2f}')
+        self.print_method(str(res.cost[0]))
+        cond = dict(p_feas=float(res.cond[0, 0]), comp=float(res.cond[0, 1]), stat=float(res.cond[0, 2]))
+        return dict(time=dur, num_iters=int(res.num_iters[0]), status=bool(res.status[0] <= 1), cost=res.cost[0],
+                    cond=cond, iter_data=[], msg=msg, init=dict(u=self.u_ws.copy(), l=None),
+                    qp_solves=int(res.qp_solves[0]))
+
+    def step(self, states: List[VehicleState], parameters: np.ndarray = np.array([])):
+        info = self.solve(states, parameters)
+        for a, st in enumerate(states):
+            st.u.u_a, st.u.u_steer = float(self.u_pred[0, NUA * a]), float(self.u_pred[0, NUA * a + 1])
+        self._fill_predictions(states[0].t)
+        self.u_prev = self.u_pred[0]
+        if info['msg'] not in ['diverged', 'qp_fail']:
+            self.set_warm_start(np.vstack((self.u_pred[1:], self.u_pred[-1])))
+        return info
+
+    def get_prediction(self) -> List[VehiclePrediction]:
+        return self.state_input_predictions
+
+    def _fill_predictions(self, t):
+        L_f, L_r = self.game.L_f, self.game.L_r
+        for a, pred in enumerate(self.state_input_predictions):
+            q = self.q_pred[:, NQA * a:NQA * (a + 1)]
+            u = self.u_pred[:, NUA * a:NUA * (a + 1)]
+            # qu2prediction (dynamics_models.py:1127-1150) incl. its psidot = v*L_r*sin(...) quirk
+            psidot = q[:-1, 2] * L_r * np.sin(np.arctan(np.tan(u[:, 1]) * L_f / (L_f + L_r)))
+            psidot = np.append(psidot, psidot[-1])
+            for name, col in (("x", 0), ("y", 1), ("v_long", 2), ("e_psi", 3), ("s", 4), ("x_tran", 5)):
+                setattr(pred, name, array.array('d', q[:, col]))
+            pred.psidot = array.array('d', psidot)
+            pred.v_tran = array.array('d', psidot * L_r)
+            pred.u_a = array.array('d', u[:, 0])
+            pred.u_steer = array.array('d', u[:, 1])
+            pred.t = t
+
+    # ------------------------------------------------------------------ batched entry point
+    def solve_batch(self, x0, u_ws, l_ws=None, stream: Optional[int] = None) -> BatchResult:
+        """Solve B instances.  ``x0`` [B, n_q], ``u_ws`` [B, n] agent-major.
+
+        NumPy inputs take the host path (H2D / D2H copies inside the library call); torch CUDA
+        tensors take the device path (no copies, outputs are torch tensors on the same device)."""
+        g = self.game
+        is_torch = hasattr(x0, "is_cuda")
+        if is_torch:
+            return self._solve_batch_device(x0, u_ws, l_ws, stream)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        u_ws = np.ascontiguousarray(u_ws, dtype=np.float64)
+        B = x0.shape[0]
+        if x0.shape != (B, g.n_q) or u_ws.shape != (B, g.n):
+            raise RuntimeError('Batch of shape %s / %s is incompatible with required (B,%i) / (B,%i)'
+                               % (x0.shape, u_ws.shape, g.n_q, g.n))
+        if l_ws is not None:
+            l_ws = np.ascontiguousarray(l_ws, dtype=np.float64)
+            if l_ws.shape != (B, g.m):
+                raise RuntimeError('Dual warm start of shape %s is incompatible with required (B,%i)' % (l_ws.shape, g.m))
+        u, l = np.empty((B, g.n)), np.empty((B, g.m))
+        x = np.empty((B, (g.N + 1) * g.n_q))
+        cost, cond = np.empty((B, g.M)), np.empty((B, 3))
+        it, st, qp = (np.empty(B, dtype=np.int32) for _ in range(3))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        t0 = time.perf_counter()
+        _abi.check(self._lib.dgsqp_solve_batch(self._h, B, p(x0), p(u_ws), p(l_ws) if l_ws is not None else None,
+                                               p(u), p(l), p(x), p(cost), p(cond), p(it), p(st), p(qp), 0,
+                                               C.c_void_p(stream or 0)))
+        return BatchResult(u, l, x, cost, cond, it, st, qp, time.perf_counter() - t0)
+
+    def _solve_batch_device(self, x0, u_ws, l_ws=None, stream=None, out=None, sync=True):
+        import torch
+        g = self.game
+        B = x0.shape[0]
+        if tuple(x0.shape) != (B, g.n_q) or tuple(u_ws.shape) != (B, g.n):
+            raise RuntimeError('Batch of shape %s / %s is incompatible with required (B,%i) / (B,%i)'
+                               % (tuple(x0.shape), tuple(u_ws.shape), g.n_q, g.n))
+        if not (x0.is_cuda and u_ws.is_cuda and x0.dtype == torch.float64 and u_ws.dtype == torch.float64):
+            raise RuntimeError("device path needs float64 CUDA tensors")
+        x0, u_ws = x0.contiguous(), u_ws.contiguous()
+        dev = x0.device
+        if out is None:
+            out = self.alloc_outputs(B, dev)
+        u, l, x, cost, cond, it, st, qp = out
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        v = lambda t: C.c_void_p(t.data_ptr())
+        lw = v(l_ws.contiguous()) if l_ws is not None else None
+        t0 = time.perf_counter()
+        if sync:
+            _abi.check(self._lib.dgsqp_solve_batch(self._h, B, v(x0), v(u_ws), lw, v(u), v(l), v(x), v(cost), v(cond),
+                                                   v(it), v(st), v(qp), 1, C.c_void_p(stream)))
+        else:
+            _abi.check(self._lib.dgsqp_solve_batch_async(self._h, B, v(x0), v(u_ws), lw, v(u), v(l), v(x), v(cost),
+                                                         v(cond), v(it), v(st), v(qp), C.c_void_p(stream)))
+        return BatchResult(u, l, x, cost, cond, it, st, qp, time.perf_counter() - t0)
+
+    def alloc_outputs(self, B, dev):
+        import torch
+        g = self.game
+        f = dict(dtype=torch.float64, device=dev)
+        i = dict(dtype=torch.int32, device=dev)
+        return (torch.empty((B, g.n), **f), torch.empty((B, g.m), **f), torch.empty((B, (g.N + 1) * g.n_q), **f),
+                torch.empty((B, g.M), **f), torch.empty((B, 3), **f), torch.empty(B, **i), torch.empty(B, **i),
+                torch.empty(B, **i))
+
+    def last_diag(self, B):
+        """[B, 4] int32: full evaluations, gradient-only evaluations, QP active-set iterations,
+        max number of negative Hessian eigenvalues -- of the last solve_batch."""
+        d = np.empty((B, 4), dtype=np.int32)
+        _abi.check(self._lib.dgsqp_last_diag(self._h, B, d.ctypes.data_as(C.c_void_p)))
+        return d
+
+    def configure(self, ctas_per_sm=0, threads=0):
+        _abi.check(self._lib.dgsqp_configure(self._h, int(ctas_per_sm), int(threads)))

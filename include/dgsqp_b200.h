@@ -1,0 +1,135 @@
+/* dgsqp_b200 -- C ABI of the batched Dynamic-Game SQP engine for NVIDIA B200 (sm_100a).
+ *
+ * The reference (zhu-edward/DGSQP) is pure Python and has no C ABI of its own; the seam its
+ * Monte-Carlo drivers call is the solver class
+ *     DGSQP(joint_dynamics, costs, agent_constraints, shared_constraints, bounds, params)
+ *     .set_warm_start(u_ws) / .solve(states) / .step(states)        DGSQP/solvers/DGSQP.py:26-34,271-507
+ * one game instance at a time.  This library is the batched replacement of that seam: the Python class
+ * dgsqp_b200.DGSQP binds these entry points with ctypes.  Plain pointers and sizes only.
+ *
+ * Every function returns 0 on success or a negative DGSQP_E* code; dgsqp_last_error() gives the text.
+ * No exceptions cross the ABI.  Buffers are owned by the caller.  A handle may be used from one host
+ * thread at a time; different handles are independent.
+ */
+#ifndef DGSQP_B200_H
+#define DGSQP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGSQP_MAX_AGENTS 4
+#define DGSQP_MAX_TRACK_SEGS 8
+
+enum {
+  DGSQP_OK = 0,
+  DGSQP_EINVAL = -1,      /* bad argument / unsupported game size */
+  DGSQP_ECUDA = -2,       /* CUDA runtime error (no device, launch failure, ...) */
+  DGSQP_ENOMEM = -3
+};
+
+/* Solve status per instance; maps 1:1 onto the reference's msg strings (DGSQP.py:383-474). */
+enum {
+  DGSQP_CONV_ABS_TOL = 0, /* 'conv_abs_tol' */
+  DGSQP_CONV_REL_TOL = 1, /* 'conv_rel_tol' */
+  DGSQP_MAX_IT = 2,       /* 'max_it'       */
+  DGSQP_DIVERGED = 3,     /* 'diverged'     */
+  DGSQP_QP_FAIL = 4,      /* 'qp_fail'      */
+  DGSQP_TIME_LIMIT = 5    /* 'time_limit' (never produced: no wall clock on device) */
+};
+
+/* Racing game of M kinematic bicycles on a constant-curvature-segment track.
+ * Replaces the CasADi objects the reference scripts build and hand to DGSQP.__init__:
+ *   vehicle  CasadiKinematicBicycleCombined            DGSQP/dynamics/dynamics_models.py:997-1079
+ *   track    RadiusArclengthTrack (Chicane/CurveTrack) DGSQP/tracks/radius_arclength_track.py:199-225,361-408
+ *   costs / constraints / bounds                       scripts/DGSQP_ALGAMES_monte_carlo_chicane.py:80-127,222-330
+ *                                                      scripts/DGSQP_monte_carlo_agents.py:64-231               */
+typedef struct {
+  int32_t M;                 /* agents, 2..4 */
+  int32_t N;                 /* horizon */
+  double dt;
+  double L_f, L_r;           /* wheel_dist_front / rear */
+  double c_dr, c_da, c_s;    /* drag, damping, slip coefficients */
+  double mass;
+  double input_weight[2];    /* stage cost 1/2*w*u^2            (u = [u_a, u_steer]) */
+  double rate_weight[2];     /* stage cost 1/2*w*(u_k-u_{k-1})^2 */
+  double comp_weights[2];    /* terminal: -c0*s_i + sum_j c1*atan(s_j - s_i) */
+  double u_ub[2], u_lb[2];   /* input box */
+  double rate_ub[2], rate_lb[2]; /* input-rate limits per second (constraint is dt*rate) */
+  double half_width;         /* |x_tran| <= half_width for k >= 1 */
+  double obs_r[DGSQP_MAX_AGENTS]; /* collision radii: (r_i+r_j)^2 - |p_i-p_j|^2 <= 0, k >= 1 */
+  int32_t track_nseg;
+  double track_seg_len[DGSQP_MAX_TRACK_SEGS];
+  double track_seg_curv[DGSQP_MAX_TRACK_SEGS];  /* signed curvature 1/r (0 = straight) */
+} dgsqp_racing_game;
+
+/* Mirrors DGSQPParams (DGSQP/solvers/solver_types.py:92-127); fields that only steer Python-side
+ * behaviour (verbose, code_gen, debug_plot, ...) stay in the Python dataclass. */
+typedef struct {
+  double reg;
+  double p_tol, d_tol;
+  double beta, tau;
+  int32_t line_search_iters;
+  int32_t sqp_iters;
+  int32_t nonmono_ls;
+  int32_t merit_function;    /* 0 = 'stat_l1', 1 = 'stat' */
+  int32_t conv_approx;
+  /* `thresh` of DGSQP._get_mu (DGSQP.py:560): the l1 penalty weight mu is |d phi|/((1-rho)*viol) when the
+   * summed constraint violation exceeds thresh, else 0.  The reference hard-codes 0, which makes mu jump
+   * between 0 and ~1e18 on rounding noise at active linear constraints; the default here is 1e-10. */
+  double mu_vio_thresh;
+} dgsqp_params;
+
+typedef struct dgsqp_handle dgsqp_handle;
+
+/* Builds the device-side solver for one game (the analogue of DGSQP.__init__/_build_solver,
+ * DGSQP.py:26-230,587-979).  device = CUDA ordinal.  Fails with DGSQP_ECUDA when no GPU is usable:
+ * there is no CPU fallback. */
+int dgsqp_create(const dgsqp_racing_game* game, const dgsqp_params* params, int device, dgsqp_handle** out);
+int dgsqp_destroy(dgsqp_handle* h);
+
+/* dims[0..3] = n_q (joint state), n_u (joint input), n = N*n_u, m = number of constraint rows */
+int dgsqp_dims(const dgsqp_handle* h, int32_t dims[4]);
+
+/* Solves B independent instances (the loop body of the Monte-Carlo drivers,
+ * scripts/DGSQP_ALGAMES_monte_carlo_chicane.py:485-488: set_warm_start + solve).
+ *   x0      [B, n_q]          joint initial state (state2q order)
+ *   u_ws    [B, n]            warm start, agent-major (DGSQP.set_warm_start, DGSQP.py:271-281)
+ *   l_ws    [B, m] or NULL    dual warm start; NULL = the reference's behaviour, l0 = max(0,-lsqr(GG',Gq))
+ *                             (DGSQP.py:312-326; set_warm_start accepts l_ws but v1 never uses it)
+ *   u_out   [B, n]            solution inputs, agent-major
+ *   l_out   [B, m]            multipliers (l_pred)
+ *   x_out   [B, (N+1)*n_q]    state trajectory (q_pred)
+ *   cost_out[B, M]  cond_out[B, 3] = (p_feas, comp, stat)
+ *   num_iters/status/qp_solves [B]
+ * memspace: 0 = host pointers (copies are done inside, on `stream`), 1 = device pointers.
+ * stream: a cudaStream_t (NULL = default stream).  The call returns after the work has completed. */
+int dgsqp_solve_batch(dgsqp_handle* h, int32_t B, const double* x0, const double* u_ws, const double* l_ws,
+                      double* u_out, double* l_out,
+                      double* x_out, double* cost_out, double* cond_out, int32_t* num_iters, int32_t* status,
+                      int32_t* qp_solves, int32_t memspace, void* stream);
+
+/* Same as dgsqp_solve_batch with device pointers but only enqueues (no synchronisation). */
+int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const double* u_ws, const double* l_ws,
+                            double* u_out,
+                            double* l_out, double* x_out, double* cost_out, double* cond_out, int32_t* num_iters,
+                            int32_t* status, int32_t* qp_solves, void* stream);
+
+/* Per-instance diagnostics of the LAST solve_batch on this handle (device->host copy), 4 ints each:
+ * full evaluations, gradient-only evaluations, QP active-set iterations, max #negative eigenvalues. */
+int dgsqp_last_diag(dgsqp_handle* h, int32_t B, int32_t* diag);
+
+/* Number of kernels launched by this library since load (for bench accounting). */
+int64_t dgsqp_kernel_launches(void);
+
+/* Grid configuration: CTAs per SM (0 = default) and threads per CTA (0 = default 128). */
+int dgsqp_configure(dgsqp_handle* h, int32_t ctas_per_sm, int32_t threads);
+
+const char* dgsqp_last_error(void);
+const char* dgsqp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,82 @@
+// Single-thread host build of the device solver source (DG_HOSTSIM).  TEST HARNESS ONLY: lets the
+// CPU test-suite exercise the exact kernel source (arithmetic, control flow, memory bounds under
+// ASan) on machines without a GPU.  It is not part of the product library and nothing in
+// dgsqp_b200/ loads it.
+#define DG_HOSTSIM 1
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../dgsqp_b200/csrc/sqp_v1.cuh"
+#include "../../dgsqp_b200/csrc/host_setup.h"
+
+extern "C" {
+
+struct HsHandle { GameDesc G; SolverParams P; Dims D; std::vector<double> ws; Workspace W; };
+
+void* hs_create(const dgsqp_racing_game* g, const dgsqp_params* p) {
+  HsHandle* h = new HsHandle();
+  if (dg_fill_game(g, &h->G) != 0 || dg_fill_params(p, &h->P) != 0) { delete h; return nullptr; }
+  h->D = make_dims(h->G.M, h->G.N);
+  Workspace tmp;
+  size_t cnt = carve_workspace(h->D, nullptr, tmp);
+  h->ws.assign(cnt, 0.0);
+  carve_workspace(h->D, h->ws.data(), h->W);
+  return h;
+}
+void hs_set_l0_perturb(void* hp, double v) { ((HsHandle*)hp)->P.dbg_l0_perturb = v; }
+void hs_destroy(void* hp) { delete (HsHandle*)hp; }
+void hs_dims(void* hp, int* out) { HsHandle* h = (HsHandle*)hp; out[0] = h->D.nq; out[1] = h->D.nu; out[2] = h->D.n; out[3] = h->D.m; }
+
+// full evaluation at (u, l): returns Q[n*n], q[n], gtl[n], g[m], x
+void hs_evaluate(void* hp, const double* x0, const double* u, const double* l, double* Q, double* q, double* gtl,
+                 double* g, double* x) {
+  HsHandle* h = (HsHandle*)hp; Cta c;
+  SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0;
+  for (int i = 0; i < h->D.nu; ++i) h->W.S.up[i] = 0.0;
+  eval_full(c, X, u, l);
+  memcpy(Q, h->W.E.Q, sizeof(double) * h->D.n * h->D.n);
+  memcpy(q, h->W.E.q, sizeof(double) * h->D.n);
+  memcpy(gtl, h->W.E.gtl, sizeof(double) * h->D.n);
+  memcpy(g, h->W.E.g, sizeof(double) * h->D.m);
+  memcpy(x, h->W.E.x, sizeof(double) * (h->D.N + 1) * h->D.nq);
+}
+// dense G (m x n) at the last evaluated point, via row extraction; plus G v and G' w products
+void hs_G_dense(void* hp, double* Gd) {
+  HsHandle* h = (HsHandle*)hp; Cta c;
+  for (int r = 0; r < h->D.m; ++r) game_G_row(c, h->D, h->W.E, r, Gd + (size_t)r * h->D.n);
+}
+void hs_G_times(void* hp, const double* v, double* y) { HsHandle* h = (HsHandle*)hp; Cta c; game_G_times(c, h->D, h->W.E, v, y); }
+void hs_GT_times(void* hp, const double* w, double* y) { HsHandle* h = (HsHandle*)hp; Cta c; game_GT_times(c, h->D, h->W.E, w, y); }
+
+int hs_nearest_pd(void* hp, const double* Qin, double* Hout) {
+  HsHandle* h = (HsHandle*)hp; Cta c;
+  int nn = nearest_pd(c, h->D.n, Qin, h->W.S.Hm, h->W.B, h->P.eig_floor, h->P.reg, h->P.conv_approx != 0);
+  memcpy(Hout, h->W.S.Hm, sizeof(double) * h->D.n * h->D.n);
+  return nn;
+}
+// QP at the last evaluated point with the given H (n*n, destroyed) and q
+int hs_qp(void* hp, double* H, const double* q, double* du, double* lam, int* iters) {
+  HsHandle* h = (HsHandle*)hp; Cta c;
+  int na = 0;
+  int st = qp_solve_gi(c, h->D, h->W.E, H, q, h->W.Q, iters, &na);
+  memcpy(du, h->W.Q.xq, sizeof(double) * h->D.n);
+  memcpy(lam, h->W.Q.lam, sizeof(double) * h->D.m);
+  return st;
+}
+int hs_lsqr(void* hp, const double* x0, const double* u, double* l_out) {
+  HsHandle* h = (HsHandle*)hp; Cta c;
+  SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0;
+  for (int i = 0; i < h->D.nu; ++i) h->W.S.up[i] = 0.0;
+  std::vector<double> l0(h->D.m, 0.0);
+  eval_grad(c, X, u, l0.data(), true);
+  return lsqr_dual_init(c, h->D, h->W.E, h->W.L, h->W.E.q, l_out);
+}
+void hs_solve(void* hp, const double* x0, const double* u_ws, const double* l_ws, double* u, double* l, double* x, double* cost, double* cond,
+              int* num_iters, int* status, int* qp_solves, int* diag, double* l_init) {
+  HsHandle* h = (HsHandle*)hp; Cta c;
+  SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0;
+  SolveOut O; O.u = u; O.l = l; O.x = x; O.cost = cost; O.cond = cond; O.num_iters = num_iters; O.status = status;
+  O.qp_solves = qp_solves; O.diag = diag; O.l_init = l_init;
+  sqp_solve_v1(c, X, u_ws, l_ws, O);
+}
+}
