@@ -1,0 +1,171 @@
+"""The CUDA kernel source, compiled for the host as a one-thread CTA (tests/hostsim), against the oracle.
+Catches arithmetic / control-flow / indexing errors on machines without a GPU; the multi-thread behaviour
+(synchronisation, reductions) is covered by the -m gpu tests."""
+import json
+import pathlib
+
+import numpy as np
+import pytest
+
+import dgsqp_b200 as dg
+from hostsim_lib import HostSim
+from oracle.dgsqp_v1 import OracleDGSQP, nearest_pd
+from oracle.qp import solve_qp_gi, kkt_residuals
+from oracle.racing_game import RacingGame
+from oracle.track import chicane_track, curve_track
+
+GOLDEN = pathlib.Path(__file__).parent / "golden"
+MSG = {0: "conv_abs_tol", 1: "conv_rel_tol", 2: "max_it", 3: "diverged", 4: "qp_fail"}
+
+
+def _instance(og, seed=0):
+    rng = np.random.default_rng(seed)
+    M = og.M
+    x0 = np.concatenate([[0, 0, 2.2 + 0.3 * a, 0.0, 0.4 + 0.9 * a, 0.5 - 0.5 * a] for a in range(M)])
+    for a in range(M):
+        x0[6 * a], x0[6 * a + 1], _ = og.track.local_to_global((x0[6 * a + 4], x0[6 * a + 5], 0.0))
+    u = rng.normal(size=og.n) * 0.15
+    l = np.abs(rng.normal(size=og.m)) * 0.3 * (rng.random(og.m) < 0.3)
+    return x0, u, l
+
+
+@pytest.mark.parametrize("M,N", [(2, 25), (3, 10), (4, 6)])
+def test_evaluate_and_G_products(M, N, asan=False):
+    tr_o = curve_track(curve_angle=np.pi / 2) if M > 2 else chicane_track()
+    og = RacingGame(tr_o, M=M, N=N, obs_r=0.4)
+    game = dg.agents_game(M=M, N=N) if M > 2 else dg.chicane_game(N=N)
+    hs = HostSim(game, dg.DGSQPParams(N=N, nonmono_ls=True), asan=asan)
+    x0, u, l = _instance(og, seed=M)
+    Q, q, G, g, x = og.evaluate(u, l, x0, np.zeros(og.n_u), True)
+    Q2, q2, gtl2, g2, x2 = hs.evaluate(x0, u, l)
+    sc = max(1.0, np.abs(Q).max())
+    assert np.abs(x - x2).max() < 1e-12 and np.abs(g - g2).max() < 1e-12 and np.abs(q - q2).max() < 1e-11
+    assert np.abs(G.T @ l - gtl2).max() < 1e-11 and np.abs(Q - Q2).max() < 1e-11 * sc
+    assert np.abs(G - hs.G_dense()).max() < 1e-12
+    rng = np.random.default_rng(0)
+    v, w = rng.normal(size=og.n), rng.normal(size=og.m)
+    assert np.abs(G @ v - hs.G_times(v)).max() < 1e-11 and np.abs(G.T @ w - hs.GT_times(w)).max() < 1e-11
+
+
+def test_nearest_pd_and_qp(chicane_full):
+    og, game, params = chicane_full
+    hs = HostSim(game, params)
+    for seed in range(3):
+        x0, u, l = _instance(og, seed)
+        Q, q, G, g, _ = og.evaluate(u, l, x0, np.zeros(4), True)
+        hs.evaluate(x0, u, l)
+        H = nearest_pd(Q) + 1e-3 * np.eye(og.n)
+        H2, nneg = hs.nearest_pd(Q)
+        assert nneg == int((np.linalg.eigvalsh((Q + Q.T) / 2) < 0).sum()) and nneg > 0
+        assert np.abs(H - H2).max() < 1e-10 * max(1.0, np.abs(H).max())
+        du, lam = solve_qp_gi(H, q, G, g)
+        st, du2, lam2, it = hs.qp(H, q)
+        assert st == 0 and np.abs(du - du2).max() < 1e-8 and np.abs(lam - lam2).max() < 1e-7
+        r = kkt_residuals(H, q, G, g, du2, lam2)
+        assert r["stat"] < 1e-8 and r["feas"] < 1e-9 and r["dual"] == 0.0 and r["comp"] < 1e-8
+
+
+def test_nearest_pd_many_negative_eigenvalues_and_clusters(chicane_full):
+    """More negative eigenvalues than one inverse-iteration chunk, with a degenerate cluster."""
+    og, game, params = chicane_full
+    hs = HostSim(game, params)
+    rng = np.random.default_rng(3)
+    n = og.n
+    U, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    s = np.concatenate([-np.linspace(0.5, 3.0, 20), [-1.0, -1.0, -1.0 - 1e-9], rng.uniform(0.1, 5, n - 23)])
+    Q = (U * s) @ U.T
+    H2, nneg = hs.nearest_pd(Q)
+    assert nneg == 23
+    assert np.abs(H2 - (nearest_pd(Q) + 1e-3 * np.eye(n))).max() < 1e-9
+    Hp, nn0 = hs.nearest_pd((U * np.abs(s)) @ U.T)
+    assert nn0 == 0
+
+
+def test_lsqr_dual_init(chicane_full):
+    """Same Paige-Saunders recurrences and stopping rules as scipy.sparse.linalg.lsqr: iteration count within
+    one, iterate within the spread two FP64 implementations of the Krylov recurrence show (loss of
+    orthogonality amplifies rounding to ~1e-3 of |l0|; measured in DESIGN.md)."""
+    og, game, params = chicane_full
+    hs = HostSim(game, params)
+    sol = OracleDGSQP(og)
+    for seed in range(3):
+        x0, u, _ = _instance(og, seed)
+        q, G, _, _ = og.evaluate(u, np.zeros(og.m), x0, np.zeros(4), False)
+        l0 = sol.dual_init(q, G)
+        l0h, itn = hs.lsqr(x0, u)
+        assert abs(itn - sol.lsqr_iters) <= 1
+        assert np.abs(l0 - l0h).max() < 2e-2 * max(1.0, np.abs(l0).max())
+
+
+def test_solve_matches_golden(chicane_full):
+    """Full solves of the kernel source vs. the oracle's committed results.  With the oracle's dual
+    initialisation handed in (so the LSQR chaos is out of the picture) the iteration path must agree."""
+    _, game, params = chicane_full
+    hs = HostSim(game, params)
+    data = np.load(GOLDEN / "chicane_N25_seed0.npz")
+    meta = json.loads((GOLDEN / "chicane_N25_seed0.json").read_text())
+    B = data["x0"].shape[0]
+    same = 0
+    for i in range(B):
+        r = hs.solve(data["x0"][i], data["u_ws"][i], data["l_init"][i])
+        ok = MSG[r["status"]] == meta["msg"][i] and r["num_iters"] == meta["num_iters"][i]
+        same += ok
+        if ok and meta["msg"][i] == "conv_abs_tol":
+            assert np.abs(r["u"] - data["u"][i]).max() < 1e-6 * max(1.0, np.abs(data["u"][i]).max())
+            assert np.abs(r["l"] - data["l"][i]).max() < 1e-6 * max(1.0, np.abs(data["l"][i]).max())
+            assert np.abs(r["x"].ravel() - data["x"][i]).max() < 1e-6 * max(1.0, np.abs(data["x"][i]).max())
+    assert same >= 0.95 * B, f"identical (status, iters) on {same}/{B}"
+
+
+# tolerance: the curve configuration runs with reg = 0 (DGSQP_ALGAMES_monte_carlo_curve.py:161), so the projected
+# Hessian keeps eigenvalues of 1e-10 (cond ~1e11) and the QP step amplifies the 1e-13 differences between
+# LAPACK's eigh and the device eigen-solver; 1e-6 is kept for the regularised games.
+@pytest.mark.parametrize("name,mk,tol", [
+    ("curve45_N15_seed1", lambda: (dg.curve_game(45.0, 15), dg.curve_params(15)), 1e-4),
+    ("agents3_N15_seed0", lambda: (dg.agents_game(3, 90.0, 15), dg.agents_params(15)), 1e-6)])
+def test_solve_other_games_match_golden(name, mk, tol):
+    game, params = mk()
+    hs = HostSim(game, params)
+    data = np.load(GOLDEN / f"{name}.npz")
+    meta = json.loads((GOLDEN / f"{name}.json").read_text())
+    B = data["x0"].shape[0]
+    same = 0
+    for i in range(B):
+        r = hs.solve(data["x0"][i], data["u_ws"][i], data["l_init"][i])
+        ok = MSG[r["status"]] == meta["msg"][i] and r["num_iters"] == meta["num_iters"][i]
+        same += ok
+        if ok and meta["msg"][i] == "conv_abs_tol":
+            assert np.abs(r["u"] - data["u"][i]).max() < tol * max(1.0, np.abs(data["u"][i]).max())
+    assert same >= 0.9 * B, f"identical (status, iters) on {same}/{B}"
+
+
+def test_kernel_source_under_asan_ubsan():
+    """One evaluate + nearestPD + QP + short solve of the kernel source under AddressSanitizer / UBSan
+    (separate process: the sanitizer runtime has to be preloaded)."""
+    import os
+    import subprocess
+    import sys
+    import hostsim_lib
+    hostsim_lib.build(asan=True)
+    libasan = subprocess.check_output(["gcc", "-print-file-name=libasan.so"], text=True).strip()
+    env = dict(os.environ, LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1",
+               UBSAN_OPTIONS="halt_on_error=1")
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, dgsqp_b200 as dg\n"
+        "from hostsim_lib import HostSim\n"
+        "from dgsqp_b200.montecarlo import sample_head_to_head\n"
+        "for N, M in ((6, 2), (5, 3)):\n"
+        "    game = dg.chicane_game(N=N) if M == 2 else dg.agents_game(M=M, N=N)\n"
+        "    hs = HostSim(game, dg.DGSQPParams(N=N, nonmono_ls=True, sqp_iters=6, line_search_iters=8), asan=True)\n"
+        "    rng = np.random.default_rng(0)\n"
+        "    x0 = np.concatenate([[0.3*a, 0.2*a, 2.5, 0.0, 0.3 + 0.9*a, 0.4 - 0.4*a] for a in range(M)])\n"
+        "    u = rng.normal(size=game.n) * 0.1\n"
+        "    Q, q, gtl, g, x = hs.evaluate(x0, u, np.abs(rng.normal(size=game.m)) * 0.1)\n"
+        "    H, nneg = hs.nearest_pd(Q)\n"
+        "    st, du, lam, it = hs.qp(H, q)\n"
+        "    r = hs.solve(x0, u)\n"
+        "    assert np.all(np.isfinite(r['u'])), r\n"
+        "print('ASAN-OK')\n") % (str(pathlib.Path(__file__).resolve().parents[1]), str(pathlib.Path(__file__).resolve().parent))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ASAN-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

@@ -10,7 +10,7 @@ torch.set_default_dtype(torch.float64)
 def _track_terms(track, s):
     L = track.track_length
     sb = torch.fmod(torch.fmod(s, L) + L, L)
-    idx = int(sum(float(sb) >= b for b in track.curv_breaks))
+    idx = int(sum(sb.item() >= b for b in track.curv_breaks))
     kap = float(track.curv_vals[idx])
     psit = float(track.cum_ang[idx]) + float(track.slopes[idx]) * (sb - float(track.cum_len[idx]))
     return kap, psit
@@ -29,7 +29,7 @@ def rollout(game, u, x0):
             v, epsi, s, ey = q[2], q[3], q[4], q[5]
             beta = torch.atan2(torch.tan(delta) * game.L_r, torch.tensor(L))
             psidot = v / game.L_r * torch.sin(beta)
-            absv = v if float(v) > 0 else -v
+            absv = v if v.item() > 0 else -v
             F = -game.c_da * v - game.c_dr * v * absv - game.c_s * psidot ** 2
             kap, psit = _track_terms(game.track, s)
             den = 1 - ey * kap
