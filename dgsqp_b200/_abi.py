@@ -34,7 +34,7 @@ class ParamsStruct(C.Structure):
 
 
 EXPORTS = ["dgsqp_create", "dgsqp_destroy", "dgsqp_dims", "dgsqp_solve_batch", "dgsqp_solve_batch_async",
-           "dgsqp_last_diag", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_last_error", "dgsqp_version"]
+           "dgsqp_last_diag", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_last_error", "dgsqp_version"]
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "libdgsqp_b200.so"
 _lib = None
@@ -69,6 +69,8 @@ def load():
     lib.dgsqp_solve_batch_async.restype = C.c_int
     lib.dgsqp_last_diag.argtypes = [vp, C.c_int32, vp]
     lib.dgsqp_last_diag.restype = C.c_int
+    lib.dgsqp_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.dgsqp_measure_fp64_peak.restype = C.c_int
     lib.dgsqp_kernel_launches.argtypes = []
     lib.dgsqp_kernel_launches.restype = C.c_int64
     lib.dgsqp_configure.argtypes = [vp, C.c_int32, C.c_int32]

@@ -21,6 +21,7 @@
 #define DG_RESTRICT
 struct Cta {
   int tid = 0, nt = 1, lane = 0, warp = 0, nwarps = 1;
+  static constexpr int wsz = 1;   // lanes per warp
   double* red = nullptr;
   inline void sync() {}
   inline double sum(double v) { return v; }
@@ -40,6 +41,7 @@ struct Cta {
 #define DG_RESTRICT __restrict__
 struct Cta {
   int tid, nt, lane, warp, nwarps;
+  static constexpr int wsz = 32;  // lanes per warp
   double* red;   // shared scratch, >= 2*nwarps+2 doubles
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ double warp_sum(double v) {

@@ -4,10 +4,22 @@
 // conlim = 1e8, iter_lim = 2*m, damp = 0, x0 = None on the singular m x m matrix G G'.  The
 // early-stopped Krylov iterate is not a closed form, so the recurrences and the ORDER of the
 // stopping tests are restated here after scipy/sparse/linalg/_isolve/lsqr.py:329-560.
+//
+// Plain LSQR loses orthogonality of its Golub-Kahan vectors and then amplifies rounding: SciPy run on
+// the dense and on the sparse form of the same G G' already returns l0 that differ by up to 5e-3 and
+// stops up to one iteration apart (measured).  To make the dual initialisation a
+// reproducible function of the instance, every new u_k / v_k is re-orthogonalised against all earlier
+// ones (classical Gram-Schmidt, two passes; basis capped at DG_LSQR_BASIS vectors).  In exact arithmetic
+// this is the same algorithm; in FP64 the iterates then track the exact-arithmetic ones to ~1e-12.
 #pragma once
 #include "racing_game.cuh"
 
+#define DG_LSQR_BASIS 64
+
 struct LsqrBuf {
+  double* Ub;  // DG_LSQR_BASIS*m  stored u_k
+  double* Vb;  // DG_LSQR_BASIS*m  stored v_k
+  double* cf;  // DG_LSQR_BASIS    projection coefficients
   double* u;   // m
   double* v;   // m
   double* w;   // m
@@ -42,6 +54,28 @@ DG_DEV double vec_norm(Cta& c, int len, const double* v) {
   return sqrt(c.sum(p));
 }
 
+// vec <- (I - B B') vec, twice; B = first nb rows of basis (orthonormal).  Warp per basis vector for the
+// dot products, thread per element for the update.
+DG_DEV void lsqr_reorth(Cta& c, int m, const double* basis, int nb, double* vec, double* cf) {
+  for (int pass = 0; pass < 2; ++pass) {
+    c.sync();
+    for (int j = c.warp; j < nb; j += c.nwarps) {
+      const double* b = basis + (size_t)j * m;
+      double p = 0.0;
+      for (int i = c.lane; i < m; i += c.wsz) p += b[i] * vec[i];
+      p = c.warp_sum(p);
+      if (c.lane == 0) cf[j] = p;
+    }
+    c.sync();
+    DG_FOR(i, m) {
+      double acc = 0.0;
+      for (int j = 0; j < nb; ++j) acc += cf[j] * basis[(size_t)j * m + i];
+      vec[i] -= acc;
+    }
+  }
+  c.sync();
+}
+
 // l_out[m] = max(0, -x_lsqr).  Returns the iteration count.
 DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D, const EvalBuf& E, const LsqrBuf& L, const double* qv, double* l_out) {
   const int m = D.m;
@@ -55,9 +89,11 @@ DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D, const EvalBuf& E, const LsqrBu
   DG_FOR(i, m) L.x[i] = 0.0;
   double bnorm = vec_norm(c, m, L.u);
   double beta = bnorm, alfa = 0.0;
+  int nU = 0, nV = 0;
   if (beta > 0.0) {
     c.sync();
-    DG_FOR(i, m) L.u[i] *= 1.0 / beta;
+    DG_FOR(i, m) { L.u[i] *= 1.0 / beta; L.Ub[i] = L.u[i]; }
+    nU = 1;
     c.sync();
     lsqr_A(c, D, E, L, L.u, L.v);
     alfa = vec_norm(c, m, L.v);
@@ -65,7 +101,7 @@ DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D, const EvalBuf& E, const LsqrBu
     DG_FOR(i, m) L.v[i] = 0.0;
   }
   c.sync();
-  if (alfa > 0.0) { DG_FOR(i, m) L.v[i] *= 1.0 / alfa; }
+  if (alfa > 0.0) { DG_FOR(i, m) { L.v[i] *= 1.0 / alfa; L.Vb[i] = L.v[i]; } nV = 1; }
   c.sync();
   DG_FOR(i, m) L.w[i] = L.v[i];
   double rhobar = alfa, phibar = beta;
@@ -76,19 +112,25 @@ DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D, const EvalBuf& E, const LsqrBu
       // u = A v - alfa u
       lsqr_A(c, D, E, L, L.v, L.tm);
       DG_FOR(i, m) L.u[i] = L.tm[i] - alfa * L.u[i];
-      c.sync();
+      lsqr_reorth(c, m, L.Ub, nU, L.u, L.cf);
       beta = vec_norm(c, m, L.u);
       if (beta > 0.0) {
         c.sync();
-        DG_FOR(i, m) L.u[i] *= 1.0 / beta;
+        const bool keepU = nU < DG_LSQR_BASIS;
+        DG_FOR(i, m) { L.u[i] *= 1.0 / beta; if (keepU) L.Ub[(size_t)nU * m + i] = L.u[i]; }
+        if (keepU) ++nU;
         c.sync();
         anorm = sqrt(anorm * anorm + alfa * alfa + beta * beta);
         lsqr_A(c, D, E, L, L.u, L.tm);
         DG_FOR(i, m) L.v[i] = L.tm[i] - beta * L.v[i];
-        c.sync();
+        lsqr_reorth(c, m, L.Vb, nV, L.v, L.cf);
         alfa = vec_norm(c, m, L.v);
         c.sync();
-        if (alfa > 0.0) { DG_FOR(i, m) L.v[i] *= 1.0 / alfa; }
+        if (alfa > 0.0) {
+          const bool keepV = nV < DG_LSQR_BASIS;
+          DG_FOR(i, m) { L.v[i] *= 1.0 / alfa; if (keepV) L.Vb[(size_t)nV * m + i] = L.v[i]; }
+          if (keepV) ++nV;
+        }
         c.sync();
       }
       double rhobar1 = rhobar, psi = 0.0;

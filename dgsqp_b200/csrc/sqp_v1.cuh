@@ -47,6 +47,7 @@ DG_HD size_t carve_workspace(const Dims& D, double* base, Workspace& W) {
   CARVE(W.Q.Rm, n * n); CARVE(W.Q.xq, n); CARVE(W.Q.dv, n); CARVE(W.Q.zv, n); CARVE(W.Q.rv, n); CARVE(W.Q.npv, n);
   CARVE(W.Q.hv, n); CARVE(W.Q.wv, n); CARVE(W.Q.lam_act, n); CARVE(W.Q.sl, m); CARVE(W.Q.lam, m);
   { double* t; CARVE(t, (n + 1) / 2 + 1); W.Q.act = (int*)t; CARVE(t, (m + 1) / 2 + 1); W.Q.is_act = (int*)t; }
+  CARVE(W.L.Ub, DG_LSQR_BASIS * m); CARVE(W.L.Vb, DG_LSQR_BASIS * m); CARVE(W.L.cf, DG_LSQR_BASIS);
   CARVE(W.L.u, m); CARVE(W.L.v, m); CARVE(W.L.w, m); CARVE(W.L.x, m); CARVE(W.L.tn, n); CARVE(W.L.tm, m);
   CARVE(W.S.u, n); CARVE(W.S.l, m); CARVE(W.S.u_im1, n); CARVE(W.S.l_im1, m);
   CARVE(W.S.du, n); CARVE(W.S.dl, m); CARVE(W.S.s, m); CARVE(W.S.ds, m);

@@ -120,6 +120,10 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
  * full evaluations, gradient-only evaluations, QP active-set iterations, max #negative eigenvalues. */
 int dgsqp_last_diag(dgsqp_handle* h, int32_t B, int32_t* diag);
 
+/* Measures the device's sustained FP64 FMA throughput (TFLOP/s, 2 flops per FMA) with a register-only
+ * probe kernel: the roofline denominator for this FP64-bound path. */
+int dgsqp_measure_fp64_peak(int device, double* tflops);
+
 /* Number of kernels launched by this library since load (for bench accounting). */
 int64_t dgsqp_kernel_launches(void);
 

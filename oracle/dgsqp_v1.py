@@ -14,12 +14,15 @@ Deviations from the reference (documented in DESIGN.md):
   between 0 and ~1e18 on rounding noise (in the reference: on OSQP's polish residual) and with it the
   whole iteration path.  ``mu_vio_thresh`` (default 1e-10) makes that choice deterministic; pass 0 for
   the literal reference rule;
+* the dual initialisation runs LSQR with reorthogonalised Golub-Kahan vectors (``dual_init_method='reorth'``):
+  SciPy's plain LSQR is only reproducible to ~1e-2 (oracle/lsqr_reorth.py); ``'scipy'`` gives the literal call;
 * ``time_limit`` is not modelled (wall-clock, default None in every BASELINE config).
 """
 import numpy as np
 import scipy.sparse.linalg as spla
 
 from .qp import solve_qp_gi, QPFailure
+from .lsqr_reorth import lsqr_reorth
 
 
 def nearest_pd(A, floor=1e-10):
@@ -34,7 +37,7 @@ def nearest_pd(A, floor=1e-10):
 class OracleDGSQP:
     def __init__(self, game, reg=1e-3, line_search_iters=50, nonmono_ls=True, sqp_iters=50,
                  p_tol=1e-3, d_tol=1e-3, beta=0.01, tau=0.5, merit_function="stat_l1",
-                 conv_approx=True, mu_vio_thresh=1e-10):
+                 conv_approx=True, mu_vio_thresh=1e-10, dual_init_method="reorth"):
         self.game = game
         self.reg, self.line_search_iters, self.nonmono_ls = reg, line_search_iters, nonmono_ls
         self.sqp_iters, self.p_tol, self.d_tol, self.beta, self.tau = sqp_iters, p_tol, d_tol, beta, tau
@@ -42,6 +45,7 @@ class OracleDGSQP:
         self.rel_tol_req = 3
         # `thresh` in _get_mu (DGSQP.py:560) is 0 in the reference; see module docstring
         self.mu_vio_thresh = mu_vio_thresh
+        self.dual_init_method = dual_init_method        # 'reorth' (canonical) or 'scipy' (the literal call)
         self.qp_stats = []            # per-QP diagnostics (active-set size, negative eigenvalues, ...)
         self.trace = None
 
@@ -169,10 +173,16 @@ class OracleDGSQP:
 
     # -------------------------------------------------------------------- solve
     def dual_init(self, q, G):
-        """l0 = max(0, -lsqr(G G^T, G q)) (DGSQP.py:323-324), SciPy defaults."""
-        sol = spla.lsqr(G @ G.T, G @ q)
-        self.lsqr_iters = sol[2]
-        return np.maximum(0, -sol[0])
+        """l0 = max(0, -lsqr(G G^T, G q)) (DGSQP.py:323-324), SciPy's default tolerances.  'scipy' is the
+        reference's literal call; 'reorth' is the same algorithm with reorthogonalised Golub-Kahan vectors,
+        the reproducible form the CUDA path implements (see oracle/lsqr_reorth.py)."""
+        if self.dual_init_method == "scipy":
+            sol = spla.lsqr(G @ G.T, G @ q)
+            x, self.lsqr_iters = sol[0], sol[2]
+        else:
+            mv = lambda v: G @ (G.T @ v)
+            x, _, self.lsqr_iters = lsqr_reorth(mv, mv, G @ q, G.shape[0])
+        return np.maximum(0, -x)
 
     def solve(self, x0, u_ws, record_trace=False, l_ws=None):
         game = self.game

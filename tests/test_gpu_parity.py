@@ -51,8 +51,8 @@ def test_stages_vs_oracle(threads):
         assert r["stat"] < 1e-8 and r["feas"] < 1e-9 and r["dual"] == 0.0 and r["comp"] < 1e-8
         q0, G0, _, _ = og.evaluate(u[i], np.zeros(game.m), x0[i], np.zeros(4), False)
         l0 = sol.dual_init(q0, G0)
-        assert abs(int(out["lsqr_it"][i]) - sol.lsqr_iters) <= 1
-        assert np.abs(out["l0"][i] - l0).max() < 2e-2 * max(1.0, np.abs(l0).max())
+        assert int(out["lsqr_it"][i]) == sol.lsqr_iters
+        assert np.abs(out["l0"][i] - l0).max() < 1e-9 * max(1.0, np.abs(l0).max())
 
 
 # ------------------------------------------------------------------ full solves vs golden (oracle) results
@@ -87,15 +87,13 @@ def test_solve_vs_golden_shared_dual_init(name, mk, tol, min_same):
 
 
 def test_solve_vs_golden_own_lsqr():
-    """End to end with the on-device LSQR dual initialisation.  Two FP64 LSQR implementations differ by
-    ~1e-3 in l0 (Krylov rounding chaos), which moves some iteration paths; the equilibria of
-    the instances whose paths agree must still match to 1e-6."""
+    """End to end with the on-device (reorthogonalised) LSQR dual initialisation."""
     game, params = dg.chicane_game(), dg.chicane_params()
     data, meta = _golden("chicane_N25_seed0")
     res = dg.DGSQP(game, params, print_method=None).solve_batch(data["x0"], data["u_ws"])
     B = data["x0"].shape[0]
     same = np.array([res.msg[i] == meta["msg"][i] and int(res.num_iters[i]) == meta["num_iters"][i] for i in range(B)])
-    assert same.mean() >= 0.7, f"identical (status, iters): {same.sum()}/{B}"
+    assert same.mean() >= 0.9, f"identical (status, iters): {same.sum()}/{B}"
     for i in np.where(same)[0]:
         if meta["msg"][i] == "conv_abs_tol":
             assert _rel(res.u[i], data["u"][i]) < 1e-6 and _rel(res.x[i], data["x"][i]) < 1e-6

@@ -23,7 +23,7 @@ def _lib():
 
 def test_header_symbols_exported():
     header = (ROOT / "include" / "dgsqp_b200.h").read_text()
-    declared = set(re.findall(r"\b(dgsqp_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(dgsqp_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_abi.EXPORTS)
     lib = _lib()
     for name in declared:

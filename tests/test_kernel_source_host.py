@@ -82,9 +82,11 @@ def test_nearest_pd_many_negative_eigenvalues_and_clusters(chicane_full):
 
 
 def test_lsqr_dual_init(chicane_full):
-    """Same Paige-Saunders recurrences and stopping rules as scipy.sparse.linalg.lsqr: iteration count within
-    one, iterate within the spread two FP64 implementations of the Krylov recurrence show (loss of
-    orthogonality amplifies rounding to ~1e-3 of |l0|; measured in DESIGN.md)."""
+    """Dual initialisation: same recurrences / stopping rules as scipy.sparse.linalg.lsqr with reorthogonalised
+    Golub-Kahan vectors.  Kernel source == oracle to rounding, iteration for iteration; the literal SciPy call
+    (what the reference runs) lies within its own reproducibility band of that result."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
     og, game, params = chicane_full
     hs = HostSim(game, params)
     sol = OracleDGSQP(og)
@@ -93,8 +95,14 @@ def test_lsqr_dual_init(chicane_full):
         q, G, _, _ = og.evaluate(u, np.zeros(og.m), x0, np.zeros(4), False)
         l0 = sol.dual_init(q, G)
         l0h, itn = hs.lsqr(x0, u)
-        assert abs(itn - sol.lsqr_iters) <= 1
-        assert np.abs(l0 - l0h).max() < 2e-2 * max(1.0, np.abs(l0).max())
+        assert itn == sol.lsqr_iters
+        assert np.abs(l0 - l0h).max() < 1e-10 * max(1.0, np.abs(l0).max())
+        # SciPy itself: dense vs sparse operator already disagree at the 1e-5..1e-2 level
+        dense = np.maximum(0, -spla.lsqr(G @ G.T, G @ q)[0])
+        Gs = sp.csc_matrix(G)
+        sparse = np.maximum(0, -spla.lsqr(Gs @ Gs.T, G @ q)[0])
+        spread = np.abs(dense - sparse).max()
+        assert np.abs(l0 - dense).max() < max(50 * spread, 5e-2 * np.abs(l0).max())
 
 
 def test_solve_matches_golden(chicane_full):
