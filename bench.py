@@ -130,7 +130,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=10000, help="instances per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="instances for the CPU baseline (0 = 2 per core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="instances for the CPU baseline (0 = 1 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -151,7 +151,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n_s = args.cpu_sample or 2 * cores
+        n_s = args.cpu_sample or cores
         x0, u_ws = sample_head_to_head(game, n_s * (args.steps + args.warmup), seed=0)
         vals, its, secs = [], [], []
         for s in range(args.warmup + args.steps):
@@ -288,7 +288,7 @@ def main():
             work=dict(full_evals=float(diag[:, 0].mean()), grad_evals=float(diag[:, 1].mean()),
                       qp_active_set_iters=float(diag[:, 2].mean()), algorithmic_mflop_per_instance=fl / B / 1e6))
         if not args.no_cpu_baseline:
-            n_s = args.cpu_sample or 2 * cores
+            n_s = args.cpu_sample or cores
             v, ips, dt, conv = cpu_oracle_throughput(x0[:n_s], u_ws[:n_s], cores)
             line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=cores, kind="port",
                                         sample=f"first {n_s} instances of the same batch, one oracle process per core, "

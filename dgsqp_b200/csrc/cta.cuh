@@ -26,12 +26,17 @@ struct Cta {
   inline void sync() {}
   inline double sum(double v) { return v; }
   inline double max(double v) { return v; }
+  inline void max3(double& a, double& b, double& d) {}
   inline double min(double v) { return v; }
   inline int imin(int v) { return v; }
   inline int isum(int v) { return v; }
   // smallest value, ties -> smallest index; every thread gets the winner
   inline void argmin(double v, int idx, double& ov, int& oi) { ov = v; oi = idx; }
   inline double warp_sum(double v) { return v; }
+  inline void syncwarp() {}
+  inline void sum2(double& a, double& b) {}
+  inline void sum3(double& a, double& b, double& d) {}
+  inline void sum4(double& a, double& b, double& d, double& e) {}
 };
 #else
 #define DG_DEV __device__ __forceinline__
@@ -42,51 +47,97 @@ struct Cta {
 struct Cta {
   int tid, nt, lane, warp, nwarps;
   static constexpr int wsz = 32;  // lanes per warp
-  double* red;   // shared scratch, >= 2*nwarps+2 doubles
+  double* red;   // shared scratch: 2 buffers x 160 doubles
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   }
+  // Block reductions use two alternating scratch buffers, so one barrier per reduction suffices: a thread
+  // can only reach the next reduction that reuses a buffer after passing the barrier of the one in between.
+  int flip = 0;
+  __device__ __forceinline__ double* next_buf() { flip ^= 1; return red + flip * 160; }
+  __device__ __forceinline__ void syncwarp() { __syncwarp(); }
   __device__ __forceinline__ double sum(double v) {
     v = warp_sum(v);
-    __syncthreads();                       // protect `red` from the previous reduction's readers
-    if (lane == 0) red[warp] = v;
+    double* b = next_buf();
+    if (lane == 0) b[warp] = v;
     __syncthreads();
     double r = 0.0;
-    for (int w = 0; w < nwarps; ++w) r += red[w];   // same order in every thread -> identical result
+    for (int w = 0; w < nwarps; ++w) r += b[w];     // same order in every thread -> identical result
     return r;
+  }
+  __device__ __forceinline__ void sum2(double& a0, double& a1) {
+    a0 = warp_sum(a0); a1 = warp_sum(a1);
+    double* b = next_buf();
+    if (lane == 0) { b[warp] = a0; b[32 + warp] = a1; }
+    __syncthreads();
+    double r0 = 0.0, r1 = 0.0;
+    for (int w = 0; w < nwarps; ++w) { r0 += b[w]; r1 += b[32 + w]; }
+    a0 = r0; a1 = r1;
+  }
+  __device__ __forceinline__ void sum3(double& a0, double& a1, double& a2) {
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    double* b = next_buf();
+    if (lane == 0) { b[warp] = a0; b[32 + warp] = a1; b[64 + warp] = a2; }
+    __syncthreads();
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    for (int w = 0; w < nwarps; ++w) { r0 += b[w]; r1 += b[32 + w]; r2 += b[64 + w]; }
+    a0 = r0; a1 = r1; a2 = r2;
+  }
+  __device__ __forceinline__ void sum4(double& a0, double& a1, double& a2, double& a3) {
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    double* b = next_buf();
+    if (lane == 0) { b[warp] = a0; b[32 + warp] = a1; b[64 + warp] = a2; b[96 + warp] = a3; }
+    __syncthreads();
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+    for (int w = 0; w < nwarps; ++w) { r0 += b[w]; r1 += b[32 + w]; r2 += b[64 + w]; r3 += b[96 + w]; }
+    a0 = r0; a1 = r1; a2 = r2; a3 = r3;
   }
   __device__ __forceinline__ double max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    double* b = next_buf();
+    if (lane == 0) b[warp] = v;
     __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    double r = red[0];
-    for (int w = 1; w < nwarps; ++w) r = fmax(r, red[w]);
+    double r = b[0];
+    for (int w = 1; w < nwarps; ++w) r = fmax(r, b[w]);
     return r;
+  }
+  __device__ __forceinline__ void max3(double& a0, double& a1, double& a2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 = fmax(a0, __shfl_xor_sync(0xffffffffu, a0, o));
+      a1 = fmax(a1, __shfl_xor_sync(0xffffffffu, a1, o));
+      a2 = fmax(a2, __shfl_xor_sync(0xffffffffu, a2, o));
+    }
+    double* b = next_buf();
+    if (lane == 0) { b[warp] = a0; b[32 + warp] = a1; b[64 + warp] = a2; }
+    __syncthreads();
+    double r0 = b[0], r1 = b[32], r2 = b[64];
+    for (int w = 1; w < nwarps; ++w) { r0 = fmax(r0, b[w]); r1 = fmax(r1, b[32 + w]); r2 = fmax(r2, b[64 + w]); }
+    a0 = r0; a1 = r1; a2 = r2;
   }
   __device__ __forceinline__ double min(double v) { return -max(-v); }
   __device__ __forceinline__ int imin(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+    int* b = (int*)next_buf();
+    if (lane == 0) b[warp] = v;
     __syncthreads();
-    if (lane == 0) ((int*)red)[warp] = v;
-    __syncthreads();
-    int r = ((int*)red)[0];
-    for (int w = 1; w < nwarps; ++w) { int t = ((int*)red)[w]; r = t < r ? t : r; }
+    int r = b[0];
+    for (int w = 1; w < nwarps; ++w) { int t = b[w]; r = t < r ? t : r; }
     return r;
   }
   __device__ __forceinline__ int isum(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if (lane == 0) ((int*)red)[warp] = v;
+    int* b = (int*)next_buf();
+    if (lane == 0) b[warp] = v;
     __syncthreads();
     int r = 0;
-    for (int w = 0; w < nwarps; ++w) r += ((int*)red)[w];
+    for (int w = 0; w < nwarps; ++w) r += b[w];
     return r;
   }
   __device__ __forceinline__ void argmin(double v, int idx, double& ov, int& oi) {
@@ -96,12 +147,12 @@ struct Cta {
       int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
       if (v2 < v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
     }
+    double* b = next_buf();
+    if (lane == 0) { b[warp] = v; ((int*)(b + 32))[warp] = idx; }
     __syncthreads();
-    if (lane == 0) { red[warp] = v; ((int*)(red + nwarps))[warp] = idx; }
-    __syncthreads();
-    ov = red[0]; oi = ((int*)(red + nwarps))[0];
+    ov = b[0]; oi = ((int*)(b + 32))[0];
     for (int w = 1; w < nwarps; ++w) {
-      double v2 = red[w]; int i2 = ((int*)(red + nwarps))[w];
+      double v2 = b[w]; int i2 = ((int*)(b + 32))[w];
       if (v2 < ov || (v2 == ov && i2 < oi)) { ov = v2; oi = i2; }
     }
   }

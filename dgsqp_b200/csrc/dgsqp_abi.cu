@@ -35,10 +35,11 @@ struct KernelArgs {
   int* counter;
 };
 
-__global__ void dgsqp_solve_kernel(const GameDesc* __restrict__ Gp, const SolverParams* __restrict__ Pp, KernelArgs A) {
+__global__ void __launch_bounds__(256, 2) dgsqp_solve_kernel(const GameDesc* __restrict__ Gp, const SolverParams* __restrict__ Pp, KernelArgs A) {
   __shared__ GameDesc sG;
   __shared__ SolverParams sP;
-  __shared__ double s_red[2 * 32 + 2];
+  __shared__ double s_red[320];
+  extern __shared__ double s_dyn[];
   __shared__ int s_inst;
   {
     const int nw = (int)(sizeof(GameDesc) / sizeof(int));
@@ -49,10 +50,11 @@ __global__ void dgsqp_solve_kernel(const GameDesc* __restrict__ Gp, const Solver
   __syncthreads();
   Cta c;
   c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
-  c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red;
+  c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red; c.flip = 0;
   SolveCtx X;
   X.G = &sG; X.P = &sP; X.D = make_dims(sG.M, sG.N);
   carve_workspace(X.D, A.ws + (size_t)blockIdx.x * A.ws_stride, X.W);
+  carve_shared(X.D, s_dyn, X.W);
   const Dims& D = X.D;
   while (true) {
     if (threadIdx.x == 0) s_inst = atomicAdd(A.counter, 1);
@@ -88,7 +90,7 @@ __global__ void dgsqp_fp64_probe_kernel(double* out, int iters, double a, double
 struct dgsqp_handle {
   GameDesc G; SolverParams P; Dims D;
   int device = 0, sm_count = 0, ctas_per_sm = 0, threads = 128, grid_cap = 0;
-  size_t ws_doubles = 0;
+  size_t ws_doubles = 0, smem_bytes = 0;
   double* d_ws = nullptr; int* d_counter = nullptr; int* d_diag = nullptr; size_t diag_cap = 0;
   GameDesc* d_G = nullptr; SolverParams* d_P = nullptr;
   // staging for host-pointer calls
@@ -108,7 +110,9 @@ static void free_stage(dgsqp_handle* h) {
 
 static int ensure_grid(dgsqp_handle* h) {
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dgsqp_solve_kernel, h->threads, 0));
+  h->smem_bytes = sizeof(double) * (size_t)h->D.n * (2 + DG_CHOL_NB);
+  CUDA_TRY(cudaFuncSetAttribute(dgsqp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dgsqp_solve_kernel, h->threads, h->smem_bytes));
   if (occ < 1) return set_err(DGSQP_ECUDA, "kernel does not fit on an SM");
   int per_sm = h->ctas_per_sm > 0 ? (h->ctas_per_sm < occ ? h->ctas_per_sm : occ) : occ;
   int cap = per_sm * h->sm_count;
@@ -209,7 +213,7 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
   A.cond_out = cond_out; A.num_iters = num_iters; A.status = status; A.qp_solves = qp_solves; A.diag = h->d_diag;
   A.ws = h->d_ws; A.ws_stride = h->ws_doubles; A.counter = h->d_counter;
   int grid = B < h->grid_cap ? B : h->grid_cap;
-  dgsqp_solve_kernel<<<grid, h->threads, 0, st>>>(h->d_G, h->d_P, A);
+  dgsqp_solve_kernel<<<grid, h->threads, h->smem_bytes, st>>>(h->d_G, h->d_P, A);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return DGSQP_OK;

@@ -126,9 +126,9 @@ struct EvalBuf {
   double* gtl;   // n   G' l
   double* cst;   // (M+1)*(N+1)*nq  costates: f<M of J^f, f==M of l'C
   double* Hc;    // (M+1)*N*M*15    sum_i p_i * T2[i]
-  double* Vbuf;  // 2*nq*nq  DP value-function Hessian (double buffered)
+  double* Vbuf;  // 2*(M+1)*nq*nq  DP value-function Hessians of all functions (double buffered)
   double* Q;     // n*n raw game Hessian (row major)
-  double* Wrow;  // n*nq  running rows of Dxu_Q in the Hessian DP
+  double* Wrow;  // (M+1)*nq*n  running rows of Dxu_Q^f in the Hessian DP, [(f*nq+q)*n + r]
   double* tmpS;  // M*N*3   state-row products for G v
   double* cf;    // M*N*3   per (a,k) coefficients for G' w
 };
@@ -459,104 +459,118 @@ DG_DEV double hc_xx(const double* hc, int i, int j) {
 DG_DEV double hc_ux(const double* hc, int cu, int j) { return (cu == 1 && j >= 2) ? hc[tri5(j - 2, 4)] : 0.0; }
 DG_DEV double hc_uu(const double* hc, int c1, int c2) { return (c1 == 1 && c2 == 1) ? hc[14] : 0.0; }
 
-// Game Hessian Q (f_Q): backward DP per function (M costs, then l'C), rows = threads.
-//   row block a of Q = grad_{u^a} grad_u (J^a + l'C)       (DGSQP.py:920-934)
-DG_DEVN void game_hessian(Cta& c, const GameDesc& G, const Dims& D, const EvalBuf& E, const double* l) {
-  const int n = D.n, nq = D.nq, N = D.N, M = D.M;
-  DG_FOR(t, n * n) E.Q[t] = 0.0;
+// Game Hessian Q (f_Q): ONE backward sweep over the stages carrying all M+1 functions (the M costs and
+// l'C); rows of Q are owned by threads.   row block a of Q = grad_{u^a} grad_u (J^a + l'C)   (DGSQP.py:920-934)
+// Thread r (stage-major input index (k_r, a_r, c_r)) keeps w^f = row r of Dxu_Q^f for every function f in
+// E.Wrow[(f*nq + q)*n + r] (coalesced).  At stage k < k_r it emits H^f[r, (k,b,cc)] = w^f[b] . B^b_k[:,cc] and
+// stores  Q[r][(k,b,cc)] = H^{a_r} + H^M  and, by symmetry of each H^f,  Q[(k,b,cc)][r] = H^b + H^M.
+// Every entry of Q is written exactly once, so Q needs no zero-fill and no read-modify-write.
+DG_DEVN void game_hessian(Cta& c, const GameDesc& G, const Dims& D, const EvalBuf& E, const double* DG_RESTRICT l) {
+  const int n = D.n, nq = D.nq, N = D.N, M = D.M, F = D.M + 1;
+  const double* xN = E.x + N * nq;
+  double* Vcur = E.Vbuf;
+  double* Vnext = E.Vbuf + F * nq * nq;
+  DG_FOR(t, F * nq * nq) {
+    int f = t / (nq * nq), e = t - f * nq * nq, i1 = e / nq, i2 = e - i1 * nq;
+    Vcur[t] = f < M ? term_hess(G, D, xN, f, i1, i2) : con_lxx(D, l, N, i1, i2);
+  }
   c.sync();
-  for (int f = 0; f <= M; ++f) {
-    const double* cst = E.cst + f * (N + 1) * nq;
-    const double* xN = E.x + N * nq;
-    // V_N
-    double* Vcur = E.Vbuf;
-    double* Vnext = E.Vbuf + nq * nq;
-    DG_FOR(t, nq * nq) {
-      int i1 = t / nq, i2 = t - i1 * nq;
-      Vcur[t] = f < M ? term_hess(G, D, xN, f, i1, i2) : con_lxx(D, l, N, i1, i2);
-    }
-    c.sync();
-    // rows handled by this thread: r = stage-major (k_r, a_r, c_r); its running row of Dxu_Q lives in
-    // E.Wrow[r] and is only ever touched by the owning thread.
-    for (int k = N - 1; k >= 0; --k) {
-      for (int r = c.tid; r < n; r += c.nt) {
-        int kr = r / D.nu, ar = (r - kr * D.nu) >> 1, cr = r & 1;
-        int rowQ = uidx(D, ar, kr, cr);
-        double* wr = E.Wrow + r * nq;
-        if (kr > k) {
-          // existing row: Duu(row r, cols of stage k) = w . B_k ; then w <- w A_k
-          for (int b = 0; b < M; ++b) {
-            const double* ABk = E.AB + (k * M + b) * 48;
-            for (int cc = 0; cc < 2; ++cc) {
-              double val = 0.0;
-              for (int i = 0; i < DG_NQA; ++i) val += wr[b * DG_NQA + i] * ABk[i * 8 + 6 + cc];
-              if (f < M && kr == k + 1 && b == ar && ar == f && cc == cr) val -= G.w_du[cc];
-              int colQ = uidx(D, b, k, cc);
-              if (f == M) { E.Q[rowQ * n + colQ] += val; E.Q[colQ * n + rowQ] += val; }
-              else {
-                if (ar == f) E.Q[rowQ * n + colQ] += val;
-                if (b == f) E.Q[colQ * n + rowQ] += val;
+  double* DG_RESTRICT Qm = E.Q;
+  for (int k = N - 1; k >= 0; --k) {
+    for (int r = c.tid; r < n; r += c.nt) {
+      const int kr = r / D.nu, ar = (r - kr * D.nu) >> 1, cr = r & 1;
+      const int rowQ = uidx(D, ar, kr, cr);
+      double* DG_RESTRICT wr = E.Wrow + r;                     // w^f[q] at wr[(f*nq + q)*n]
+      if (kr > k) {
+        for (int b = 0; b < M; ++b) {
+          const double* DG_RESTRICT ABk = E.AB + (k * M + b) * 48;
+          double hM[2] = {0.0, 0.0}, hA[2] = {0.0, 0.0}, hB[2] = {0.0, 0.0};
+          for (int f = 0; f < F; ++f) {
+            if (f != M && f != ar && f != b) {
+              // this function's row is only propagated
+            }
+            double wv6[DG_NQA];
+            for (int i = 0; i < DG_NQA; ++i) wv6[i] = wr[(f * nq + b * DG_NQA + i) * n];
+            if (f == M || f == ar || f == b) {
+              for (int cc = 0; cc < 2; ++cc) {
+                double val = 0.0;
+                for (int i = 0; i < DG_NQA; ++i) val += wv6[i] * ABk[i * 8 + 6 + cc];
+                if (f < M && kr == k + 1 && b == ar && f == ar && cc == cr) val -= G.w_du[cc];
+                if (f == M) hM[cc] = val;
+                if (f == ar) hA[cc] = val;
+                if (f == b) hB[cc] = val;
               }
             }
-            double tn[DG_NQA];
             for (int j = 0; j < DG_NQA; ++j) {
               double acc = 0.0;
-              for (int i = 0; i < DG_NQA; ++i) acc += wr[b * DG_NQA + i] * ABk[i * 8 + j];
-              tn[j] = acc;
+              for (int i = 0; i < DG_NQA; ++i) acc += wv6[i] * ABk[i * 8 + j];
+              wr[(f * nq + b * DG_NQA + j) * n] = acc;
             }
-            for (int j = 0; j < DG_NQA; ++j) wr[b * DG_NQA + j] = tn[j];
           }
-        } else if (kr == k) {
-          // new row (k, ar, cr):  t = B[:, (ar,cr)]' V[ar-block rows, :]
-          const double* ABa = E.AB + (k * M + ar) * 48;
-          const double* hc = E.Hc + ((f * N + k) * M + ar) * 15;
+          for (int cc = 0; cc < 2; ++cc) {
+            const int colQ = uidx(D, b, k, cc);
+            Qm[rowQ * n + colQ] = hA[cc] + hM[cc];
+            Qm[colQ * n + rowQ] = hB[cc] + hM[cc];
+          }
+        }
+      } else if (kr == k) {
+        const double* DG_RESTRICT ABa = E.AB + (k * M + ar) * 48;
+        double a1M[2 * DG_MAX_AGENTS], a1A[2 * DG_MAX_AGENTS];
+        for (int f = 0; f < F; ++f) {
+          const double* DG_RESTRICT Vf = Vcur + f * nq * nq;
+          const double* DG_RESTRICT hc = E.Hc + ((f * N + k) * M + ar) * 15;
           double tv[DG_MAX_NQ];
           for (int j = 0; j < nq; ++j) {
             double acc = 0.0;
-            for (int i = 0; i < DG_NQA; ++i) acc += ABa[i * 8 + 6 + cr] * Vcur[(ar * DG_NQA + i) * nq + j];
+            for (int i = 0; i < DG_NQA; ++i) acc += ABa[i * 8 + 6 + cr] * Vf[(ar * DG_NQA + i) * nq + j];
             tv[j] = acc;
           }
-          // same-stage block A1 = luu + B'VB + F.p
-          for (int b = 0; b < M; ++b) {
-            const double* ABb = E.AB + (k * M + b) * 48;
-            for (int cc = 0; cc < 2; ++cc) {
-              double val = 0.0;
-              for (int i = 0; i < DG_NQA; ++i) val += tv[b * DG_NQA + i] * ABb[i * 8 + 6 + cc];
-              if (b == ar) {
-                val += hc_uu(hc, cr, cc);
-                if (f < M && ar == f && cc == cr) val += G.w_u[cc] + G.w_du[cc] + (k + 1 < N ? G.w_du[cc] : 0.0);
+          if (f == M || f == ar) {
+            // same-stage block A1 = luu + B'VB + F.p
+            for (int b = 0; b < M; ++b) {
+              const double* DG_RESTRICT ABb = E.AB + (k * M + b) * 48;
+              for (int cc = 0; cc < 2; ++cc) {
+                double val = 0.0;
+                for (int i = 0; i < DG_NQA; ++i) val += tv[b * DG_NQA + i] * ABb[i * 8 + 6 + cc];
+                if (b == ar) {
+                  val += hc_uu(hc, cr, cc);
+                  if (f < M && cc == cr) val += G.w_u[cc] + G.w_du[cc] + (k + 1 < N ? G.w_du[cc] : 0.0);
+                }
+                if (f == M) a1M[b * 2 + cc] = val; else a1A[b * 2 + cc] = val;
               }
-              if (f == M || ar == f) E.Q[rowQ * n + uidx(D, b, k, cc)] += val;
             }
           }
           // w = t A_k + (G.p)[(ar,cr), ar-block]
           for (int b = 0; b < M; ++b) {
-            const double* ABb = E.AB + (k * M + b) * 48;
+            const double* DG_RESTRICT ABb = E.AB + (k * M + b) * 48;
             for (int j = 0; j < DG_NQA; ++j) {
               double acc = b == ar ? hc_ux(hc, cr, j) : 0.0;
               for (int i = 0; i < DG_NQA; ++i) acc += tv[b * DG_NQA + i] * ABb[i * 8 + j];
-              wr[b * DG_NQA + j] = acc;
+              wr[(f * nq + b * DG_NQA + j) * n] = acc;
             }
           }
         }
+        for (int b = 0; b < M; ++b)
+          for (int cc = 0; cc < 2; ++cc) Qm[rowQ * n + uidx(D, b, k, cc)] = a1A[b * 2 + cc] + a1M[b * 2 + cc];
       }
-      // V_k = lxx_k + A'VA + E.p   (into the other buffer)
-      DG_FOR(t, nq * nq) {
-        int i1 = t / nq, i2 = t - i1 * nq, b1 = i1 / DG_NQA, b2 = i2 / DG_NQA, c1 = i1 - b1 * DG_NQA, c2 = i2 - b2 * DG_NQA;
-        const double* A1 = E.AB + (k * M + b1) * 48;
-        const double* A2 = E.AB + (k * M + b2) * 48;
-        double acc = (f == M && k >= 1) ? con_lxx(D, l, k, i1, i2) : 0.0;
-        if (b1 == b2) acc += hc_xx(E.Hc + ((f * N + k) * M + b1) * 15, c1, c2);
-        for (int i = 0; i < DG_NQA; ++i) {
-          double rowacc = 0.0;
-          for (int j = 0; j < DG_NQA; ++j) rowacc += Vcur[(b1 * DG_NQA + i) * nq + b2 * DG_NQA + j] * A2[j * 8 + c2];
-          acc += A1[i * 8 + c1] * rowacc;
-        }
-        Vnext[t] = acc;
+    }
+    // V_k = lxx_k + A'VA + E.p  for every function (into the other buffer)
+    DG_FOR(t, F * nq * nq) {
+      int f = t / (nq * nq), e = t - f * nq * nq;
+      int i1 = e / nq, i2 = e - i1 * nq, b1 = i1 / DG_NQA, b2 = i2 / DG_NQA, c1 = i1 - b1 * DG_NQA, c2 = i2 - b2 * DG_NQA;
+      const double* DG_RESTRICT A1 = E.AB + (k * M + b1) * 48;
+      const double* DG_RESTRICT A2 = E.AB + (k * M + b2) * 48;
+      const double* DG_RESTRICT Vf = Vcur + f * nq * nq;
+      double acc = (f == M && k >= 1) ? con_lxx(D, l, k, i1, i2) : 0.0;
+      if (b1 == b2) acc += hc_xx(E.Hc + ((f * N + k) * M + b1) * 15, c1, c2);
+      for (int i = 0; i < DG_NQA; ++i) {
+        double rowacc = 0.0;
+        for (int j = 0; j < DG_NQA; ++j) rowacc += Vf[(b1 * DG_NQA + i) * nq + b2 * DG_NQA + j] * A2[j * 8 + c2];
+        acc += A1[i * 8 + c1] * rowacc;
       }
-      c.sync();
-      double* tmp = Vcur; Vcur = Vnext; Vnext = tmp;
+      Vnext[t] = acc;
     }
     c.sync();
+    double* tmp = Vcur; Vcur = Vnext; Vnext = tmp;
   }
 }

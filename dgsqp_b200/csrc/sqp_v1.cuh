@@ -31,6 +31,12 @@ struct SqpBuf {
 
 struct Workspace { EvalBuf E; LinBuf B; QpBuf Q; LsqrBuf L; SqpBuf S; };
 
+// Shared-memory scratch of one CTA (doubles): two n-vectors and the Cholesky panel.
+DG_HD size_t carve_shared(const Dims& D, double* sbase, Workspace& W) {
+  W.B.pv = sbase; W.B.wv = sbase ? sbase + D.n : nullptr; W.B.sp = sbase ? sbase + 2 * D.n : nullptr;
+  return (size_t)D.n * (2 + DG_CHOL_NB);
+}
+
 // Carve one CTA's workspace out of a flat double array; returns the number of doubles used.
 // Called with base == nullptr to measure.
 DG_HD size_t carve_workspace(const Dims& D, double* base, Workspace& W) {
@@ -39,13 +45,13 @@ DG_HD size_t carve_workspace(const Dims& D, double* base, Workspace& W) {
 #define CARVE(ptr, cnt) do { (ptr) = base ? base + off : nullptr; off += (((size_t)(cnt)) + 1) & ~(size_t)1; } while (0)
   CARVE(W.E.x, (N + 1) * nq); CARVE(W.E.AB, N * M * 48); CARVE(W.E.T2, N * M * 90);
   CARVE(W.E.S, M * N * 3 * 2 * N); CARVE(W.E.g, m); CARVE(W.E.q, n); CARVE(W.E.gtl, n);
-  CARVE(W.E.cst, (M + 1) * (N + 1) * nq); CARVE(W.E.Hc, (M + 1) * N * M * 15); CARVE(W.E.Vbuf, 2 * nq * nq);
-  CARVE(W.E.Q, n * n); CARVE(W.E.Wrow, n * nq); CARVE(W.E.tmpS, M * N * 3); CARVE(W.E.cf, M * N * 3);
-  CARVE(W.B.W, n * n); CARVE(W.B.dg, n); CARVE(W.B.od, n); CARVE(W.B.tau, n); CARVE(W.B.pv, n); CARVE(W.B.wv, n);
+  CARVE(W.E.cst, (M + 1) * (N + 1) * nq); CARVE(W.E.Hc, (M + 1) * N * M * 15); CARVE(W.E.Vbuf, 2 * (M + 1) * nq * nq);
+  CARVE(W.E.Q, n * n); CARVE(W.E.Wrow, (M + 1) * nq * n); CARVE(W.E.tmpS, M * N * 3); CARVE(W.E.cf, M * N * 3);
+  CARVE(W.B.W, n * n); CARVE(W.B.dg, n); CARVE(W.B.od, n); CARVE(W.B.od2, n); CARVE(W.B.tau, n);
   CARVE(W.B.lam, n); CARVE(W.B.Z, DG_EIG_CHUNK * n); CARVE(W.B.itw, DG_EIG_CHUNK * 5 * n);
-  W.Q.Jm = W.B.W;                       // the tridiagonalisation workspace is free once H is formed
+  W.Q.Y = W.B.W;                        // the tridiagonalisation workspace is free once H is formed
   CARVE(W.Q.Rm, n * n); CARVE(W.Q.xq, n); CARVE(W.Q.dv, n); CARVE(W.Q.zv, n); CARVE(W.Q.rv, n); CARVE(W.Q.npv, n);
-  CARVE(W.Q.hv, n); CARVE(W.Q.wv, n); CARVE(W.Q.lam_act, n); CARVE(W.Q.sl, m); CARVE(W.Q.lam, m);
+  CARVE(W.Q.lam_act, n); CARVE(W.Q.sl, m); CARVE(W.Q.lam, m);
   { double* t; CARVE(t, (n + 1) / 2 + 1); W.Q.act = (int*)t; CARVE(t, (m + 1) / 2 + 1); W.Q.is_act = (int*)t; }
   CARVE(W.L.Ub, DG_LSQR_BASIS * m); CARVE(W.L.Vb, DG_LSQR_BASIS * m); CARVE(W.L.cf, DG_LSQR_BASIS);
   CARVE(W.L.u, m); CARVE(W.L.v, m); CARVE(W.L.w, m); CARVE(W.L.x, m); CARVE(W.L.tn, n); CARVE(W.L.tm, m);
@@ -111,7 +117,8 @@ DG_DEV double merit_here(Cta& c, SolveCtx& X, const double* l, const double* s, 
   double p1 = 0.0, p2 = 0.0, p3 = 0.0;
   DG_FOR(i, D.n) { double d = E.q[i] + E.gtl[i]; p1 += d * d; }
   DG_FOR(r, D.m) { p2 += l[r] * E.g[r]; p3 += E.g[r] - (s[r] + (ds ? alpha * ds[r] : 0.0)); }
-  double dd = c.sum(p1), lg = c.sum(p2), vio = c.sum(p3);
+  c.sum3(p1, p2, p3);
+  double dd = p1, lg = p2, vio = p3;
   double val = 0.5 * (dd + lg * lg);
   if (X.P->merit_l1) val += mu * vio;
   return val;
@@ -143,7 +150,9 @@ DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du
   DG_FOR(r, m) {
     p3 += l_b[r] * E.g[r]; p4 += l_b[r] * S.Gdu[r]; p5 += dl[r] * E.g[r]; p6 += E.g[r] - s[r];
   }
-  double dd = c.sum(p1), dQ = c.sum(p2), lg = c.sum(p3), lGdu = c.sum(p4), dlg = c.sum(p5), vio = c.sum(p6);
+  c.sum3(p1, p2, p3);
+  c.sum3(p4, p5, p6);
+  double dd = p1, dQ = p2, lg = p3, lGdu = p4, dlg = p5, vio = p6;
   double dstat = dQ + lg * (lGdu + dlg);
   if (compute_mu) {
     mu = 0.0;
@@ -160,7 +169,7 @@ DG_DEVN int solve_qp_here(Cta& c, SolveCtx& X) {
   int nneg = nearest_pd(c, D.n, X.W.E.Q, X.W.S.Hm, X.W.B, X.P->eig_floor, X.P->reg, X.P->conv_approx != 0);
   if (nneg > X.n_neg_max) X.n_neg_max = nneg;
   int it = 0, na = 0;
-  int st = qp_solve_gi(c, D, X.W.E, X.W.S.Hm, X.W.E.q, X.W.Q, &it, &na);
+  int st = qp_solve_gi(c, D, X.W.E, X.W.S.Hm, X.W.E.q, X.W.Q, X.W.B, &it, &na);
   X.n_gi_iters += it;
   return st;
 }
@@ -304,9 +313,14 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
   while (true) {
     eval_full(c, X, S.u, S.l);
     double a1 = -1e300, a2 = 0.0, a3 = 0.0;
-    DG_FOR(r, m) { a1 = fmax(a1, E.g[r]); a2 = fmax(a2, fabs(E.g[r] * S.l[r])); }
-    DG_FOR(j, n) a3 = fmax(a3, fabs(E.q[j] + E.gtl[j]));
-    p_feas = fmax(0.0, c.max(a1)); comp = c.max(a2); stat = c.max(a3);
+    // NaN must not look like convergence (fmax drops NaNs): map it to +inf -> 'diverged'
+    DG_FOR(r, m) {
+      double gv = E.g[r], cv = fabs(gv * S.l[r]);
+      a1 = fmax(a1, gv != gv ? 1e300 : gv); a2 = fmax(a2, cv != cv ? 1e300 : cv);
+    }
+    DG_FOR(j, n) { double dv = fabs(E.q[j] + E.gtl[j]); a3 = fmax(a3, dv != dv ? 1e300 : dv); }
+    c.max3(a1, a2, a3);
+    p_feas = fmax(0.0, a1); comp = a2; stat = a3;
     c.sync();
     vcopy(c, n, S.u_im1, S.u); vcopy(c, m, S.l_im1, S.l);
     if (stat > P.diverge_tol) { status = ST_DIVERGED; break; }
@@ -329,7 +343,8 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
     double q1 = 0.0, q2 = 0.0;
     DG_FOR(j, n) { double d = S.u[j] - S.u_im1[j]; q1 += d * d; }
     DG_FOR(r, m) { double d = S.l[r] - S.l_im1[r]; q2 += d * d; }
-    double nu_ = sqrt(c.sum(q1)), nl_ = sqrt(c.sum(q2));
+    c.sum2(q1, q2);
+    double nu_ = sqrt(q1), nl_ = sqrt(q2);
     if (nu_ < P.p_tol / 2 && nl_ < P.d_tol / 2) {
       ++rel_its;
       if (rel_its >= P.rel_tol_req && p_feas < P.p_tol) { status = ST_CONV_REL; break; }

@@ -13,11 +13,13 @@ struct UnitArgs {
 };
 
 __global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArgs A) {
-  __shared__ double s_red[66];
+  __shared__ double s_red[320];
+  extern __shared__ double s_dyn[];
   Cta c; c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
-  c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red;
+  c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red; c.flip = 0;
   SolveCtx X; X.G = Gp; X.P = Pp; X.D = make_dims(Gp->M, Gp->N);
   carve_workspace(X.D, A.ws + (size_t)blockIdx.x * A.ws_stride, X.W);
+  carve_shared(X.D, s_dyn, X.W);
   const Dims& D = X.D; const int n = D.n, m = D.m;
   for (int inst = blockIdx.x; inst < A.B; inst += gridDim.x) {
     X.x0 = A.x0 + (size_t)inst * D.nq;
@@ -33,7 +35,7 @@ __global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArg
     DG_FOR(t, n * n) A.H[(size_t)inst * n * n + t] = X.W.S.Hm[t];
     c.sync();
     int it = 0, na = 0;
-    int st = qp_solve_gi(c, D, X.W.E, X.W.S.Hm, X.W.E.q, X.W.Q, &it, &na);
+    int st = qp_solve_gi(c, D, X.W.E, X.W.S.Hm, X.W.E.q, X.W.Q, X.W.B, &it, &na);
     DG_FOR(t, n) A.du[(size_t)inst * n + t] = X.W.Q.xq[t];
     DG_FOR(t, m) A.lam[(size_t)inst * m + t] = X.W.Q.lam[t];
     c.sync();
@@ -72,7 +74,8 @@ extern "C" int units_run(const dgsqp_racing_game* game, const dgsqp_params* para
   CK(cudaMalloc(&A.g, 8 * B * m)); CK(cudaMalloc(&A.du, 8 * B * n)); CK(cudaMalloc(&A.lam, 8 * B * m)); CK(cudaMalloc(&A.l0, 8 * B * m));
   CK(cudaMalloc(&A.nneg, 4 * B)); CK(cudaMalloc(&A.qpst, 4 * B)); CK(cudaMalloc(&A.qpit, 4 * B)); CK(cudaMalloc(&A.lsqr_it, 4 * B));
   cudaDeviceSetLimit(cudaLimitStackSize, 8192);
-  units_kernel<<<grid, threads>>>(dG, dP, A);
+  size_t smem = sizeof(double) * (size_t)D.n * (2 + DG_CHOL_NB);
+  units_kernel<<<grid, threads, smem>>>(dG, dP, A);
   CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(Q, A.Q, 8 * B * n * n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(H, A.H, 8 * B * n * n, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(q, A.q, 8 * B * n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(gtl, A.gtl, 8 * B * n, cudaMemcpyDeviceToHost));

@@ -11,7 +11,7 @@
 
 extern "C" {
 
-struct HsHandle { GameDesc G; SolverParams P; Dims D; std::vector<double> ws; Workspace W; };
+struct HsHandle { GameDesc G; SolverParams P; Dims D; std::vector<double> ws, sh; Workspace W; };
 
 void* hs_create(const dgsqp_racing_game* g, const dgsqp_params* p) {
   HsHandle* h = new HsHandle();
@@ -21,6 +21,8 @@ void* hs_create(const dgsqp_racing_game* g, const dgsqp_params* p) {
   size_t cnt = carve_workspace(h->D, nullptr, tmp);
   h->ws.assign(cnt, 0.0);
   carve_workspace(h->D, h->ws.data(), h->W);
+  h->sh.assign(carve_shared(h->D, nullptr, tmp), 0.0);
+  carve_shared(h->D, h->sh.data(), h->W);
   return h;
 }
 void hs_set_l0_perturb(void* hp, double v) { ((HsHandle*)hp)->P.dbg_l0_perturb = v; }
@@ -58,7 +60,7 @@ int hs_nearest_pd(void* hp, const double* Qin, double* Hout) {
 int hs_qp(void* hp, double* H, const double* q, double* du, double* lam, int* iters) {
   HsHandle* h = (HsHandle*)hp; Cta c;
   int na = 0;
-  int st = qp_solve_gi(c, h->D, h->W.E, H, q, h->W.Q, iters, &na);
+  int st = qp_solve_gi(c, h->D, h->W.E, H, q, h->W.Q, h->W.B, iters, &na);
   memcpy(du, h->W.Q.xq, sizeof(double) * h->D.n);
   memcpy(lam, h->W.Q.lam, sizeof(double) * h->D.m);
   return st;
