@@ -10,6 +10,9 @@ import pathlib
 MAX_AGENTS = 4
 MAX_TRACK_SEGS = 8
 
+PHASES = ["lin_full", "adj_full", "hessian", "pd_tridiag", "pd_eig", "cholesky", "tri_inverse", "active_set", "lsqr",
+          "lin_grad", "adj_grad", "merit", "other"]
+
 STATUS_MSG = {0: "conv_abs_tol", 1: "conv_rel_tol", 2: "max_it", 3: "diverged", 4: "qp_fail", 5: "time_limit"}
 
 
@@ -34,7 +37,7 @@ class ParamsStruct(C.Structure):
 
 
 EXPORTS = ["dgsqp_create", "dgsqp_destroy", "dgsqp_dims", "dgsqp_solve_batch", "dgsqp_solve_batch_async",
-           "dgsqp_last_diag", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_last_error", "dgsqp_version"]
+           "dgsqp_last_diag", "dgsqp_phase_count", "dgsqp_last_phase_cycles", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_last_error", "dgsqp_version"]
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "libdgsqp_b200.so"
 _lib = None
@@ -69,6 +72,10 @@ def load():
     lib.dgsqp_solve_batch_async.restype = C.c_int
     lib.dgsqp_last_diag.argtypes = [vp, C.c_int32, vp]
     lib.dgsqp_last_diag.restype = C.c_int
+    lib.dgsqp_phase_count.argtypes = []
+    lib.dgsqp_phase_count.restype = C.c_int
+    lib.dgsqp_last_phase_cycles.argtypes = [vp, C.c_int32, vp]
+    lib.dgsqp_last_phase_cycles.restype = C.c_int
     lib.dgsqp_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.dgsqp_measure_fp64_peak.restype = C.c_int
     lib.dgsqp_kernel_launches.argtypes = []

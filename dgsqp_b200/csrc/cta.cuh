@@ -13,6 +13,10 @@
 #include <math.h>
 #include <stdint.h>
 
+// phases of the per-instance profile (cycles, dgsqp_last_phase_cycles)
+enum { PH_LIN_FULL = 0, PH_ADJ_FULL, PH_HESS, PH_PD_TRIDIAG, PH_PD_EIG, PH_CHOL, PH_TRINV, PH_GI, PH_LSQR,
+       PH_LIN_GRAD, PH_ADJ_GRAD, PH_MERIT, PH_OTHER, DG_NPHASE };
+
 #ifdef DG_HOSTSIM
 #define DG_DEV static inline
 #define DG_HD static inline
@@ -37,6 +41,7 @@ struct Cta {
   inline void sum2(double& a, double& b) {}
   inline void sum3(double& a, double& b, double& d) {}
   inline void sum4(double& a, double& b, double& d, double& e) {}
+  inline void lap(int) {}
 };
 #else
 #define DG_DEV __device__ __forceinline__
@@ -48,6 +53,12 @@ struct Cta {
   int tid, nt, lane, warp, nwarps;
   static constexpr int wsz = 32;  // lanes per warp
   double* red;   // shared scratch: 2 buffers x 160 doubles
+  // phase profile: cycles between consecutive lap() calls are charged to the phase named by the later call
+  // (thread 0 only; counters live in shared memory: ph[0..DG_NPHASE) cycles, ph[DG_NPHASE] = time of the last lap)
+  long long* ph;
+  __device__ __forceinline__ void lap(int id) {
+    if (tid == 0) { long long t = clock64(); ph[id] += t - ph[DG_NPHASE]; ph[DG_NPHASE] = t; }
+  }
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

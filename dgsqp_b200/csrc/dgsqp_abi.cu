@@ -30,7 +30,7 @@ struct KernelArgs {
   int B;
   const double* x0; const double* u_ws; const double* l_ws;
   double* u_out; double* l_out; double* x_out; double* cost_out; double* cond_out;
-  int* num_iters; int* status; int* qp_solves; int* diag;
+  int* num_iters; int* status; int* qp_solves; int* diag; long long* phase;
   double* ws; size_t ws_stride;
   int* counter;
 };
@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256, 2) dgsqp_solve_kernel(const GameDesc* __r
   __shared__ double s_red[320];
   extern __shared__ double s_dyn[];
   __shared__ int s_inst;
+  __shared__ long long s_ph[DG_NPHASE + 1];
   {
     const int nw = (int)(sizeof(GameDesc) / sizeof(int));
     for (int i = threadIdx.x; i < nw; i += blockDim.x) ((int*)&sG)[i] = ((const int*)Gp)[i];
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256, 2) dgsqp_solve_kernel(const GameDesc* __r
   __syncthreads();
   Cta c;
   c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
-  c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red; c.flip = 0;
+  c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red; c.flip = 0; c.ph = s_ph;
   SolveCtx X;
   X.G = &sG; X.P = &sP; X.D = make_dims(sG.M, sG.N);
   carve_workspace(X.D, A.ws + (size_t)blockIdx.x * A.ws_stride, X.W);
@@ -72,7 +73,10 @@ __global__ void __launch_bounds__(256, 2) dgsqp_solve_kernel(const GameDesc* __r
     O.num_iters = A.num_iters + inst; O.status = A.status + inst; O.qp_solves = A.qp_solves + inst;
     O.diag = A.diag ? A.diag + (size_t)inst * 4 : nullptr;
     O.l_init = nullptr;
+    if (threadIdx.x == 0) { for (int i = 0; i < DG_NPHASE; ++i) s_ph[i] = 0; s_ph[DG_NPHASE] = clock64(); }
     sqp_solve_v1(c, X, A.u_ws + (size_t)inst * D.n, A.l_ws ? A.l_ws + (size_t)inst * D.m : nullptr, O);
+    c.lap(PH_OTHER);
+    if (threadIdx.x == 0 && A.phase) for (int i = 0; i < DG_NPHASE; ++i) A.phase[(size_t)inst * DG_NPHASE + i] = s_ph[i];
   }
 }
 
@@ -91,7 +95,7 @@ struct dgsqp_handle {
   GameDesc G; SolverParams P; Dims D;
   int device = 0, sm_count = 0, ctas_per_sm = 0, threads = 128, grid_cap = 0;
   size_t ws_doubles = 0, smem_bytes = 0;
-  double* d_ws = nullptr; int* d_counter = nullptr; int* d_diag = nullptr; size_t diag_cap = 0;
+  double* d_ws = nullptr; int* d_counter = nullptr; int* d_diag = nullptr; long long* d_phase = nullptr; size_t diag_cap = 0;
   GameDesc* d_G = nullptr; SolverParams* d_P = nullptr;
   // staging for host-pointer calls
   size_t stage_cap = 0;
@@ -171,7 +175,7 @@ int dgsqp_create(const dgsqp_racing_game* game, const dgsqp_params* params, int 
 int dgsqp_destroy(dgsqp_handle* h) {
   if (!h) return DGSQP_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_ws); cudaFree(h->d_counter); cudaFree(h->d_diag); cudaFree(h->d_G); cudaFree(h->d_P);
+  cudaFree(h->d_ws); cudaFree(h->d_counter); cudaFree(h->d_diag); cudaFree(h->d_phase); cudaFree(h->d_G); cudaFree(h->d_P);
   free_stage(h);
   delete h;
   return DGSQP_OK;
@@ -204,13 +208,15 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
   cudaStream_t st = (cudaStream_t)stream;
   if ((size_t)B > h->diag_cap) {
     if (h->d_diag) { cudaFree(h->d_diag); h->d_diag = nullptr; h->diag_cap = 0; }
+    if (h->d_phase) { cudaFree(h->d_phase); h->d_phase = nullptr; }
     CUDA_TRY(cudaMalloc(&h->d_diag, sizeof(int) * 4 * (size_t)B));
+    CUDA_TRY(cudaMalloc(&h->d_phase, sizeof(long long) * DG_NPHASE * (size_t)B));
     h->diag_cap = (size_t)B;
   }
   CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
   KernelArgs A;
   A.B = B; A.x0 = x0; A.u_ws = u_ws; A.l_ws = l_ws; A.u_out = u_out; A.l_out = l_out; A.x_out = x_out; A.cost_out = cost_out;
-  A.cond_out = cond_out; A.num_iters = num_iters; A.status = status; A.qp_solves = qp_solves; A.diag = h->d_diag;
+  A.cond_out = cond_out; A.num_iters = num_iters; A.status = status; A.qp_solves = qp_solves; A.diag = h->d_diag; A.phase = h->d_phase;
   A.ws = h->d_ws; A.ws_stride = h->ws_doubles; A.counter = h->d_counter;
   int grid = B < h->grid_cap ? B : h->grid_cap;
   dgsqp_solve_kernel<<<grid, h->threads, h->smem_bytes, st>>>(h->d_G, h->d_P, A);
@@ -304,6 +310,16 @@ int dgsqp_last_diag(dgsqp_handle* h, int32_t B, int32_t* diag) {
   if (B < 0 || (size_t)B > h->diag_cap) return set_err(DGSQP_EINVAL, "B exceeds the last batch size");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemcpy(diag, h->d_diag, sizeof(int) * 4 * (size_t)B, cudaMemcpyDeviceToHost));
+  return DGSQP_OK;
+}
+
+int dgsqp_phase_count(void) { return DG_NPHASE; }
+
+int dgsqp_last_phase_cycles(dgsqp_handle* h, int32_t B, int64_t* cycles) {
+  if (!h || !cycles) return set_err(DGSQP_EINVAL, "NULL argument");
+  if (B < 0 || (size_t)B > h->diag_cap) return set_err(DGSQP_EINVAL, "B exceeds the last batch size");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpy(cycles, h->d_phase, sizeof(long long) * DG_NPHASE * (size_t)B, cudaMemcpyDeviceToHost));
   return DGSQP_OK;
 }
 

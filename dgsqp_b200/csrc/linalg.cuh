@@ -207,6 +207,7 @@ DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, doubl
 DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, double* DG_RESTRICT Hm, const LinBuf& B,
                        double floor_val, double reg, bool conv_approx) {
   // symmetric part into W and Hm (thread = column: Qraw[i][j] coalesced, Qraw[j][i] strided but L1 resident)
+  c.lap(PH_OTHER);
   DG_FOR(t, n * n) {
     int i = t / n, j = t - i * n;
     double sv = 0.5 * (Qraw[i * n + j] + Qraw[j * n + i]);
@@ -216,6 +217,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, double* DG
   int nneg = 0;
   if (conv_approx) {
     sym_tridiag(c, n, B);
+    c.lap(PH_PD_TRIDIAG);
     double tn = 0.0;
     DG_FOR(i, n) {
       double r = fabs(B.dg[i]) + fabs(B.od[i]) + (i > 0 ? fabs(B.od[i - 1]) : 0.0);
@@ -300,6 +302,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, double* DG
   }
   if (reg > 0.0) { DG_FOR(i, n) Hm[i * n + i] += reg; }
   c.sync();
+  c.lap(PH_PD_EIG);
   return nneg;
 }
 

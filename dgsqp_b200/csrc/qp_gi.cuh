@@ -40,6 +40,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, double* DG_REST
   const int n = D.n, m = D.m;
   double* DG_RESTRICT Y = Q.Y;
   if (!cholesky_lower(c, n, Hm, B.sp)) return 1;
+  c.lap(PH_CHOL);
   tri_inverse(c, n, Hm, Y);
   // x = -J J' q = -Y' (Y q):   t = Y q (warp per row), x_i = -sum_j Y[j][i] t_j (thread per column)
   for (int j = c.warp; j < n; j += c.nwarps) {
@@ -58,6 +59,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, double* DG_REST
     for (; j < n; ++j) a0 += Y[j * n + i] * Q.dv[j];
     Q.xq[i] = -(a0 + a1);
   }
+  c.lap(PH_TRINV);
   int iq = 0, it = 0;
   const int max_iter = 10 * (n + m);
   int status = 0;
@@ -201,5 +203,6 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, double* DG_REST
   }
   if (n_iter_out) *n_iter_out = it;
   if (n_active_out) *n_active_out = iq;
+  c.lap(PH_GI);
   return status;
 }

@@ -78,10 +78,12 @@ struct SolveCtx {
 DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l) {
   const Dims& D = X.D; const EvalBuf& E = X.W.E;
   c.sync();
+  c.lap(PH_OTHER);
   game_rollout(c, *X.G, D, u, X.x0, E.x);
   c.sync();
   game_linearize(c, *X.G, D, u, E, true);
   c.sync();
+  c.lap(PH_LIN_FULL);
   game_constraints(c, *X.G, D, u, X.W.S.up, E.x, E.g);
   game_costates(c, *X.G, D, E, l);
   game_sens(c, D, E);
@@ -89,7 +91,9 @@ DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l) {
   game_contract(c, D, E);
   game_gradients(c, *X.G, D, E, u, X.W.S.up, l);
   c.sync();
+  c.lap(PH_ADJ_FULL);
   game_hessian(c, *X.G, D, E, l);
+  c.lap(PH_HESS);
   ++X.n_evals_full;
 }
 
@@ -97,16 +101,19 @@ DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l) {
 DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l, bool with_sens) {
   const Dims& D = X.D; const EvalBuf& E = X.W.E;
   c.sync();
+  c.lap(PH_OTHER);
   game_rollout(c, *X.G, D, u, X.x0, E.x);
   c.sync();
   game_linearize(c, *X.G, D, u, E, false);
   c.sync();
+  c.lap(PH_LIN_GRAD);
   game_constraints(c, *X.G, D, u, X.W.S.up, E.x, E.g);
   game_costates(c, *X.G, D, E, l);
   if (with_sens) game_sens(c, D, E);
   c.sync();
   game_gradients(c, *X.G, D, E, u, X.W.S.up, l);
   c.sync();
+  c.lap(PH_ADJ_GRAD);
   ++X.n_evals_grad;
 }
 
@@ -121,6 +128,7 @@ DG_DEV double merit_here(Cta& c, SolveCtx& X, const double* l, const double* s, 
   double dd = p1, lg = p2, vio = p3;
   double val = 0.5 * (dd + lg * lg);
   if (X.P->merit_l1) val += mu * vio;
+  c.lap(PH_MERIT);
   return val;
 }
 
@@ -130,6 +138,7 @@ DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du
                         double* dl, double* s, double* ds, bool compute_mu, double& mu, double& phi, double& dphi) {
   const Dims& D = X.D; const EvalBuf& E = X.W.E; SqpBuf& S = X.W.S;
   const int n = D.n, m = D.m;
+  c.lap(PH_OTHER);
   game_G_times(c, D, E, du, S.Gdu);
   DG_FOR(r, m) {
     dl[r] = l_hat[r] - l_b[r];
@@ -161,6 +170,7 @@ DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du
   phi = 0.5 * (dd + lg * lg);
   dphi = dstat;
   if (X.P->merit_l1) { phi += mu * vio; dphi -= mu * vio; }
+  c.lap(PH_MERIT);
 }
 
 // _solve_qp at the currently evaluated point.  Result in W.Q.xq / W.Q.lam.  Returns 0 on success.
@@ -302,6 +312,7 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
   } else {
     eval_grad(c, X, S.u, S.l, true);
     lsqr_dual_init(c, D, E, X.W.L, E.q, S.l);
+    c.lap(PH_LSQR);
   }
   if (P.dbg_l0_perturb != 0.0) {
     DG_FOR(r, m) S.l[r] *= 1.0 + P.dbg_l0_perturb * (2.0 * (double)((r * 2654435761u) % 1000u) / 1000.0 - 1.0);

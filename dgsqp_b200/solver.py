@@ -229,5 +229,13 @@ class DGSQP:
         _abi.check(self._lib.dgsqp_last_diag(self._h, B, d.ctypes.data_as(C.c_void_p)))
         return d
 
+    def last_phase_cycles(self, B):
+        """[B, len(_abi.PHASES)] int64 SM-clock cycles spent per solver phase -- of the last solve_batch."""
+        k = self._lib.dgsqp_phase_count()
+        assert k == len(_abi.PHASES)
+        d = np.empty((B, k), dtype=np.int64)
+        _abi.check(self._lib.dgsqp_last_phase_cycles(self._h, B, d.ctypes.data_as(C.c_void_p)))
+        return d
+
     def configure(self, ctas_per_sm=0, threads=0):
         _abi.check(self._lib.dgsqp_configure(self._h, int(ctas_per_sm), int(threads)))

@@ -120,6 +120,14 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
  * full evaluations, gradient-only evaluations, QP active-set iterations, max #negative eigenvalues. */
 int dgsqp_last_diag(dgsqp_handle* h, int32_t B, int32_t* diag);
 
+/* Per-instance phase profile of the LAST solve_batch: dgsqp_phase_count() SM-clock cycle counters per
+ * instance (order: rollout+derivatives [full], adjoints/sensitivities [full], Hessian DP, tridiagonalisation,
+ * negative eigenpairs, Cholesky, triangular inverse, active-set loop, LSQR, rollout+Jacobians [gradient-only],
+ * adjoints [gradient-only], merit, other).  Replaces the reference's verbose per-phase wall-clock prints
+ * (DGSQP.py:233,261,349,443,510,525). */
+int dgsqp_phase_count(void);
+int dgsqp_last_phase_cycles(dgsqp_handle* h, int32_t B, int64_t* cycles);
+
 /* Measures the device's sustained FP64 FMA throughput (TFLOP/s, 2 flops per FMA) with a register-only
  * probe kernel: the roofline denominator for this FP64-bound path. */
 int dgsqp_measure_fp64_peak(int device, double* tflops);

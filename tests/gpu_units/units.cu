@@ -14,9 +14,10 @@ struct UnitArgs {
 
 __global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArgs A) {
   __shared__ double s_red[320];
+  __shared__ long long s_ph[DG_NPHASE + 1];
   extern __shared__ double s_dyn[];
   Cta c; c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
-  c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red; c.flip = 0;
+  c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red; c.flip = 0; c.ph = s_ph;
   SolveCtx X; X.G = Gp; X.P = Pp; X.D = make_dims(Gp->M, Gp->N);
   carve_workspace(X.D, A.ws + (size_t)blockIdx.x * A.ws_stride, X.W);
   carve_shared(X.D, s_dyn, X.W);
