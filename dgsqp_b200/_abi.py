@@ -10,6 +10,7 @@ import pathlib
 MAX_AGENTS = 4
 MAX_TRACK_SEGS = 8
 
+NDIAG = 8   # DGSQP_NDIAG
 PHASES = ["lin_full", "adj_full", "hessian", "pd_tridiag", "pd_eig", "cholesky", "tri_inverse", "active_set", "lsqr",
           "lin_grad", "adj_grad", "merit", "other"]
 
@@ -37,7 +38,7 @@ class ParamsStruct(C.Structure):
 
 
 EXPORTS = ["dgsqp_create", "dgsqp_destroy", "dgsqp_dims", "dgsqp_solve_batch", "dgsqp_solve_batch_async",
-           "dgsqp_last_diag", "dgsqp_phase_count", "dgsqp_last_phase_cycles", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_last_error", "dgsqp_version"]
+           "dgsqp_last_diag", "dgsqp_phase_count", "dgsqp_last_phase_cycles", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_memory_plan", "dgsqp_set_smem_limit", "dgsqp_last_error", "dgsqp_version"]
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "libdgsqp_b200.so"
 _lib = None
@@ -82,6 +83,10 @@ def load():
     lib.dgsqp_kernel_launches.restype = C.c_int64
     lib.dgsqp_configure.argtypes = [vp, C.c_int32, C.c_int32]
     lib.dgsqp_configure.restype = C.c_int
+    lib.dgsqp_memory_plan.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.dgsqp_memory_plan.restype = C.c_int
+    lib.dgsqp_set_smem_limit.argtypes = [vp, C.c_int64]
+    lib.dgsqp_set_smem_limit.restype = C.c_int
     lib.dgsqp_last_error.argtypes = []
     lib.dgsqp_last_error.restype = C.c_char_p
     lib.dgsqp_version.argtypes = []

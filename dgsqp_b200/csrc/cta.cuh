@@ -70,41 +70,44 @@ struct Cta {
   int flip = 0;
   __device__ __forceinline__ double* next_buf() { flip ^= 1; return red + flip * 160; }
   __device__ __forceinline__ void syncwarp() { __syncwarp(); }
+  // sum of the nwarps (<= 16) per-warp partials at b[0..]: fixed pairwise tree, identical in every thread
+  __device__ __forceinline__ double tree16(const double* b) const {
+    double t[16];
+#pragma unroll
+    for (int w = 0; w < 16; ++w) t[w] = w < nwarps ? b[w] : 0.0;
+#pragma unroll
+    for (int s = 8; s > 0; s >>= 1)
+#pragma unroll
+      for (int w = 0; w < s; ++w) t[w] += t[w + s];
+    return t[0];
+  }
   __device__ __forceinline__ double sum(double v) {
     v = warp_sum(v);
     double* b = next_buf();
     if (lane == 0) b[warp] = v;
     __syncthreads();
-    double r = 0.0;
-    for (int w = 0; w < nwarps; ++w) r += b[w];     // same order in every thread -> identical result
-    return r;
+    return tree16(b);
   }
   __device__ __forceinline__ void sum2(double& a0, double& a1) {
     a0 = warp_sum(a0); a1 = warp_sum(a1);
     double* b = next_buf();
     if (lane == 0) { b[warp] = a0; b[32 + warp] = a1; }
     __syncthreads();
-    double r0 = 0.0, r1 = 0.0;
-    for (int w = 0; w < nwarps; ++w) { r0 += b[w]; r1 += b[32 + w]; }
-    a0 = r0; a1 = r1;
+    a0 = tree16(b); a1 = tree16(b + 32);
   }
   __device__ __forceinline__ void sum3(double& a0, double& a1, double& a2) {
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     double* b = next_buf();
     if (lane == 0) { b[warp] = a0; b[32 + warp] = a1; b[64 + warp] = a2; }
     __syncthreads();
-    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-    for (int w = 0; w < nwarps; ++w) { r0 += b[w]; r1 += b[32 + w]; r2 += b[64 + w]; }
-    a0 = r0; a1 = r1; a2 = r2;
+    a0 = tree16(b); a1 = tree16(b + 32); a2 = tree16(b + 64);
   }
   __device__ __forceinline__ void sum4(double& a0, double& a1, double& a2, double& a3) {
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
     double* b = next_buf();
     if (lane == 0) { b[warp] = a0; b[32 + warp] = a1; b[64 + warp] = a2; b[96 + warp] = a3; }
     __syncthreads();
-    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
-    for (int w = 0; w < nwarps; ++w) { r0 += b[w]; r1 += b[32 + w]; r2 += b[64 + w]; r3 += b[96 + w]; }
-    a0 = r0; a1 = r1; a2 = r2; a3 = r3;
+    a0 = tree16(b); a1 = tree16(b + 32); a2 = tree16(b + 64); a3 = tree16(b + 96);
   }
   __device__ __forceinline__ double max(double v) {
 #pragma unroll
@@ -171,3 +174,20 @@ struct Cta {
 #endif
 
 #define DG_FOR(i, n) for (int i = c.tid; i < (n); i += c.nt)
+// same loop with the thread numbering rotated by `off`: lets independent phases inside one barrier interval run on
+// different warps instead of piling up on the low thread ids
+#define DG_FOR_OFF(i, n, off) for (int i = (c.tid + c.nt - ((off) % c.nt)) % c.nt; i < (n); i += c.nt)
+
+// 2D decomposition of a (len columns) x (depth) iteration space over the CTA: consecutive threads own consecutive
+// columns (conflict-free / coalesced), the G column groups interleave the depth index.
+//   for (int i = s.i0; i < len; i += s.istep) for (int j = j_begin + s.g; j < j_end; j += s.G) ...
+struct Split2 { int i0, istep, g, G; };
+DG_DEV Split2 split2(const Cta& c, int len) {
+  int cw = (len + Cta::wsz - 1) / Cta::wsz * Cta::wsz;
+  if (cw > c.nt) cw = c.nt;
+  if (cw < 1) cw = 1;
+  Split2 s;
+  s.G = c.nt / cw; s.g = c.tid / cw; s.i0 = c.tid - s.g * cw; s.istep = cw;
+  if (s.g >= s.G) s.i0 = len;                  // leftover threads idle
+  return s;
+}

@@ -13,6 +13,7 @@
 #include "sqp_v1.cuh"
 #include "host_setup.h"
 
+#define DG_MAX_THREADS 512
 #define DGSQP_VERSION_STR "dgsqp_b200 0.1.0 (sm_100a)"
 
 static thread_local std::string g_last_error;
@@ -31,11 +32,11 @@ struct KernelArgs {
   const double* x0; const double* u_ws; const double* l_ws;
   double* u_out; double* l_out; double* x_out; double* cost_out; double* cond_out;
   int* num_iters; int* status; int* qp_solves; int* diag; long long* phase;
-  double* ws; size_t ws_stride;
+  double* ws; size_t ws_stride; size_t smem_doubles;
   int* counter;
 };
 
-__global__ void __launch_bounds__(256, 2) dgsqp_solve_kernel(const GameDesc* __restrict__ Gp, const SolverParams* __restrict__ Pp, KernelArgs A) {
+__global__ void __launch_bounds__(DG_MAX_THREADS, 1) dgsqp_solve_kernel(const GameDesc* __restrict__ Gp, const SolverParams* __restrict__ Pp, KernelArgs A) {
   __shared__ GameDesc sG;
   __shared__ SolverParams sP;
   __shared__ double s_red[320];
@@ -54,8 +55,7 @@ __global__ void __launch_bounds__(256, 2) dgsqp_solve_kernel(const GameDesc* __r
   c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red; c.flip = 0; c.ph = s_ph;
   SolveCtx X;
   X.G = &sG; X.P = &sP; X.D = make_dims(sG.M, sG.N);
-  carve_workspace(X.D, A.ws + (size_t)blockIdx.x * A.ws_stride, X.W);
-  carve_shared(X.D, s_dyn, X.W);
+  plan_memory(X.D, A.ws + (size_t)blockIdx.x * A.ws_stride, s_dyn, A.smem_doubles, X.W);
   const Dims& D = X.D;
   while (true) {
     if (threadIdx.x == 0) s_inst = atomicAdd(A.counter, 1);
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256, 2) dgsqp_solve_kernel(const GameDesc* __r
     O.cost = A.cost_out + (size_t)inst * D.M;
     O.cond = A.cond_out + (size_t)inst * 3;
     O.num_iters = A.num_iters + inst; O.status = A.status + inst; O.qp_solves = A.qp_solves + inst;
-    O.diag = A.diag ? A.diag + (size_t)inst * 4 : nullptr;
+    O.diag = A.diag ? A.diag + (size_t)inst * DG_NDIAG : nullptr;
     O.l_init = nullptr;
     if (threadIdx.x == 0) { for (int i = 0; i < DG_NPHASE; ++i) s_ph[i] = 0; s_ph[DG_NPHASE] = clock64(); }
     sqp_solve_v1(c, X, A.u_ws + (size_t)inst * D.n, A.l_ws ? A.l_ws + (size_t)inst * D.m : nullptr, O);
@@ -93,8 +93,9 @@ __global__ void dgsqp_fp64_probe_kernel(double* out, int iters, double a, double
 
 struct dgsqp_handle {
   GameDesc G; SolverParams P; Dims D;
-  int device = 0, sm_count = 0, ctas_per_sm = 0, threads = 128, grid_cap = 0;
-  size_t ws_doubles = 0, smem_bytes = 0;
+  int device = 0, sm_count = 0, ctas_per_sm = 0, threads = 256, grid_cap = 0;
+  size_t ws_doubles = 0, smem_bytes = 0, smem_budget = 0, smem_limit = 0;   // budget/limit in doubles (0 limit = device maximum)
+  MemPlan plan; size_t ws_alloc = 0;
   double* d_ws = nullptr; int* d_counter = nullptr; int* d_diag = nullptr; long long* d_phase = nullptr; size_t diag_cap = 0;
   GameDesc* d_G = nullptr; SolverParams* d_P = nullptr;
   // staging for host-pointer calls
@@ -114,17 +115,30 @@ static void free_stage(dgsqp_handle* h) {
 
 static int ensure_grid(dgsqp_handle* h) {
   int occ = 0;
-  h->smem_bytes = sizeof(double) * (size_t)h->D.n * (2 + DG_CHOL_NB);
+  {
+    // shared-memory budget of one CTA: the opt-in maximum minus the kernel's static shared memory
+    int optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, dgsqp_solve_kernel));
+    size_t avail = (size_t)optin > fa.sharedSizeBytes + 64 ? ((size_t)optin - fa.sharedSizeBytes - 64) / sizeof(double) : 0;
+    if (h->smem_limit && h->smem_limit < avail) avail = h->smem_limit;
+    h->smem_budget = avail;
+    Workspace tmp;
+    h->plan = plan_memory(h->D, nullptr, nullptr, h->smem_budget, tmp);
+    h->ws_doubles = h->plan.gmem;
+    h->smem_bytes = sizeof(double) * h->plan.smem;
+  }
   CUDA_TRY(cudaFuncSetAttribute(dgsqp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dgsqp_solve_kernel, h->threads, h->smem_bytes));
   if (occ < 1) return set_err(DGSQP_ECUDA, "kernel does not fit on an SM");
   int per_sm = h->ctas_per_sm > 0 ? (h->ctas_per_sm < occ ? h->ctas_per_sm : occ) : occ;
   int cap = per_sm * h->sm_count;
-  if (cap != h->grid_cap) {
+  if (cap != h->grid_cap || h->ws_doubles != h->ws_alloc) {
     if (h->d_ws) { cudaFree(h->d_ws); h->d_ws = nullptr; }
     CUDA_TRY(cudaMalloc(&h->d_ws, sizeof(double) * h->ws_doubles * (size_t)cap));
     CUDA_TRY(cudaMemset(h->d_ws, 0, sizeof(double) * h->ws_doubles * (size_t)cap));
-    h->grid_cap = cap;
+    h->grid_cap = cap; h->ws_alloc = h->ws_doubles;
   }
   return 0;
 }
@@ -157,8 +171,6 @@ int dgsqp_create(const dgsqp_racing_game* game, const dgsqp_params* params, int 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = set_err(DGSQP_ECUDA, "cudaGetDeviceProperties failed"); break; }
     h->sm_count = prop.multiProcessorCount;
-    Workspace tmp;
-    h->ws_doubles = carve_workspace(h->D, nullptr, tmp);
     if (cudaMalloc(&h->d_G, sizeof(GameDesc)) != cudaSuccess || cudaMalloc(&h->d_P, sizeof(SolverParams)) != cudaSuccess ||
         cudaMalloc(&h->d_counter, sizeof(int)) != cudaSuccess) { rc = set_err(DGSQP_ENOMEM, "device allocation failed"); break; }
     cudaMemcpy(h->d_G, &h->G, sizeof(GameDesc), cudaMemcpyHostToDevice);
@@ -189,7 +201,7 @@ int dgsqp_dims(const dgsqp_handle* h, int32_t dims[4]) {
 
 int dgsqp_configure(dgsqp_handle* h, int32_t ctas_per_sm, int32_t threads) {
   if (!h) return set_err(DGSQP_EINVAL, "NULL handle");
-  if (threads != 0 && (threads < 32 || threads > 1024 || (threads & 31))) return set_err(DGSQP_EINVAL, "threads must be a multiple of 32 in [32,1024]");
+  if (threads != 0 && (threads < 32 || threads > DG_MAX_THREADS || (threads & 31))) return set_err(DGSQP_EINVAL, "threads must be a multiple of 32 in [32,512]");
   CUDA_TRY(cudaSetDevice(h->device));
   h->ctas_per_sm = ctas_per_sm;
   if (threads) h->threads = threads;
@@ -209,7 +221,7 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
   if ((size_t)B > h->diag_cap) {
     if (h->d_diag) { cudaFree(h->d_diag); h->d_diag = nullptr; h->diag_cap = 0; }
     if (h->d_phase) { cudaFree(h->d_phase); h->d_phase = nullptr; }
-    CUDA_TRY(cudaMalloc(&h->d_diag, sizeof(int) * 4 * (size_t)B));
+    CUDA_TRY(cudaMalloc(&h->d_diag, sizeof(int) * DG_NDIAG * (size_t)B));
     CUDA_TRY(cudaMalloc(&h->d_phase, sizeof(long long) * DG_NPHASE * (size_t)B));
     h->diag_cap = (size_t)B;
   }
@@ -217,7 +229,7 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
   KernelArgs A;
   A.B = B; A.x0 = x0; A.u_ws = u_ws; A.l_ws = l_ws; A.u_out = u_out; A.l_out = l_out; A.x_out = x_out; A.cost_out = cost_out;
   A.cond_out = cond_out; A.num_iters = num_iters; A.status = status; A.qp_solves = qp_solves; A.diag = h->d_diag; A.phase = h->d_phase;
-  A.ws = h->d_ws; A.ws_stride = h->ws_doubles; A.counter = h->d_counter;
+  A.ws = h->d_ws; A.ws_stride = h->ws_doubles; A.smem_doubles = h->smem_budget; A.counter = h->d_counter;
   int grid = B < h->grid_cap ? B : h->grid_cap;
   dgsqp_solve_kernel<<<grid, h->threads, h->smem_bytes, st>>>(h->d_G, h->d_P, A);
   g_launches.fetch_add(1);
@@ -309,7 +321,21 @@ int dgsqp_last_diag(dgsqp_handle* h, int32_t B, int32_t* diag) {
   if (!h || !diag) return set_err(DGSQP_EINVAL, "NULL argument");
   if (B < 0 || (size_t)B > h->diag_cap) return set_err(DGSQP_EINVAL, "B exceeds the last batch size");
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(cudaMemcpy(diag, h->d_diag, sizeof(int) * 4 * (size_t)B, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(diag, h->d_diag, sizeof(int) * DG_NDIAG * (size_t)B, cudaMemcpyDeviceToHost));
+  return DGSQP_OK;
+}
+
+int dgsqp_set_smem_limit(dgsqp_handle* h, int64_t bytes) {
+  if (!h || bytes < 0) return set_err(DGSQP_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->smem_limit = bytes == 0 ? 0 : (size_t)bytes / sizeof(double) + 1;
+  return ensure_grid(h);
+}
+
+int dgsqp_memory_plan(const dgsqp_handle* h, int64_t out[4]) {
+  if (!h || !out) return set_err(DGSQP_EINVAL, "NULL argument");
+  out[0] = (int64_t)(h->plan.smem * sizeof(double)); out[1] = (int64_t)(h->plan.gmem * sizeof(double));
+  out[2] = h->plan.mats_in_smem; out[3] = h->plan.sens_in_smem;
   return DGSQP_OK;
 }
 

@@ -17,122 +17,139 @@
 #include "cta.cuh"
 
 #define DG_EIG_CHUNK 16     // eigenvectors computed concurrently by inverse iteration
+#define DG_EIG_INVIT 3      // inverse-iteration sweeps per eigenvector (shifts are accurate to ~1 ulp of |T|)
 #define DG_CHOL_NB 8        // Cholesky panel width
+#ifndef DG_MAX_THREADS
+#define DG_MAX_THREADS 512
+#endif
 
 struct LinBuf {
-  double* W;      // n*n   tridiagonalisation workspace (holds the reflectors afterwards)
+  int ld;         // leading dimension of matA / matB
+  double* matA;   // n*ld  tridiagonalisation workspace W (reflectors) -> H = nearestPD + reg I -> Cholesky factor L
+  double* matB;   // n*ld  inverse-iteration scratch + eigenvectors (during nearest_pd) -> J' of the QP (qp_gi.cuh)
+  double* Zg;     // n*n   global spill for the eigenvectors when they do not fit beside the scratch in matB
+  // phase-aliased small vectors (one region of 8n doubles, see plan_memory)
   double* dg;     // n     tridiagonal diagonal
   double* od;     // n     off-diagonal (od[k] couples k, k+1)
   double* od2;    // n     od^2
   double* tau;    // n
   double* lam;    // n     negative eigenvalues (ascending)
-  double* Z;      // DG_EIG_CHUNK*n  eigenvectors of the chunk
-  double* itw;    // DG_EIG_CHUNK*5*n  inverse-iteration factor storage
-  // shared memory scratch
   double* pv;     // n
   double* wv;     // n
-  double* sp;     // n*DG_CHOL_NB  Cholesky panel
+  double* sp;     // n*DG_CHOL_NB  Cholesky panel (aliases the seven vectors above)
+  double* part;   // max(DG_MAX_THREADS, n)  partial sums of the 2D-decomposed products
 };
 
-// Householder reduction of the symmetric matrix W (full storage, both triangles kept consistent)
+// Householder reduction of the symmetric matrix W = B.matA (full storage, both triangles kept consistent)
 // to tridiagonal form; reflector k is stored in W[k+2.., k] (v[0] = 1 implicit) with tau[k].
-// Three barriers per step: [trailing update + next norm], [matvec + dot], [w ready].
+// Both O(len^2) parts of a step -- p = tau A22 v and A22 -= v w' + w v' -- are spread over the whole CTA with the 2D
+// decomposition (thread = column, column groups interleave the rows).  Four barriers per step.
 DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B) {
-  double* DG_RESTRICT W = B.W;
+  double* DG_RESTRICT W = B.matA;
+  const int ld = B.ld;
   double* DG_RESTRICT pv = B.pv;
   double* DG_RESTRICT wv = B.wv;
+  double* DG_RESTRICT part = B.part;
   // norm of the first column below the sub-diagonal
-  double part = 0.0;
-  for (int i = c.tid + 2; i < n; i += c.nt) { double xv = W[i * n]; part += xv * xv; }
-  double xn2 = c.sum(part);
+  double nrm = 0.0;
+  for (int i = c.tid + 2; i < n; i += c.nt) { double xv = W[i * ld]; nrm += xv * xv; }
+  double xn2 = c.sum(nrm);
   for (int k = 0; k + 1 < n; ++k) {
     const int len = n - k - 1;            // x = W[k+1.., k]
     const int off = k + 1;
-    const double alpha = W[off * n + k];
+    const double alpha = W[off * ld + k];
     double tauk = 0.0, beta = alpha, scale = 0.0;
     if (xn2 > 0.0) {
       beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
       tauk = (beta - alpha) / beta;
       scale = 1.0 / (alpha - beta);
     }
-    if (c.tid == 0) { B.dg[k] = W[k * n + k]; B.od[k] = beta; B.od2[k] = beta * beta; B.tau[k] = tauk; }
+    if (c.tid == 0) { B.dg[k] = W[k * ld + k]; B.od[k] = beta; B.od2[k] = beta * beta; B.tau[k] = tauk; }
     if (tauk == 0.0) {
       // nothing to annihilate: next column norm straight from memory
-      part = 0.0;
-      for (int i = c.tid + 2; i < len; i += c.nt) { double xv = W[(off + i) * n + off]; part += xv * xv; }
-      xn2 = c.sum(part);
+      nrm = 0.0;
+      for (int i = c.tid + 2; i < len; i += c.nt) { double xv = W[(off + i) * ld + off]; nrm += xv * xv; }
+      xn2 = c.sum(nrm);
       continue;
     }
-    // p = tau * A22 v with v_j = (j == 0 ? 1 : W[off+j][k] * scale); thread i owns column i (coalesced)
-    double pdot = 0.0;
-    DG_FOR(i, len) {
-      const double* DG_RESTRICT col = W + off * n + off + i;
-      const double* DG_RESTRICT vc = W + off * n + k;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int j = 1;
-      for (; j + 4 <= len; j += 4) {
-        a0 += col[(j + 0) * n] * vc[(j + 0) * n];
-        a1 += col[(j + 1) * n] * vc[(j + 1) * n];
-        a2 += col[(j + 2) * n] * vc[(j + 2) * n];
-        a3 += col[(j + 3) * n] * vc[(j + 3) * n];
-      }
-      for (; j < len; ++j) a1 += col[j * n] * vc[j * n];
-      // only the j >= 1 terms carry the scale factor
-      double acc = (col[0] + scale * ((a0 + a1) + (a2 + a3))) * tauk;            // j = 0 term has v_0 = 1
-      double vi = i == 0 ? 1.0 : vc[i * n] * scale;
-      pv[i] = vi;
-      wv[i] = acc;
-      pdot += acc * vi;
-    }
-    const double hk = 0.5 * tauk * c.sum(pdot);
-    DG_FOR(i, len) {
-      wv[i] -= hk * pv[i];
-      if (i > 0) W[(off + i) * n + k] = pv[i];                    // keep the reflector
+    const Split2 sp = split2(c, len);
+    const double* DG_RESTRICT vc = W + off * ld + k;            // x_j = vc[j*ld]
+    // partial products  sum_{j>=1, j = g (mod G)} A22[j][i] x_j   (the j = 0 term has v_0 = 1 and no scale)
+    for (int i = sp.i0; i < len; i += sp.istep) {
+      const double* DG_RESTRICT col = W + off * ld + off + i;
+      double a0 = 0.0, a1 = 0.0;
+      int j = sp.g == 0 ? sp.G : sp.g;
+      for (; j + sp.G < len; j += 2 * sp.G) { a0 += col[j * ld] * vc[j * ld]; a1 += col[(j + sp.G) * ld] * vc[(j + sp.G) * ld]; }
+      if (j < len) a0 += col[j * ld] * vc[j * ld];
+      part[sp.g * sp.istep + i] = a0 + a1;
     }
     c.sync();
-    // A22 -= v w' + w v'   (thread per column); accumulate the next column norm on the fly
-    part = 0.0;
-    DG_FOR(j, len) {
-      const double vj = pv[j], wj = wv[j];
-      double* DG_RESTRICT col = W + off * n + off + j;
-      int i = 0;
-      for (; i + 4 <= len; i += 4) {
-        double c0 = col[(i + 0) * n], c1 = col[(i + 1) * n], c2 = col[(i + 2) * n], c3 = col[(i + 3) * n];
-        c0 -= pv[i + 0] * wj + wv[i + 0] * vj;
-        c1 -= pv[i + 1] * wj + wv[i + 1] * vj;
-        c2 -= pv[i + 2] * wj + wv[i + 2] * vj;
-        c3 -= pv[i + 3] * wj + wv[i + 3] * vj;
-        col[(i + 0) * n] = c0; col[(i + 1) * n] = c1; col[(i + 2) * n] = c2; col[(i + 3) * n] = c3;
+    double pdot = 0.0;
+    if (sp.g == 0) {
+      for (int i = sp.i0; i < len; i += sp.istep) {
+        double acc = part[i];
+        for (int g = 1; g < sp.G; ++g) acc += part[g * sp.istep + i];
+        const double pi = (W[off * ld + off + i] + scale * acc) * tauk;
+        const double vi = i == 0 ? 1.0 : vc[i * ld] * scale;
+        pv[i] = vi; wv[i] = pi;
+        pdot += pi * vi;
       }
-      for (; i < len; ++i) col[i * n] -= pv[i] * wj + wv[i] * vj;
-      // next step's x is column 0 of the updated block below its sub-diagonal == row 0, columns >= 2
-      if (j >= 2) { double xv = col[0]; part += xv * xv; }
     }
-    xn2 = c.sum(part);
+    const double hk = 0.5 * tauk * c.sum(pdot);
+    if (sp.g == 0) {
+      for (int i = sp.i0; i < len; i += sp.istep) {
+        wv[i] -= hk * pv[i];
+        if (i > 0) W[(off + i) * ld + k] = pv[i];                  // keep the reflector
+      }
+    }
+    c.sync();
+    // A22 -= v w' + w v'; the next column norm (row 0 of the updated block, columns >= 2) on the fly
+    nrm = 0.0;
+    for (int j = sp.i0; j < len; j += sp.istep) {
+      const double vj = pv[j], wj = wv[j];
+      double* DG_RESTRICT col = W + off * ld + off + j;
+      for (int i = sp.g; i < len; i += sp.G) {
+        const double cv = col[i * ld] - (pv[i] * wj + wv[i] * vj);
+        col[i * ld] = cv;
+        if (i == 0 && j >= 2) nrm += cv * cv;
+      }
+    }
+    xn2 = c.sum(nrm);
   }
-  if (c.tid == 0) { B.dg[n - 1] = W[(n - 1) * n + (n - 1)]; B.od[n - 1] = 0.0; B.od2[n - 1] = 0.0; }
+  if (c.tid == 0) { B.dg[n - 1] = W[(n - 1) * ld + (n - 1)]; B.od[n - 1] = 0.0; B.od2[n - 1] = 0.0; }
   c.sync();
 }
 
-// number of eigenvalues of tridiag(dg, od) that are < x   (od2 = od^2)
+// number of eigenvalues of tridiag(dg, od) that are < x   (od2 = od^2).
+// Sturm sequence in product form  p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}  (sign changes = negative pivots of
+// the ratio form q_i = p_i / p_{i-1} that LAPACK's dstebz counts): one dependent FMA per row instead of a
+// division.  The pair (p_{i-1}, p_i) is rescaled by powers of two, which leaves the signs untouched; an exact zero
+// is replaced like dstebz's pivmin rule (q = -pivmin).
 DG_DEV int sturm_count(int n, const double* DG_RESTRICT dg, const double* DG_RESTRICT od2, double x, double pivmin) {
+  const double BIG = 1.3407807929942597e154 /* 2^512 */, SMALL = 7.458340731200207e-155 /* 2^-512 */;
   int cnt = 0;
-  double q = dg[0] - x;
-  if (fabs(q) < pivmin) q = -pivmin;
-  cnt += q < 0.0;
+  double pm = 1.0, pc = dg[0] - x;
+  if (fabs(pc) < pivmin) pc = -pivmin;
+  cnt += pc < 0.0;
   for (int i = 1; i < n; ++i) {
-    q = dg[i] - x - od2[i - 1] / q;
-    if (fabs(q) < pivmin) q = -pivmin;
-    cnt += q < 0.0;
+    double pn = (dg[i] - x) * pc - od2[i - 1] * pm;
+    if (fabs(pn) < pivmin * fabs(pc)) pn = -pivmin * pc;
+    cnt += (pn < 0.0) != (pc < 0.0);
+    pm = pc; pc = pn;
+    const double ap = fabs(pc);
+    if (ap > BIG) { pc *= SMALL; pm *= SMALL; }
+    else if (ap < SMALL) { pc *= BIG; pm *= BIG; }
   }
   return cnt;
 }
 
 // Solve (T - lam I) y = b in place (y overwrites b) by Gaussian elimination with partial pivoting.
-// fw: 5*n scratch (diag, sup1, sup2, mult, swapped)
+// fw: 5 arrays of n (diag, sup1, sup2, mult, swapped) and y are INTERLEAVED over the vectors of a chunk:
+// element i of this thread's vector sits at [i * st] (st = chunk width), so that the threads of a warp
+// touch consecutive words.
 DG_DEV void tridiag_shift_solve(int n, const double* dg, const double* od, double lam, double tiny,
-                                double* fw, double* y, bool refactor) {
-  double* a = fw; double* b1 = fw + n; double* b2 = fw + 2 * n; double* ml = fw + 3 * n; double* sw = fw + 4 * n;
+                                double* fw, double* y, int st, bool refactor) {
+  double* a = fw; double* b1 = fw + n * st; double* b2 = fw + 2 * n * st; double* ml = fw + 3 * n * st; double* sw = fw + 4 * n * st;
   if (refactor) {
     // work row "cur" = (p, q, r) starting at column i
     double p = dg[0] - lam, q = n > 1 ? od[0] : 0.0, r = 0.0;
@@ -140,45 +157,44 @@ DG_DEV void tridiag_shift_solve(int n, const double* dg, const double* od, doubl
       double sub = od[i], nd = dg[i + 1] - lam, ns = i + 2 < n ? od[i + 1] : 0.0;
       if (fabs(sub) > fabs(p)) {
         double m = p / sub;                       // pivot row is the next row (sub, nd, ns)
-        a[i] = sub; b1[i] = nd; b2[i] = ns; ml[i] = m; sw[i] = 1.0;
+        a[i * st] = sub; b1[i * st] = nd; b2[i * st] = ns; ml[i * st] = m; sw[i * st] = 1.0;
         p = q - m * nd; q = r - m * ns; r = 0.0;
       } else {
         if (p == 0.0) p = tiny;
         double m = sub / p;
-        a[i] = p; b1[i] = q; b2[i] = r; ml[i] = m; sw[i] = 0.0;
+        a[i * st] = p; b1[i * st] = q; b2[i * st] = r; ml[i * st] = m; sw[i * st] = 0.0;
         p = nd - m * q; q = ns - m * r; r = 0.0;
       }
     }
     if (fabs(p) < tiny) p = p < 0.0 ? -tiny : tiny;
-    a[n - 1] = p; b1[n - 1] = 0.0; b2[n - 1] = 0.0;
+    a[(n - 1) * st] = p; b1[(n - 1) * st] = 0.0; b2[(n - 1) * st] = 0.0;
   }
   for (int i = 0; i + 1 < n; ++i) {
-    if (sw[i] != 0.0) { double t = y[i]; y[i] = y[i + 1]; y[i + 1] = t - ml[i] * y[i]; }
-    else y[i + 1] -= ml[i] * y[i];
+    if (sw[i * st] != 0.0) { double t = y[i * st]; y[i * st] = y[(i + 1) * st]; y[(i + 1) * st] = t - ml[i * st] * y[i * st]; }
+    else y[(i + 1) * st] -= ml[i * st] * y[i * st];
   }
   for (int i = n - 1; i >= 0; --i) {
-    double t = y[i];
-    if (i + 1 < n) t -= b1[i] * y[i + 1];
-    if (i + 2 < n) t -= b2[i] * y[i + 2];
-    double piv = a[i];
+    double t = y[i * st];
+    if (i + 1 < n) t -= b1[i * st] * y[(i + 1) * st];
+    if (i + 2 < n) t -= b2[i * st] * y[(i + 2) * st];
+    double piv = a[i * st];
     if (fabs(piv) < tiny) piv = piv < 0.0 ? -tiny : tiny;
-    y[i] = t / piv;
+    y[i * st] = t / piv;
   }
 }
 
 // Negative eigenvalues of the tridiagonal matrix into B.lam[0..nneg): Sturm-count multisection.  All
 // eigenvalues are refined together: each round spends the CTA's nt probes evenly over the brackets.
+// lo/hi: nneg doubles each; cnts: nt ints of scratch.
 DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, double tnorm, double pivmin,
-                                 double* lo, double* hi) {
-  // lo/hi: shared or global scratch of nneg doubles each (B.pv / B.wv are free here)
+                                 double* lo, double* hi, int* cnts) {
   DG_FOR(j, nneg) { lo[j] = -tnorm * 1.0000001 - pivmin; hi[j] = 0.0; }
   c.sync();
   int per = c.nt / nneg;                       // probes per eigenvalue per round
   if (per < 1) per = 1;
   const int groups = c.nt / per;               // eigenvalues refined concurrently
-  int rounds = (int)ceil(56.0 * 0.6931471805599453 / log((double)per + 1.0));
+  int rounds = (int)ceil(54.0 * 0.6931471805599453 / log((double)per + 1.0));
   if (rounds < 1) rounds = 1;
-  int* cnts = (int*)(B.itw);                   // nt ints of scratch
   for (int j0 = 0; j0 < nneg; j0 += groups) {
     const int g = c.tid / per, t = c.tid - g * per, j = j0 + g;
     const bool act = g < groups && j < nneg;
@@ -190,11 +206,11 @@ DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, doubl
         cnts[c.tid] = sturm_count(n, B.dg, B.od2, a + h * (double)(t + 1), pivmin);
       }
       c.sync();
-      if (act && t == 0) {
-        int first = per;                        // first probe with count >= j+1
-        for (int s = 0; s < per; ++s) if (cnts[c.tid + s] >= j + 1) { first = s; break; }
-        lo[j] = first > 0 ? a + h * (double)first : a;
-        hi[j] = first < per ? a + h * (double)(first + 1) : b;
+      if (act) {
+        // the probe where the count first reaches j+1 narrows the bracket (exactly one thread per eigenvalue writes)
+        const bool mine = cnts[c.tid] >= j + 1, prev = t > 0 && cnts[c.tid - 1] >= j + 1;
+        if (mine && !prev) { if (t > 0) lo[j] = a + h * (double)t; hi[j] = a + h * (double)(t + 1); }
+        else if (!mine && t == per - 1) lo[j] = a + h * (double)per;
       }
       c.sync();
     }
@@ -203,19 +219,22 @@ DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, doubl
   c.sync();
 }
 
-// Hm <- nearestPD(Qraw) + reg*I.  Returns the number of negative eigenvalues (uniform across threads).
-DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, double* DG_RESTRICT Hm, const LinBuf& B,
+// matA <- nearestPD(Qraw) + reg*I  (n x n, leading dimension B.ld).  Qraw is row-major n x n (global memory, read
+// twice).  matB is scratch.  Returns the number of negative eigenvalues (uniform across threads).
+DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinBuf& B,
                        double floor_val, double reg, bool conv_approx) {
-  // symmetric part into W and Hm (thread = column: Qraw[i][j] coalesced, Qraw[j][i] strided but L1 resident)
+  const int ld = B.ld;
+  double* DG_RESTRICT Hm = B.matA;
   c.lap(PH_OTHER);
-  DG_FOR(t, n * n) {
-    int i = t / n, j = t - i * n;
-    double sv = 0.5 * (Qraw[i * n + j] + Qraw[j * n + i]);
-    B.W[t] = sv; Hm[t] = sv;
-  }
-  c.sync();
   int nneg = 0;
+  const double* Zall = nullptr;
   if (conv_approx) {
+    // symmetric part into W
+    DG_FOR(t, n * n) {
+      int i = t / n, j = t - i * n;
+      Hm[i * ld + j] = 0.5 * (Qraw[i * n + j] + Qraw[j * n + i]);
+    }
+    c.sync();
     sym_tridiag(c, n, B);
     c.lap(PH_PD_TRIDIAG);
     double tn = 0.0;
@@ -227,143 +246,177 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, double* DG
     const double pivmin = 2.2250738585072014e-308 * fmax(1.0, tnorm * tnorm);
     nneg = sturm_count(n, B.dg, B.od2, 0.0, pivmin);      // every thread computes the same count
     if (nneg > 0) {
-      negative_eigenvalues(c, n, B, nneg, tnorm, pivmin, B.pv, B.wv);
-      // --- eigenvectors in chunks: inverse iteration (thread per vector), Gram-Schmidt inside clusters,
-      //     warp-private back-transformation, rank-one corrections of Hm
+      // scratch carved from matB: [cnts | itw (5 n CH, interleaved) | Zt (n CH, interleaved) | Z (nneg n, vector major)]
+      const int CH = DG_EIG_CHUNK;
+      double* scr = B.matB;
+      int* cnts = (int*)scr;
+      double* itw = scr + ((c.nt + 1) / 2 + 1);
+      double* Zt = itw + 5 * n * CH;
+      double* Zs = Zt + n * CH;
+      const long cap = ((long)n * ld - (Zs - scr)) / n;    // eigenvectors that fit behind the scratch
+      double* Z = nneg <= cap ? Zs : B.Zg;
+      negative_eigenvalues(c, n, B, nneg, tnorm, pivmin, B.pv, B.wv, cnts);
+      // --- eigenvectors in chunks: inverse iteration (thread per vector), Gram-Schmidt inside clusters
       const double tiny = fmax(tnorm, 1.0) * 1.1e-16;
-      for (int j0 = 0; j0 < nneg; j0 += DG_EIG_CHUNK) {
-        const int kc = nneg - j0 < DG_EIG_CHUNK ? nneg - j0 : DG_EIG_CHUNK;
+      for (int j0 = 0; j0 < nneg; j0 += CH) {
+        const int kc = nneg - j0 < CH ? nneg - j0 : CH;
         bool cluster = false;
         for (int jj = 1; jj < kc; ++jj)
           if (fabs(B.lam[j0 + jj] - B.lam[j0 + jj - 1]) <= 1e-3 * tnorm) cluster = true;
-        for (int itn = 0; itn < 4; ++itn) {
+        for (int itn = 0; itn < DG_EIG_INVIT; ++itn) {
           DG_FOR(jj, kc) {
-            double* z = B.Z + jj * n;
+            double* z = Zt + jj;
             if (itn == 0)
-              for (int i = 0; i < n; ++i) z[i] = 1.0 + 0.37 * (double)(((i + 1) * 7919 + (j0 + jj) * 104729) % 97) / 97.0;
-            tridiag_shift_solve(n, B.dg, B.od, B.lam[j0 + jj], tiny, B.itw + jj * 5 * n, z, itn == 0);
+              for (int i = 0; i < n; ++i) z[i * CH] = 1.0 + 0.37 * (double)(((i + 1) * 7919 + (j0 + jj) * 104729) % 97) / 97.0;
+            tridiag_shift_solve(n, B.dg, B.od, B.lam[j0 + jj], tiny, itw + jj, z, CH, itn == 0);
             double nr = 0.0;
-            for (int i = 0; i < n; ++i) nr += z[i] * z[i];
+            for (int i = 0; i < n; ++i) nr += z[i * CH] * z[i * CH];
             nr = 1.0 / sqrt(nr);
-            for (int i = 0; i < n; ++i) z[i] *= nr;
+            for (int i = 0; i < n; ++i) z[i * CH] *= nr;
           }
           c.sync();
           if (cluster) {
-            if (c.tid == 0) {
+            if (c.warp == 0) {                   // modified Gram-Schmidt inside clusters, lanes along the vectors
               for (int jj = 1; jj < kc; ++jj) {
-                double* z = B.Z + jj * n;
+                double* z = Zt + jj;
                 bool changed = false;
                 for (int ii = 0; ii < jj; ++ii) {
                   if (fabs(B.lam[j0 + jj] - B.lam[j0 + ii]) > 1e-3 * tnorm) continue;
-                  const double* zi = B.Z + ii * n;
+                  const double* zi = Zt + ii;
                   double dt = 0.0;
-                  for (int i = 0; i < n; ++i) dt += zi[i] * z[i];
-                  for (int i = 0; i < n; ++i) z[i] -= dt * zi[i];
+                  for (int i = c.lane; i < n; i += c.wsz) dt += zi[i * CH] * z[i * CH];
+                  dt = c.warp_sum(dt);
+                  for (int i = c.lane; i < n; i += c.wsz) z[i * CH] -= dt * zi[i * CH];
+                  c.syncwarp();
                   changed = true;
                 }
                 if (changed) {
                   double nr = 0.0;
-                  for (int i = 0; i < n; ++i) nr += z[i] * z[i];
-                  nr = 1.0 / sqrt(nr);
-                  for (int i = 0; i < n; ++i) z[i] *= nr;
+                  for (int i = c.lane; i < n; i += c.wsz) nr += z[i * CH] * z[i * CH];
+                  nr = 1.0 / sqrt(c.warp_sum(nr));
+                  for (int i = c.lane; i < n; i += c.wsz) z[i * CH] *= nr;
+                  c.syncwarp();
                 }
               }
             }
             c.sync();
           }
         }
-        // back-transform y = H_0 H_1 ... H_{n-2} z (last reflector first): one warp per eigenvector,
-        // no CTA barrier inside
-        for (int jj = c.warp; jj < kc; jj += c.nwarps) {
-          double* DG_RESTRICT z = B.Z + jj * n;
-          for (int k = n - 3; k >= 0; --k) {
-            const double tk = B.tau[k];
-            if (tk == 0.0) continue;
-            const int len = n - k - 1;
-            const double* DG_RESTRICT vcol = B.W + (k + 1) * n + k;
-            double p = 0.0;
-            for (int i = c.lane; i < len; i += c.wsz) p += (i == 0 ? 1.0 : vcol[i * n]) * z[k + 1 + i];
-            p = c.warp_sum(p) * tk;
-            for (int i = c.lane; i < len; i += c.wsz) z[k + 1 + i] -= p * (i == 0 ? 1.0 : vcol[i * n]);
-            c.syncwarp();
-          }
-        }
-        c.sync();
-        // Hm += sum_j (floor - lam_j) y_j y_j'
-        DG_FOR(t, n * n) {
-          int i = t / n, j = t - i * n;
-          double acc = 0.0;
-          for (int jj = 0; jj < kc; ++jj) acc += (floor_val - B.lam[j0 + jj]) * B.Z[jj * n + i] * B.Z[jj * n + j];
-          Hm[t] += acc;
-        }
+        // de-interleave the chunk into the vector-major store
+        for (int e = c.tid; e < kc * n; e += c.nt) { int jj = e / n, i = e - jj * n; Z[(size_t)(j0 + jj) * n + i] = Zt[i * CH + jj]; }
         c.sync();
       }
+      // back-transform y = H_0 H_1 ... H_{n-2} z (last reflector first): one warp per eigenvector, no CTA barrier inside
+      for (int jv = c.warp; jv < nneg; jv += c.nwarps) {
+        double* DG_RESTRICT z = Z + (size_t)jv * n;
+        for (int k = n - 3; k >= 0; --k) {
+          const double tk = B.tau[k];
+          if (tk == 0.0) continue;
+          const int len = n - k - 1;
+          const double* DG_RESTRICT vcol = Hm + (k + 1) * ld + k;
+          double pp = 0.0;
+          for (int i = c.lane; i < len; i += c.wsz) pp += (i == 0 ? 1.0 : vcol[i * ld]) * z[k + 1 + i];
+          pp = c.warp_sum(pp) * tk;
+          for (int i = c.lane; i < len; i += c.wsz) z[k + 1 + i] -= pp * (i == 0 ? 1.0 : vcol[i * ld]);
+          c.syncwarp();
+        }
+      }
+      c.sync();
+      Zall = Z;
     }
   }
-  if (reg > 0.0) { DG_FOR(i, n) Hm[i * n + i] += reg; }
+  // H = sym(Q) + sum_j (floor - lam_j) y_j y_j' + reg I   (the reflectors in matA are dead now)
+  DG_FOR(t, n * n) {
+    int i = t / n, j = t - i * n;
+    double acc = 0.5 * (Qraw[i * n + j] + Qraw[j * n + i]);
+    for (int jv = 0; jv < nneg; ++jv) acc += (floor_val - B.lam[jv]) * Zall[(size_t)jv * n + i] * Zall[(size_t)jv * n + j];
+    if (i == j) acc += reg;
+    Hm[i * ld + j] = acc;
+  }
   c.sync();
   c.lap(PH_PD_EIG);
   return nneg;
 }
 
-// In-place lower Cholesky of the symmetric matrix Hm (row-major), blocked right-looking with the
-// panel (n x NB) staged in shared memory.  Returns false (uniformly) on a non-positive pivot.
-DG_DEVN bool cholesky_lower(Cta& c, int n, double* DG_RESTRICT Hm, double* DG_RESTRICT sp) {
-  const int NB = DG_CHOL_NB;
+// In-place lower Cholesky of the symmetric matrix Hm (row-major, leading dimension ld), blocked right-looking with
+// the panel (n x NB) staged in `sp`.  Per panel: warp 0 factors the NB x NB diagonal block (warp-level
+// synchronisation only), then thread r solves its own panel row against it, then the trailing lower triangle is
+// updated by the whole CTA.  Four barriers per panel.  scr: NB + 1 doubles of scratch.
+// Returns false (uniformly) on a non-positive pivot.
+DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, double* DG_RESTRICT sp, double* DG_RESTRICT scr) {
+  constexpr int NB = DG_CHOL_NB;
   for (int k0 = 0; k0 < n; k0 += NB) {
     const int nb = n - k0 < NB ? n - k0 : NB;
     const int rows = n - k0;
-    // stage panel rows k0.. into shared memory: sp[(i-k0)*NB + t] = Hm[i][k0+t]
+    // stage panel rows k0.. : sp[(i-k0)*NB + t] = Hm[i][k0+t]
     for (int e = c.tid; e < rows * NB; e += c.nt) {
       int r = e / NB, t = e - r * NB;
-      sp[e] = t < nb ? Hm[(k0 + r) * n + k0 + t] : 0.0;
+      sp[e] = t < nb ? Hm[(k0 + r) * ld + k0 + t] : 0.0;
     }
     c.sync();
-    for (int kk = 0; kk < nb; ++kk) {
-      // pivot (every thread computes it from the finished row kk of the panel)
-      double piv = sp[kk * NB + kk];
-      for (int t = 0; t < kk; ++t) piv -= sp[kk * NB + t] * sp[kk * NB + t];
-      if (!(piv > 0.0)) return false;
-      const double inv = 1.0 / sqrt(piv);
-      c.sync();                                   // all pivots read before row kk's entry is overwritten
-      for (int r = kk + c.tid; r < rows; r += c.nt) {
-        double v = sp[r * NB + kk];
-        if (r == kk) v = piv * inv;               // sqrt(piv)
-        else {
-          for (int t = 0; t < kk; ++t) v -= sp[r * NB + t] * sp[kk * NB + t];
-          v *= inv;
+    if (c.warp == 0) {
+      bool ok = true;
+      for (int kk = 0; kk < nb; ++kk) {
+        double piv = sp[kk * NB + kk];
+        for (int t = 0; t < kk; ++t) piv -= sp[kk * NB + t] * sp[kk * NB + t];
+        if (!(piv > 0.0)) ok = false;
+        const double inv = 1.0 / sqrt(piv);
+        c.syncwarp();                               // pivot read by every lane before it is overwritten
+        for (int r = kk + c.lane; r < nb; r += c.wsz) {
+          double v;
+          if (r == kk) { v = piv * inv; scr[kk] = inv; }          // sqrt(piv)
+          else {
+            v = sp[r * NB + kk];
+            for (int t = 0; t < kk; ++t) v -= sp[r * NB + t] * sp[kk * NB + t];
+            v *= inv;
+          }
+          sp[r * NB + kk] = v;
         }
-        sp[r * NB + kk] = v;
+        c.syncwarp();
       }
-      c.sync();
+      if (c.lane == 0) scr[NB] = ok ? 1.0 : 0.0;
     }
+    c.sync();
+    if (scr[NB] == 0.0) return false;
+    // panel rows below the diagonal block: x Ld' = a, row by row (thread = row)
+    for (int r = nb + c.tid; r < rows; r += c.nt) {
+      double x[NB];
+#pragma unroll
+      for (int kk = 0; kk < NB; ++kk) {
+        double v = sp[r * NB + kk];
+#pragma unroll
+        for (int t = 0; t < kk; ++t) v -= x[t] * sp[kk * NB + t];
+        x[kk] = kk < nb ? v * scr[kk] : 0.0;
+      }
+#pragma unroll
+      for (int t = 0; t < NB; ++t) sp[r * NB + t] = x[t];
+    }
+    c.sync();
     // write the finished panel back (upper part of the diagonal block is left untouched: never read)
     for (int e = c.tid; e < rows * NB; e += c.nt) {
       int r = e / NB, t = e - r * NB;
-      if (t < nb && t <= r) Hm[(k0 + r) * n + k0 + t] = sp[e];
+      if (t < nb && t <= r) Hm[(k0 + r) * ld + k0 + t] = sp[e];
     }
-    // trailing update of the lower triangle: thread = column j, rows i >= j; panel rows from shared memory
+    // trailing update of the lower triangle, spread over all threads: work item (gi, jl) owns column
+    // j = j0 + jl and the rows i = j + gi, j + gi + groups, ...  (a warp shares i: the panel row is a broadcast)
     const int j0 = k0 + nb;
-    for (int j = j0 + c.tid; j < n; j += c.nt) {
-      double lj[DG_CHOL_NB];
+    const int ncol = n - j0;
+    if (ncol > 0) {
+      int groups = c.nt / ncol;
+      if (groups < 1) groups = 1;
+      for (int e = c.tid; e < ncol * groups; e += c.nt) {
+        const int gi = e / ncol, j = j0 + (e - gi * ncol);
+        double lj[NB];
 #pragma unroll
-      for (int t = 0; t < DG_CHOL_NB; ++t) lj[t] = sp[(j - k0) * NB + t];
-      double* DG_RESTRICT col = Hm + j;
-      int i = j;
-      for (; i + 2 <= n; i += 2) {
-        const double* DG_RESTRICT r0 = sp + (i - k0) * NB;
-        const double* DG_RESTRICT r1 = r0 + NB;
-        double c0 = col[i * n], c1 = col[(i + 1) * n];
+        for (int t = 0; t < NB; ++t) lj[t] = sp[(j - k0) * NB + t];
+        double* DG_RESTRICT col = Hm + j;
+        for (int i = j + gi; i < n; i += groups) {
+          const double* DG_RESTRICT r0 = sp + (i - k0) * NB;
+          double c0 = col[i * ld];
 #pragma unroll
-        for (int t = 0; t < DG_CHOL_NB; ++t) { c0 -= r0[t] * lj[t]; c1 -= r1[t] * lj[t]; }
-        col[i * n] = c0; col[(i + 1) * n] = c1;
-      }
-      for (; i < n; ++i) {
-        const double* DG_RESTRICT r0 = sp + (i - k0) * NB;
-        double c0 = col[i * n];
-#pragma unroll
-        for (int t = 0; t < DG_CHOL_NB; ++t) c0 -= r0[t] * lj[t];
-        col[i * n] = c0;
+          for (int t = 0; t < NB; ++t) c0 -= r0[t] * lj[t];
+          col[i * ld] = c0;
+        }
       }
     }
     c.sync();
@@ -371,25 +424,44 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, double* DG_RESTRICT Hm, double* DG_RE
   return true;
 }
 
-// Y = L^{-1} (lower triangular, row-major: Y[i][c]); thread c owns column c, so every access is coalesced.
+// Y = L^{-1} (lower triangular; L and Y row-major with leading dimension ld: Y[i][c]).  Columns are independent:
 //   Y[c][c] = 1/L[c][c];  Y[i][c] = -(sum_{j=c}^{i-1} L[i][j] Y[j][c]) / L[i][i]
-// The GI solver uses J = L^{-T} = Y' through the accessor J(i,j) = Y[j*n+i].
-DG_DEVN void tri_inverse(Cta& c, int n, const double* DG_RESTRICT Lm, double* DG_RESTRICT Y) {
-  DG_FOR(cc, n) {
-    for (int i = 0; i < cc; ++i) Y[i * n + cc] = 0.0;
-    Y[cc * n + cc] = 1.0 / Lm[cc * n + cc];
-    for (int i = cc + 1; i < n; ++i) {
-      const double* DG_RESTRICT Li = Lm + i * n;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int j = cc;
-      for (; j + 4 <= i; j += 4) {
-        a0 += Li[j] * Y[j * n + cc];
-        a1 += Li[j + 1] * Y[(j + 1) * n + cc];
-        a2 += Li[j + 2] * Y[(j + 2) * n + cc];
-        a3 += Li[j + 3] * Y[(j + 3) * n + cc];
+// Each column is owned by a group of TG adjacent lanes that split the dot product and combine it with shuffles, so
+// the whole inverse runs without a CTA barrier; lane s of a group stores (and later re-reads) the rows i with
+// (i - c) mod TG == s, i.e. it only ever reads what it wrote itself.
+// The GI solver uses J = L^{-T} = Y' through the accessor J(i,j) = Y[j*ld+i].
+DG_DEVN void tri_inverse(Cta& c, int n, int ld, const double* DG_RESTRICT Lm, double* DG_RESTRICT Y) {
+#ifdef DG_HOSTSIM
+  const int TG = 1;
+#else
+  const int TG = c.nt >= 4 * n ? 4 : (c.nt >= 2 * n ? 2 : 1);
+#endif
+  const int ngroups = c.nt / TG;
+  const int s = c.tid % TG;
+  const int wfirst = (c.tid - c.lane) / TG;        // first column group of this warp
+  for (int base = 0; base + wfirst < n; base += ngroups) {       // warp-uniform trip count
+    const int cc = base + c.tid / TG;
+    const bool act = cc < n;
+    if (act) {
+      for (int i = s; i < cc; i += TG) Y[i * ld + cc] = 0.0;
+      if (s == 0) Y[cc * ld + cc] = 1.0 / Lm[cc * ld + cc];
+    }
+    for (int i = base + wfirst + 1; i < n; ++i) {                // warp-uniform: the shuffles need every lane
+      const double* DG_RESTRICT Li = Lm + i * ld;
+      double acc = 0.0;
+      const bool on = act && i > cc;
+      if (on) {
+        double a0 = 0.0, a1 = 0.0;
+        int j = cc + s;
+        for (; j + TG < i; j += 2 * TG) { a0 += Li[j] * Y[j * ld + cc]; a1 += Li[j + TG] * Y[(j + TG) * ld + cc]; }
+        if (j < i) a0 += Li[j] * Y[j * ld + cc];
+        acc = a0 + a1;
       }
-      for (; j < i; ++j) a0 += Li[j] * Y[j * n + cc];
-      Y[i * n + cc] = -((a0 + a1) + (a2 + a3)) / Li[i];
+#ifndef DG_HOSTSIM
+      if (TG >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (TG >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+#endif
+      if (on && (i - cc) % TG == s) Y[i * ld + cc] = -acc / Li[i];
     }
   }
   c.sync();

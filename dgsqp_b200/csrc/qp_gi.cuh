@@ -8,10 +8,11 @@
 // Conventions: slack s_i = -g_i - G_i x >= 0, normal n_i = -G_i', multipliers lam >= 0,
 // H x + q + G' lam = 0.
 //
-// Storage: Y = J' (row-major), i.e. J(i,j) = Y[j*n+i].  Y starts as L^-1 (tri_inverse) and every
-// per-iteration O(n^2) operation touches it with thread = column of Y (coalesced): z = J2 d2, the
-// Householder update of J's trailing columns and the Givens rotations of a drop.  Only d = J'n needs
-// rows of Y; it is computed warp-per-row.
+// Storage: Y = J' (row-major, leading dimension ld), i.e. J(i,j) = Y[j*ld+i].  Y starts as L^-1 (tri_inverse).
+// Every O(n^2) operation of an iteration is spread over the whole CTA: products with J' run warp-per-row, products
+// with J and the Householder update of J's trailing columns use the 2D decomposition of cta.cuh (consecutive
+// threads = consecutive columns of Y, column groups interleave the rows) with partial sums combined through
+// B.part; the triangular solve with R runs on one warp while the others combine the partial sums.
 #pragma once
 #include "racing_game.cuh"
 #include "linalg.cuh"
@@ -20,13 +21,13 @@
 #define DG_QP_DEP_TOL 1e-20
 
 struct QpBuf {
-  double* Y;      // n*n   J transposed
-  double* Rm;     // n*n   upper triangular factor of the active normals in J-coordinates
+  // Y = J' lives in LinBuf::matB, R (upper triangular factor of the active normals in J-coordinates) in
+  // LinBuf::matA once the Cholesky factor stored there has been inverted
   double* xq;     // n   primal iterate (du)
   double* dv;     // n   J' n_p
   double* zv;     // n   primal step direction
   double* rv;     // n   dual step direction (active part)
-  double* npv;    // n   G row of the entering constraint (normal is -npv)
+  double* npv;    // n   G row of the entering constraint (normal is -npv); reused for the Householder vector
   double* lam_act;// n
   double* sl;     // m   G x
   double* lam;    // m   output multipliers
@@ -34,17 +35,44 @@ struct QpBuf {
   int* is_act;    // m   flags
 };
 
+// out[i] = scale * sum_{j in [j0, n)} Y[j][i] * d[j],  i < n.  All threads; ends with a barrier.
+DG_DEV void gi_cols_times(Cta& c, int n, int ld, const double* DG_RESTRICT Y, const double* DG_RESTRICT d, int j0,
+                          double* DG_RESTRICT part, double* DG_RESTRICT out, double scale) {
+  const Split2 sp = split2(c, n);
+  for (int i = sp.i0; i < n; i += sp.istep) {
+    double a0 = 0.0, a1 = 0.0;
+    int j = j0 + sp.g;
+    for (; j + sp.G < n; j += 2 * sp.G) { a0 += Y[j * ld + i] * d[j]; a1 += Y[(j + sp.G) * ld + i] * d[j + sp.G]; }
+    if (j < n) a0 += Y[j * ld + i] * d[j];
+    if (sp.G == 1) out[i] = scale * (a0 + a1);
+    else part[sp.g * sp.istep + i] = a0 + a1;
+  }
+  c.sync();
+  if (sp.G > 1) {
+    if (sp.g == 0) {
+      for (int i = sp.i0; i < n; i += sp.istep) {
+        double acc = part[i];
+        for (int g = 1; g < sp.G; ++g) acc += part[g * sp.istep + i];
+        out[i] = scale * acc;
+      }
+    }
+    c.sync();
+  }
+}
+
+// H (symmetric positive definite) is expected in B.matA and is destroyed.
 // returns 0 ok, 1 not PD, 2 infeasible, 3 iteration limit.  Output: Q.xq (du), Q.lam (l_hat).
-DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, double* DG_RESTRICT Hm, const double* DG_RESTRICT qv,
+DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, const double* DG_RESTRICT qv,
                         const QpBuf& Q, const LinBuf& B, int* n_iter_out, int* n_active_out) {
-  const int n = D.n, m = D.m;
-  double* DG_RESTRICT Y = Q.Y;
-  if (!cholesky_lower(c, n, Hm, B.sp)) return 1;
+  const int n = D.n, m = D.m, ld = B.ld;
+  double* DG_RESTRICT Y = B.matB;
+  double* DG_RESTRICT Rm = B.matA;
+  if (!cholesky_lower(c, n, ld, B.matA, B.sp, B.part)) return 1;
   c.lap(PH_CHOL);
-  tri_inverse(c, n, Hm, Y);
-  // x = -J J' q = -Y' (Y q):   t = Y q (warp per row), x_i = -sum_j Y[j][i] t_j (thread per column)
+  tri_inverse(c, n, ld, B.matA, Y);
+  // x = -J J' q = -Y' (Y q):   t = Y q (warp per row), x_i = -sum_j Y[j][i] t_j
   for (int j = c.warp; j < n; j += c.nwarps) {
-    const double* DG_RESTRICT Yj = Y + j * n;
+    const double* DG_RESTRICT Yj = Y + j * ld;
     double p = 0.0;
     for (int i = c.lane; i <= j; i += c.wsz) p += Yj[i] * qv[i];
     p = c.warp_sum(p);
@@ -52,13 +80,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, double* DG_REST
   }
   DG_FOR(r, m) { Q.is_act[r] = 0; Q.lam[r] = 0.0; }
   c.sync();
-  DG_FOR(i, n) {
-    double a0 = 0.0, a1 = 0.0;
-    int j = i;
-    for (; j + 2 <= n; j += 2) { a0 += Y[j * n + i] * Q.dv[j]; a1 += Y[(j + 1) * n + i] * Q.dv[j + 1]; }
-    for (; j < n; ++j) a0 += Y[j * n + i] * Q.dv[j];
-    Q.xq[i] = -(a0 + a1);
-  }
+  gi_cols_times(c, n, ld, Y, Q.dv, 0, B.part, Q.xq, -1.0);
   c.lap(PH_TRINV);
   int iq = 0, it = 0;
   const int max_iter = 10 * (n + m);
@@ -85,7 +107,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, double* DG_REST
       // d = J' n_p = -Y npv   (warp per row);  also npv . x
       double dd_tail = 0.0, dd_all = 0.0, gx = 0.0;
       for (int j = c.warp; j < n; j += c.nwarps) {
-        const double* DG_RESTRICT Yj = Y + j * n;
+        const double* DG_RESTRICT Yj = Y + j * ld;
         double pp = 0.0;
         for (int i = c.lane; i < n; i += c.wsz) pp += Yj[i] * Q.npv[i];
         pp = -c.warp_sum(pp);
@@ -98,19 +120,38 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, double* DG_REST
       DG_FOR(i, n) gx += Q.npv[i] * Q.xq[i];
       c.sum3(dd_tail, dd_all, gx);
       const double zn = dd_tail, dall = dd_all;
-      // z = J[:, iq:] d[iq:]  (thread per column of Y)     r = R^-1 d[:iq]  (thread 0)
-      DG_FOR(i, n) {
-        double a0 = 0.0, a1 = 0.0;
-        int j = iq;
-        for (; j + 2 <= n; j += 2) { a0 += Y[j * n + i] * Q.dv[j]; a1 += Y[(j + 1) * n + i] * Q.dv[j + 1]; }
-        for (; j < n; ++j) a0 += Y[j * n + i] * Q.dv[j];
-        Q.zv[i] = a0 + a1;
-      }
-      if (c.tid == c.nt - 1) {
-        for (int i = iq - 1; i >= 0; --i) {
-          double acc = Q.dv[i];
-          for (int j = i + 1; j < iq; ++j) acc -= Q.Rm[i * n + j] * Q.rv[j];
-          Q.rv[i] = acc / Q.Rm[i * n + i];
+      // z = J[:, iq:] d[iq:]  (2D over the CTA);  r = R^-1 d[:iq]  (column-oriented back substitution on the last warp,
+      // while the first column group combines the partial sums of z)
+      {
+        const Split2 sp = split2(c, n);
+        for (int i = sp.i0; i < n; i += sp.istep) {
+          double a0 = 0.0, a1 = 0.0;
+          int j = iq + sp.g;
+          for (; j + sp.G < n; j += 2 * sp.G) { a0 += Y[j * ld + i] * Q.dv[j]; a1 += Y[(j + sp.G) * ld + i] * Q.dv[j + sp.G]; }
+          if (j < n) a0 += Y[j * ld + i] * Q.dv[j];
+          if (sp.G == 1) Q.zv[i] = a0 + a1;
+          else B.part[sp.g * sp.istep + i] = a0 + a1;
+        }
+        if (sp.G > 1) {
+          c.sync();
+          if (sp.g == 0) {
+            for (int i = sp.i0; i < n; i += sp.istep) {
+              double acc = B.part[i];
+              for (int g = 1; g < sp.G; ++g) acc += B.part[g * sp.istep + i];
+              Q.zv[i] = acc;
+            }
+          }
+        }
+        if (c.warp == c.nwarps - 1) {
+          for (int i = c.lane; i < iq; i += c.wsz) Q.rv[i] = Q.dv[i];
+          c.syncwarp();
+          for (int i = iq - 1; i >= 0; --i) {
+            const double ri = Q.rv[i] / Rm[i * ld + i];
+            c.syncwarp();
+            if (c.lane == 0) Q.rv[i] = ri;
+            for (int j = c.lane; j < i; j += c.wsz) Q.rv[j] -= Rm[j * ld + i] * ri;
+            c.syncwarp();
+          }
         }
       }
       c.sync();
@@ -138,23 +179,19 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, double* DG_REST
         const double vv = 2.0 * (zn - alpha * d0);
         if (vv > 0.0) {
           const double sc = 2.0 / vv;
-          DG_FOR(i, n) {
-            const double wi = (Q.zv[i] - alpha * Y[iq * n + i]) * sc;
-            double* DG_RESTRICT col = Y + iq * n + i;
-            col[0] -= (d0 - alpha) * wi;
-            int j = 1;
-            for (; j + 4 <= len; j += 4) {
-              double y0 = col[(j + 0) * n], y1 = col[(j + 1) * n], y2 = col[(j + 2) * n], y3 = col[(j + 3) * n];
-              y0 -= Q.dv[iq + j + 0] * wi; y1 -= Q.dv[iq + j + 1] * wi;
-              y2 -= Q.dv[iq + j + 2] * wi; y3 -= Q.dv[iq + j + 3] * wi;
-              col[(j + 0) * n] = y0; col[(j + 1) * n] = y1; col[(j + 2) * n] = y2; col[(j + 3) * n] = y3;
-            }
-            for (; j < len; ++j) col[j * n] -= Q.dv[iq + j] * wi;
+          // w = (J2 v) * 2/(v'v) into npv (the entering row is not needed any more)
+          DG_FOR(i, n) Q.npv[i] = (Q.zv[i] - alpha * Y[iq * ld + i]) * sc;
+          c.sync();
+          const Split2 sp = split2(c, n);
+          for (int i = sp.i0; i < n; i += sp.istep) {
+            const double wi = Q.npv[i];
+            double* DG_RESTRICT col = Y + iq * ld + i;
+            for (int j = sp.g; j < len; j += sp.G) col[j * ld] -= (j == 0 ? d0 - alpha : Q.dv[iq + j]) * wi;
           }
         }
-        DG_FOR(i, iq) Q.Rm[i * n + iq] = Q.dv[i];
+        DG_FOR(i, iq) Rm[i * ld + iq] = Q.dv[i];
         if (c.tid == 0) {
-          Q.Rm[iq * n + iq] = alpha;
+          Rm[iq * ld + iq] = alpha;
           Q.act[iq] = p; Q.is_act[p] = 1; Q.lam_act[iq] = lam_p;
         }
         ++iq;
@@ -168,25 +205,25 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, double* DG_REST
           for (int k = ldrop; k < iq - 1; ++k) { Q.act[k] = Q.act[k + 1]; Q.lam_act[k] = Q.lam_act[k + 1]; }
         }
         DG_FOR(i, iq) {
-          for (int j = ldrop; j < iq - 1; ++j) Q.Rm[i * n + j] = Q.Rm[i * n + j + 1];
-          Q.Rm[i * n + iq - 1] = 0.0;
+          for (int j = ldrop; j < iq - 1; ++j) Rm[i * ld + j] = Rm[i * ld + j + 1];
+          Rm[i * ld + iq - 1] = 0.0;
         }
         c.sync();
         for (int j = ldrop; j < iq - 1; ++j) {
-          double a = Q.Rm[j * n + j], b = Q.Rm[(j + 1) * n + j];
+          double a = Rm[j * ld + j], b = Rm[(j + 1) * ld + j];
           double h = hypot(a, b);
           c.sync();                               // rotation parameters read before rows change
           if (h != 0.0) {
             double cs = a / h, sn = b / h;
             for (int col = j + c.tid; col < iq - 1; col += c.nt) {
-              double r0 = Q.Rm[j * n + col], r1 = Q.Rm[(j + 1) * n + col];
-              Q.Rm[j * n + col] = cs * r0 + sn * r1;
-              Q.Rm[(j + 1) * n + col] = -sn * r0 + cs * r1;
+              double r0 = Rm[j * ld + col], r1 = Rm[(j + 1) * ld + col];
+              Rm[j * ld + col] = cs * r0 + sn * r1;
+              Rm[(j + 1) * ld + col] = -sn * r0 + cs * r1;
             }
-            DG_FOR(i, n) {                        // columns j, j+1 of J = rows j, j+1 of Y
-              double j0 = Y[j * n + i], j1 = Y[(j + 1) * n + i];
-              Y[j * n + i] = cs * j0 + sn * j1;
-              Y[(j + 1) * n + i] = -sn * j0 + cs * j1;
+            DG_FOR_OFF(i, n, 128) {               // columns j, j+1 of J = rows j, j+1 of Y
+              double j0 = Y[j * ld + i], j1 = Y[(j + 1) * ld + i];
+              Y[j * ld + i] = cs * j0 + sn * j1;
+              Y[(j + 1) * ld + i] = -sn * j0 + cs * j1;
             }
           }
           c.sync();

@@ -41,6 +41,8 @@ struct GameDesc {
 
 struct Dims {
   int M, N, nq, nu, n, m, P, nc0, nck, ncN, twoN;
+  int ld;        // leading dimension of the n x n work matrices (odd: conflict-free row AND column walks in shared memory)
+  int sens_sz;   // doubles of packed sensitivity rows per agent
 };
 
 DG_HD Dims make_dims(int M, int N) {
@@ -50,6 +52,8 @@ DG_HD Dims make_dims(int M, int N) {
   d.nc0 = 8 * M; d.nck = d.P + 10 * M; d.ncN = d.P + 2 * M;
   d.m = d.nc0 + (N - 1) * d.nck + d.ncN;
   d.twoN = 2 * N;
+  d.ld = d.n | 1;
+  d.sens_sz = 3 * N * (N + 1);
   return d;
 }
 
@@ -120,7 +124,8 @@ struct EvalBuf {
   double* x;     // (N+1)*nq
   double* AB;    // N*M*48      d fd / d [q;u]  per (k,a)
   double* T2;    // N*M*90      second derivatives per (k,a)
-  double* S;     // M*N*3*2N    sensitivity rows (x, y, e_y) of stages 1..N wrt own inputs
+  double* S;     // M*3N(N+1)   sensitivity rows (x, y, e_y) of stages 1..N wrt own inputs, packed: row (a,k,r) holds the
+                 //             2k columns of inputs u^a_0..u^a_{k-1} at  a*sens_sz + 3k(k-1) + r*2k
   double* g;     // m
   double* q;     // n   [grad_{u^a} J^a]_a
   double* gtl;   // n   G' l
@@ -185,6 +190,9 @@ DG_DEVN void game_constraints(Cta& c, const GameDesc& G, const Dims& D, const do
   }
 }
 
+// start of packed sensitivity row (a, k, r): k in 1..N, r in {0:x, 1:y, 2:e_y}; 2k entries
+DG_DEV int sens_off(const Dims& D, int a, int k, int r) { return a * D.sens_sz + 3 * k * (k - 1) + r * 2 * k; }
+
 // Sensitivity rows (f_Du_x restricted to x, y, e_y): thread per input column (a, j).
 DG_DEVN void game_sens(Cta& c, const Dims& D, const EvalBuf& E) {
   const int twoN = D.twoN;
@@ -193,9 +201,7 @@ DG_DEVN void game_sens(Cta& c, const Dims& D, const EvalBuf& E) {
     double s6[DG_NQA];
     const double* AB = E.AB + (kj * D.M + a) * 48;
     for (int i = 0; i < DG_NQA; ++i) s6[i] = AB[i * 8 + 6 + cc];
-    for (int k = 1; k <= D.N; ++k) {
-      double* Sk = E.S + ((a * D.N + (k - 1)) * 3) * twoN + j;
-      if (k <= kj) { Sk[0] = 0.0; Sk[twoN] = 0.0; Sk[2 * twoN] = 0.0; continue; }
+    for (int k = kj + 1; k <= D.N; ++k) {
       if (k > kj + 1) {
         const double* Ak = E.AB + ((k - 1) * D.M + a) * 48;
         double t6[DG_NQA];
@@ -206,16 +212,17 @@ DG_DEVN void game_sens(Cta& c, const Dims& D, const EvalBuf& E) {
         }
         for (int i = 0; i < DG_NQA; ++i) s6[i] = t6[i];
       }
-      Sk[0] = s6[0]; Sk[twoN] = s6[1]; Sk[2 * twoN] = s6[5];
+      double* Sk = E.S + sens_off(D, a, k, 0) + j;
+      Sk[0] = s6[0]; Sk[2 * k] = s6[1]; Sk[4 * k] = s6[5];
     }
   }
 }
 
 DG_DEV double sens_dot(const Dims& D, const EvalBuf& E, int a, int k, int row, const double* va) {
-  const double* Sk = E.S + ((a * D.N + (k - 1)) * 3 + row) * D.twoN;
-  double acc = 0.0;
-  for (int j = 0; j < 2 * k; ++j) acc += Sk[j] * va[j];
-  return acc;
+  const double* DG_RESTRICT Sk = E.S + sens_off(D, a, k, row);
+  double a0 = 0.0, a1 = 0.0;
+  for (int j = 0; j < 2 * k; j += 2) { a0 += Sk[j] * va[j]; a1 += Sk[j + 1] * va[j + 1]; }
+  return a0 + a1;
 }
 
 // y = G v   (v in R^n agent-major, y in R^m).  Two phases with one sync.
@@ -285,9 +292,9 @@ DG_DEVN void game_GT_times(Cta& c, const Dims& D, const EvalBuf& E, const double
     int a = t / D.twoN, j = t - a * D.twoN, kj = j >> 1, cc = j & 1;
     double acc = game_GT_direct(D, w, a, kj, cc);
     for (int k = kj + 1; k <= D.N; ++k) {
-      const double* Sk = E.S + ((a * D.N + (k - 1)) * 3) * D.twoN + j;
+      const double* Sk = E.S + sens_off(D, a, k, 0) + j;
       const double* cf = E.cf + (a * D.N + (k - 1)) * 3;
-      acc += cf[0] * Sk[0] + cf[1] * Sk[D.twoN] + cf[2] * Sk[2 * D.twoN];
+      acc += cf[0] * Sk[0] + cf[1] * Sk[2 * k] + cf[2] * Sk[4 * k];
     }
     y[t] = acc;
   }
@@ -305,9 +312,9 @@ DG_DEVN void game_G_row(Cta& c, const Dims& D, const EvalBuf& E, int r, double* 
       if ((ta == a || ta == b) && kj < k) {
         double dx = E.x[k * D.nq + a * DG_NQA] - E.x[k * D.nq + b * DG_NQA];
         double dy = E.x[k * D.nq + a * DG_NQA + 1] - E.x[k * D.nq + b * DG_NQA + 1];
-        const double* Sk = E.S + ((ta * D.N + (k - 1)) * 3) * D.twoN + j;
+        const double* Sk = E.S + sens_off(D, ta, k, 0) + j;
         double sg = ta == a ? -2.0 : 2.0;
-        val = sg * (dx * Sk[0] + dy * Sk[D.twoN]);
+        val = sg * (dx * Sk[0] + dy * Sk[2 * k]);
       }
     } else if (kind == K_RATE) {
       if (ta == a && cc == (b >> 1)) {
@@ -319,7 +326,7 @@ DG_DEVN void game_G_row(Cta& c, const Dims& D, const EvalBuf& E, int r, double* 
     else if (kind == K_INLB) { if (ta == a && kj == k && cc == b) val = -1.0; }
     else {
       if (ta == a && kj < k) {
-        double sv = E.S[((ta * D.N + (k - 1)) * 3 + 2) * D.twoN + j];
+        double sv = E.S[sens_off(D, ta, k, 2) + j];
         val = kind == K_STUB ? sv : -sv;
       }
     }

@@ -10,6 +10,7 @@
 #include "qp_gi.cuh"
 #include "lsqr.cuh"
 
+#define DG_NDIAG 8
 enum { ST_CONV_ABS = 0, ST_CONV_REL = 1, ST_MAX_IT = 2, ST_DIVERGED = 3, ST_QP_FAIL = 4, ST_TIME_LIMIT = 5 };
 
 struct SolverParams {
@@ -25,43 +26,80 @@ struct SqpBuf {
   double *u_t, *l_t, *du_t, *dl_t, *s_t, *ds_t;
   double *u_c, *l_c;                 // candidate point
   double *Gdu, *tn, *tn2;
-  double *Hm;
-  double *up;                        // nu (zeros: v1 resets u_prev every solve, DGSQP.py:305)
+  double* up;                        // nu (zeros: v1 resets u_prev every solve, DGSQP.py:305)
 };
 
 struct Workspace { EvalBuf E; LinBuf B; QpBuf Q; LsqrBuf L; SqpBuf S; };
 
-// Shared-memory scratch of one CTA (doubles): two n-vectors and the Cholesky panel.
-DG_HD size_t carve_shared(const Dims& D, double* sbase, Workspace& W) {
-  W.B.pv = sbase; W.B.wv = sbase ? sbase + D.n : nullptr; W.B.sp = sbase ? sbase + 2 * D.n : nullptr;
-  return (size_t)D.n * (2 + DG_CHOL_NB);
-}
+struct MemPlan { size_t smem, gmem; int mats_in_smem, sens_in_smem; };   // doubles used in each space
 
-// Carve one CTA's workspace out of a flat double array; returns the number of doubles used.
-// Called with base == nullptr to measure.
-DG_HD size_t carve_workspace(const Dims& D, double* base, Workspace& W) {
-  size_t off = 0;
-  const size_t n = D.n, m = D.m, nq = D.nq, N = D.N, M = D.M;
-#define CARVE(ptr, cnt) do { (ptr) = base ? base + off : nullptr; off += (((size_t)(cnt)) + 1) & ~(size_t)1; } while (0)
-  CARVE(W.E.x, (N + 1) * nq); CARVE(W.E.AB, N * M * 48); CARVE(W.E.T2, N * M * 90);
-  CARVE(W.E.S, M * N * 3 * 2 * N); CARVE(W.E.g, m); CARVE(W.E.q, n); CARVE(W.E.gtl, n);
-  CARVE(W.E.cst, (M + 1) * (N + 1) * nq); CARVE(W.E.Hc, (M + 1) * N * M * 15); CARVE(W.E.Vbuf, 2 * (M + 1) * nq * nq);
-  CARVE(W.E.Q, n * n); CARVE(W.E.Wrow, (M + 1) * nq * n); CARVE(W.E.tmpS, M * N * 3); CARVE(W.E.cf, M * N * 3);
-  CARVE(W.B.W, n * n); CARVE(W.B.dg, n); CARVE(W.B.od, n); CARVE(W.B.od2, n); CARVE(W.B.tau, n);
-  CARVE(W.B.lam, n); CARVE(W.B.Z, DG_EIG_CHUNK * n); CARVE(W.B.itw, DG_EIG_CHUNK * 5 * n);
-  W.Q.Y = W.B.W;                        // the tridiagonalisation workspace is free once H is formed
-  CARVE(W.Q.Rm, n * n); CARVE(W.Q.xq, n); CARVE(W.Q.dv, n); CARVE(W.Q.zv, n); CARVE(W.Q.rv, n); CARVE(W.Q.npv, n);
-  CARVE(W.Q.lam_act, n); CARVE(W.Q.sl, m); CARVE(W.Q.lam, m);
-  { double* t; CARVE(t, (n + 1) / 2 + 1); W.Q.act = (int*)t; CARVE(t, (m + 1) / 2 + 1); W.Q.is_act = (int*)t; }
-  CARVE(W.L.Ub, DG_LSQR_BASIS * m); CARVE(W.L.Vb, DG_LSQR_BASIS * m); CARVE(W.L.cf, DG_LSQR_BASIS);
-  CARVE(W.L.u, m); CARVE(W.L.v, m); CARVE(W.L.w, m); CARVE(W.L.x, m); CARVE(W.L.tn, n); CARVE(W.L.tm, m);
-  CARVE(W.S.u, n); CARVE(W.S.l, m); CARVE(W.S.u_im1, n); CARVE(W.S.l_im1, m);
-  CARVE(W.S.du, n); CARVE(W.S.dl, m); CARVE(W.S.s, m); CARVE(W.S.ds, m);
-  CARVE(W.S.u_t, n); CARVE(W.S.l_t, m); CARVE(W.S.du_t, n); CARVE(W.S.dl_t, m); CARVE(W.S.s_t, m); CARVE(W.S.ds_t, m);
-  CARVE(W.S.u_c, n); CARVE(W.S.l_c, m); CARVE(W.S.Gdu, m); CARVE(W.S.tn, n); CARVE(W.S.tn2, n);
-  CARVE(W.S.Hm, n * n); CARVE(W.S.up, D.nu);
-#undef CARVE
-  return off;
+// Memory plan of one CTA (= one game instance in flight).  Everything a latency-bound phase walks through
+// lives in shared memory when it fits (budget `sbudget` doubles), the rest in the CTA's slice of global
+// workspace.  Layout decisions, in priority order:
+//   POOL   small hot vectors: trajectory, constraint values, gradients, the phase-aliased 8n region
+//          (tridiagonal data | Cholesky panel | active-set vectors), slacks, active-set bookkeeping
+//   ARENA  two n x ld matrices matA | matB (see LinBuf).  While the game is being evaluated no matrix is alive
+//          and the arena holds the per-stage derivative data instead (AB, costates, contracted second
+//          derivatives, value-function Hessians, the Hessian-DP rows)
+//   SENS   packed sensitivity rows (alive from the evaluation through the QP and the merit computation)
+//   then the SQP iterate vectors while room remains.
+// The raw game Hessian Q, the LSQR Krylov basis and the cold SQP vectors stay in global memory (streamed
+// with coalesced accesses, never on a dependent chain).
+// Called with null bases to measure; decisions depend only on (D, sbudget).
+DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sbudget, Workspace& W) {
+  size_t so = 0, go = 0;
+  const size_t n = D.n, m = D.m, nq = D.nq, N = D.N, M = D.M, ld = D.ld;
+  auto rnd = [](size_t c) { return (c + 1) & ~(size_t)1; };
+#define GTAKE(ptr, cnt) do { (ptr) = gbase ? gbase + go : nullptr; go += rnd(cnt); } while (0)
+#define STAKE(ptr, cnt) do { (ptr) = sbase ? sbase + so : nullptr; so += rnd(cnt); } while (0)
+#define PLACE(ptr, cnt) do { if (so + rnd(cnt) <= sbudget) STAKE(ptr, cnt); else GTAKE(ptr, cnt); } while (0)
+  MemPlan P; P.mats_in_smem = 0; P.sens_in_smem = 0;
+  // ---- POOL
+  PLACE(W.E.x, (N + 1) * nq); PLACE(W.E.g, m); PLACE(W.E.q, n); PLACE(W.E.gtl, n);
+  PLACE(W.E.tmpS, M * N * 3); PLACE(W.E.cf, M * N * 3); PLACE(W.S.up, D.nu);
+  {
+    double* reg8 = nullptr;
+    PLACE(reg8, 8 * n);
+    double* z = reg8;
+    auto at = [&](size_t k) { return z ? z + k * n : nullptr; };
+    W.B.dg = at(0); W.B.od = at(1); W.B.od2 = at(2); W.B.tau = at(3); W.B.lam = at(4); W.B.pv = at(5); W.B.wv = at(6);
+    W.B.sp = at(0);                                              // n * DG_CHOL_NB, DG_CHOL_NB == 8
+    W.Q.xq = at(0); W.Q.dv = at(1); W.Q.zv = at(2); W.Q.rv = at(3); W.Q.npv = at(4); W.Q.lam_act = at(5);
+  }
+  PLACE(W.Q.sl, m);
+  PLACE(W.B.part, (n > DG_MAX_THREADS ? n : DG_MAX_THREADS));
+  { double* t; PLACE(t, (n + 1) / 2 + 1); W.Q.act = (int*)t; PLACE(t, (m + 1) / 2 + 1); W.Q.is_act = (int*)t; }
+  // ---- ARENA
+  const size_t ev_a = rnd(N * M * 48) + rnd((M + 1) * (N + 1) * nq) + rnd((M + 1) * N * M * 15) + rnd(2 * (M + 1) * nq * nq) +
+                      rnd((M + 1) * nq * n) + rnd(N * M * 90);
+  const size_t mats = 2 * rnd(n * ld);
+  const size_t arena = ev_a > mats ? ev_a : mats;
+  double* ar = nullptr;
+  if (so + arena <= sbudget) { STAKE(ar, arena); P.mats_in_smem = 1; } else GTAKE(ar, arena);
+  {
+    size_t o = 0;
+    auto sub = [&](size_t cnt) { double* r = ar ? ar + o : nullptr; o += rnd(cnt); return r; };
+    W.E.AB = sub(N * M * 48); W.E.cst = sub((M + 1) * (N + 1) * nq); W.E.Hc = sub((M + 1) * N * M * 15);
+    W.E.Vbuf = sub(2 * (M + 1) * nq * nq); W.E.Wrow = sub((M + 1) * nq * n); W.E.T2 = sub(N * M * 90);
+    W.B.ld = (int)ld; W.B.matA = ar; W.B.matB = ar ? ar + rnd(n * ld) : nullptr;
+  }
+  // ---- SENS
+  if (so + rnd(M * D.sens_sz) <= sbudget) { STAKE(W.E.S, M * D.sens_sz); P.sens_in_smem = 1; } else GTAKE(W.E.S, M * D.sens_sz);
+  // ---- SQP iterate vectors, hottest first
+  PLACE(W.S.u, n); PLACE(W.S.du, n); PLACE(W.S.l, m); PLACE(W.S.dl, m); PLACE(W.Q.lam, m);
+  PLACE(W.S.u_c, n); PLACE(W.S.l_c, m); PLACE(W.S.s, m); PLACE(W.S.ds, m); PLACE(W.S.Gdu, m);
+  PLACE(W.S.tn, n); PLACE(W.S.tn2, n);
+  // ---- global only
+  GTAKE(W.E.Q, n * n); GTAKE(W.B.Zg, n * n);
+  GTAKE(W.L.Ub, DG_LSQR_BASIS * m); GTAKE(W.L.Vb, DG_LSQR_BASIS * m); GTAKE(W.L.cf, DG_LSQR_BASIS);
+  GTAKE(W.L.u, m); GTAKE(W.L.v, m); GTAKE(W.L.w, m); GTAKE(W.L.x, m); GTAKE(W.L.tn, n); GTAKE(W.L.tm, m);
+  GTAKE(W.S.u_im1, n); GTAKE(W.S.l_im1, m);
+  GTAKE(W.S.u_t, n); GTAKE(W.S.l_t, m); GTAKE(W.S.du_t, n); GTAKE(W.S.dl_t, m); GTAKE(W.S.s_t, m); GTAKE(W.S.ds_t, m);
+#undef GTAKE
+#undef STAKE
+#undef PLACE
+  P.smem = so; P.gmem = go;
+  return P;
 }
 
 struct SolveCtx {
@@ -71,7 +109,7 @@ struct SolveCtx {
   Workspace W;
   const double* x0;
   // counters (uniform across threads)
-  int n_evals_full, n_evals_grad, n_gi_iters, n_neg_max;
+  int n_evals_full, n_evals_grad, n_gi_iters, n_neg_max, n_qp_indef, n_neg_sum, n_act_sum, n_ls_trials;
 };
 
 // _evaluate(u, l, hessian=True)
@@ -149,11 +187,15 @@ DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du
   c.sync();
   game_GT_times(c, D, E, dl, S.tn2);
   // tn = Q du (raw, unsymmetrised Q -- DGSQP.py:416 passes Q_i)
-  DG_FOR(i, n) {
+  // (Q streams from global memory: warp per row, lanes along the row)
+  for (int i = c.warp; i < n; i += c.nwarps) {
+    const double* DG_RESTRICT Qi = E.Q + (size_t)i * n;
     double acc = 0.0;
-    for (int j = 0; j < n; ++j) acc += E.Q[i * n + j] * du[j];
-    S.tn[i] = acc;
+    for (int j = c.lane; j < n; j += c.wsz) acc += Qi[j] * du[j];
+    acc = c.warp_sum(acc);
+    if (c.lane == 0) S.tn[i] = acc;
   }
+  c.sync();
   double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0, p5 = 0.0, p6 = 0.0;
   DG_FOR(i, n) { double d = E.q[i] + E.gtl[i]; p1 += d * d; p2 += d * (S.tn[i] + S.tn2[i]); }
   DG_FOR(r, m) {
@@ -176,11 +218,12 @@ DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du
 // _solve_qp at the currently evaluated point.  Result in W.Q.xq / W.Q.lam.  Returns 0 on success.
 DG_DEVN int solve_qp_here(Cta& c, SolveCtx& X) {
   const Dims& D = X.D;
-  int nneg = nearest_pd(c, D.n, X.W.E.Q, X.W.S.Hm, X.W.B, X.P->eig_floor, X.P->reg, X.P->conv_approx != 0);
+  int nneg = nearest_pd(c, D.n, X.W.E.Q, X.W.B, X.P->eig_floor, X.P->reg, X.P->conv_approx != 0);
   if (nneg > X.n_neg_max) X.n_neg_max = nneg;
+  if (nneg > 0) { ++X.n_qp_indef; X.n_neg_sum += nneg; }
   int it = 0, na = 0;
-  int st = qp_solve_gi(c, D, X.W.E, X.W.S.Hm, X.W.E.q, X.W.Q, X.W.B, &it, &na);
-  X.n_gi_iters += it;
+  int st = qp_solve_gi(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na);
+  X.n_gi_iters += it; X.n_act_sum += na;
   return st;
 }
 
@@ -194,6 +237,7 @@ DG_DEVN double line_search_3(Cta& c, SolveCtx& X, const double* u, const double*
     DG_FOR(j, D.n) S.u_c[j] = u[j] + alpha * du[j];
     DG_FOR(r, D.m) S.l_c[r] = l[r] + alpha * dl[r];
     eval_grad(c, X, S.u_c, S.l_c, false);
+    ++X.n_ls_trials;
     phi_t = merit_here(c, X, S.l_c, s, ds, alpha, mu);
     if (phi_t <= phi0 + X.P->beta * alpha * dphi0) break;
     alpha *= X.P->tau;
@@ -292,7 +336,7 @@ struct SolveOut {
   double* cost;   // M
   double* cond;   // 3: p_feas, comp, stat
   int* num_iters; int* status; int* qp_solves;
-  int* diag;      // 4: full evals, grad evals, GI iterations, max #negative eigenvalues  (may be null)
+  int* diag;      // DG_NDIAG work counters (may be null), see dgsqp_last_diag
   double* l_init; // m  (may be null): dual initialisation
 };
 
@@ -300,7 +344,7 @@ struct SolveOut {
 DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double* l_ws, const SolveOut& O) {
   const Dims& D = X.D; SqpBuf& S = X.W.S; const EvalBuf& E = X.W.E; const SolverParams& P = *X.P;
   const int n = D.n, m = D.m;
-  X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = 0;
+  X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0;
   DG_FOR(j, n) S.u[j] = u_ws[j];
   DG_FOR(r, m) S.l[r] = 0.0;
   DG_FOR(j, D.nu) S.up[j] = 0.0;
@@ -386,7 +430,10 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
   if (c.tid == 0) {
     O.cond[0] = p_feas; O.cond[1] = comp; O.cond[2] = stat;
     *O.num_iters = sqp_it; *O.status = status; *O.qp_solves = total_qp;
-    if (O.diag) { O.diag[0] = X.n_evals_full; O.diag[1] = X.n_evals_grad; O.diag[2] = X.n_gi_iters; O.diag[3] = X.n_neg_max; }
+    if (O.diag) {
+      O.diag[0] = X.n_evals_full; O.diag[1] = X.n_evals_grad; O.diag[2] = X.n_gi_iters; O.diag[3] = X.n_neg_max;
+      O.diag[4] = X.n_qp_indef; O.diag[5] = X.n_neg_sum; O.diag[6] = X.n_act_sum; O.diag[7] = X.n_ls_trials;
+    }
   }
   c.sync();
 }

@@ -225,7 +225,7 @@ class DGSQP:
     def last_diag(self, B):
         """[B, 4] int32: full evaluations, gradient-only evaluations, QP active-set iterations,
         max number of negative Hessian eigenvalues -- of the last solve_batch."""
-        d = np.empty((B, 4), dtype=np.int32)
+        d = np.empty((B, _abi.NDIAG), dtype=np.int32)
         _abi.check(self._lib.dgsqp_last_diag(self._h, B, d.ctypes.data_as(C.c_void_p)))
         return d
 
@@ -236,6 +236,15 @@ class DGSQP:
         d = np.empty((B, k), dtype=np.int64)
         _abi.check(self._lib.dgsqp_last_phase_cycles(self._h, B, d.ctypes.data_as(C.c_void_p)))
         return d
+
+    def memory_plan(self):
+        """dict(smem_bytes, gmem_bytes, mats_in_smem, sens_in_smem) of one CTA."""
+        o = (C.c_int64 * 4)()
+        _abi.check(self._lib.dgsqp_memory_plan(self._h, o))
+        return dict(smem_bytes=int(o[0]), gmem_bytes=int(o[1]), mats_in_smem=bool(o[2]), sens_in_smem=bool(o[3]))
+
+    def set_smem_limit(self, nbytes):
+        _abi.check(self._lib.dgsqp_set_smem_limit(self._h, int(nbytes)))
 
     def configure(self, ctas_per_sm=0, threads=0):
         _abi.check(self._lib.dgsqp_configure(self._h, int(ctas_per_sm), int(threads)))

@@ -116,8 +116,10 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
                             double* l_out, double* x_out, double* cost_out, double* cond_out, int32_t* num_iters,
                             int32_t* status, int32_t* qp_solves, void* stream);
 
-/* Per-instance diagnostics of the LAST solve_batch on this handle (device->host copy), 4 ints each:
- * full evaluations, gradient-only evaluations, QP active-set iterations, max #negative eigenvalues. */
+/* Per-instance work counters of the LAST solve_batch on this handle (device->host copy), DGSQP_NDIAG = 8 ints each:
+ * full evaluations, gradient-only evaluations, QP active-set iterations, max #negative eigenvalues of a Hessian,
+ * QPs whose Hessian was indefinite, sum of #negative eigenvalues, sum of final active-set sizes, line-search trials. */
+#define DGSQP_NDIAG 8
 int dgsqp_last_diag(dgsqp_handle* h, int32_t B, int32_t* diag);
 
 /* Per-instance phase profile of the LAST solve_batch: dgsqp_phase_count() SM-clock cycle counters per
@@ -135,7 +137,14 @@ int dgsqp_measure_fp64_peak(int device, double* tflops);
 /* Number of kernels launched by this library since load (for bench accounting). */
 int64_t dgsqp_kernel_launches(void);
 
-/* Grid configuration: CTAs per SM (0 = default) and threads per CTA (0 = default 128). */
+/* Memory placement of one CTA (one game instance in flight): out[0] = dynamic shared memory bytes, out[1] = global
+ * workspace bytes, out[2] = 1 when the two n x n work matrices are shared-memory resident, out[3] = 1 when the packed
+ * sensitivity rows are.  dgsqp_set_smem_limit caps the shared memory the planner may use (0 = device maximum);
+ * with a small cap everything falls back to the global workspace (used by the tests to cover both placements). */
+int dgsqp_memory_plan(const dgsqp_handle* h, int64_t out[4]);
+int dgsqp_set_smem_limit(dgsqp_handle* h, int64_t bytes);
+
+/* Grid configuration: CTAs per SM (0 = as many as fit) and threads per CTA (0 = default 256, at most 512). */
 int dgsqp_configure(dgsqp_handle* h, int32_t ctas_per_sm, int32_t threads);
 
 const char* dgsqp_last_error(void);

@@ -25,7 +25,7 @@ st = r.status.cpu().numpy(); it = r.num_iters.cpu().numpy(); qp = r.qp_solves.cp
 print(f"B {B} threads {threads} ctas/SM {ctas}: {el:.3f} s -> {B/el:.1f} solves/s, converged {int((st<=1).sum())}, iters/s {it.sum()/el:.0f}")
 print("status hist", np.bincount(st, minlength=5), "mean iters", it.mean(), "mean qp", qp.mean())
 d = solver.last_diag(B)
-print("diag mean [full evals, grad evals, GI iters, max nneg]:", d.mean(axis=0), "max", d.max(axis=0))
+print("diag mean [full evals, grad evals, GI iters, max nneg, indef QPs, sum nneg, sum active, ls trials]:", d.mean(axis=0), "max", d.max(axis=0))
 ph = solver.last_phase_cycles(B).astype(np.float64)
 tot = ph.sum()
 print("phase shares (of CTA cycles) and mean kcycles per instance:")

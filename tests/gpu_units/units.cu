@@ -9,7 +9,7 @@ struct UnitArgs {
   int B; const double* x0; const double* u; const double* l;
   double *Q, *q, *gtl, *g, *H, *du, *lam, *l0;
   int *nneg, *qpst, *qpit, *lsqr_it;
-  double* ws; size_t ws_stride;
+  double* ws; size_t ws_stride; size_t smem_doubles;
 };
 
 __global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArgs A) {
@@ -19,8 +19,7 @@ __global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArg
   Cta c; c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
   c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red; c.flip = 0; c.ph = s_ph;
   SolveCtx X; X.G = Gp; X.P = Pp; X.D = make_dims(Gp->M, Gp->N);
-  carve_workspace(X.D, A.ws + (size_t)blockIdx.x * A.ws_stride, X.W);
-  carve_shared(X.D, s_dyn, X.W);
+  plan_memory(X.D, A.ws + (size_t)blockIdx.x * A.ws_stride, s_dyn, A.smem_doubles, X.W);
   const Dims& D = X.D; const int n = D.n, m = D.m;
   for (int inst = blockIdx.x; inst < A.B; inst += gridDim.x) {
     X.x0 = A.x0 + (size_t)inst * D.nq;
@@ -32,11 +31,11 @@ __global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArg
     DG_FOR(t, n * n) A.Q[(size_t)inst * n * n + t] = X.W.E.Q[t];
     DG_FOR(t, n) { A.q[(size_t)inst * n + t] = X.W.E.q[t]; A.gtl[(size_t)inst * n + t] = X.W.E.gtl[t]; }
     DG_FOR(t, m) A.g[(size_t)inst * m + t] = X.W.E.g[t];
-    int nneg = nearest_pd(c, n, X.W.E.Q, X.W.S.Hm, X.W.B, Pp->eig_floor, Pp->reg, Pp->conv_approx != 0);
-    DG_FOR(t, n * n) A.H[(size_t)inst * n * n + t] = X.W.S.Hm[t];
+    int nneg = nearest_pd(c, n, X.W.E.Q, X.W.B, Pp->eig_floor, Pp->reg, Pp->conv_approx != 0);
+    DG_FOR(t, n * n) A.H[(size_t)inst * n * n + t] = X.W.B.matA[(t / n) * D.ld + (t % n)];
     c.sync();
     int it = 0, na = 0;
-    int st = qp_solve_gi(c, D, X.W.E, X.W.S.Hm, X.W.E.q, X.W.Q, X.W.B, &it, &na);
+    int st = qp_solve_gi(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na);
     DG_FOR(t, n) A.du[(size_t)inst * n + t] = X.W.Q.xq[t];
     DG_FOR(t, m) A.lam[(size_t)inst * m + t] = X.W.Q.lam[t];
     c.sync();
@@ -52,20 +51,25 @@ __global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArg
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e)); return -2; } } while (0)
 
-extern "C" int units_run(const dgsqp_racing_game* game, const dgsqp_params* params, int B, int threads, const double* x0,
+extern "C" int units_run(const dgsqp_racing_game* game, const dgsqp_params* params, int B, int threads, long smem_limit_doubles, const double* x0,
                          const double* u, const double* l, double* Q, double* q, double* gtl, double* g, double* H,
                          double* du, double* lam, double* l0, int* nneg, int* qpst, int* qpit, int* lsqr_it) {
   GameDesc G; SolverParams P;
   if (dg_fill_game(game, &G) || dg_fill_params(params, &P)) return -1;
   Dims D = make_dims(G.M, G.N);
-  Workspace tmp; size_t wsd = carve_workspace(D, nullptr, tmp);
+  int optin = 0; CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0));
+  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, units_kernel));
+  size_t budget = ((size_t)optin - fa.sharedSizeBytes - 64) / sizeof(double);
+  if (smem_limit_doubles > 0 && (size_t)smem_limit_doubles < budget) budget = (size_t)smem_limit_doubles;
+  Workspace tmp; MemPlan pl = plan_memory(D, nullptr, nullptr, budget, tmp);
+  size_t wsd = pl.gmem;
   const size_t n = D.n, m = D.m;
   GameDesc* dG; SolverParams* dP; double* ws;
   CK(cudaMalloc(&dG, sizeof(G))); CK(cudaMalloc(&dP, sizeof(P)));
   CK(cudaMemcpy(dG, &G, sizeof(G), cudaMemcpyHostToDevice)); CK(cudaMemcpy(dP, &P, sizeof(P), cudaMemcpyHostToDevice));
   int grid = B < 64 ? B : 64;
   CK(cudaMalloc(&ws, sizeof(double) * wsd * grid)); CK(cudaMemset(ws, 0, sizeof(double) * wsd * grid));
-  UnitArgs A; A.B = B; A.ws = ws; A.ws_stride = wsd;
+  UnitArgs A; A.B = B; A.ws = ws; A.ws_stride = wsd; A.smem_doubles = budget;
   double *dx0, *du_, *dl_;
   CK(cudaMalloc(&dx0, 8 * B * D.nq)); CK(cudaMalloc(&du_, 8 * B * n)); CK(cudaMalloc(&dl_, 8 * B * m));
   CK(cudaMemcpy(dx0, x0, 8 * B * D.nq, cudaMemcpyHostToDevice)); CK(cudaMemcpy(du_, u, 8 * B * n, cudaMemcpyHostToDevice));
@@ -75,7 +79,8 @@ extern "C" int units_run(const dgsqp_racing_game* game, const dgsqp_params* para
   CK(cudaMalloc(&A.g, 8 * B * m)); CK(cudaMalloc(&A.du, 8 * B * n)); CK(cudaMalloc(&A.lam, 8 * B * m)); CK(cudaMalloc(&A.l0, 8 * B * m));
   CK(cudaMalloc(&A.nneg, 4 * B)); CK(cudaMalloc(&A.qpst, 4 * B)); CK(cudaMalloc(&A.qpit, 4 * B)); CK(cudaMalloc(&A.lsqr_it, 4 * B));
   cudaDeviceSetLimit(cudaLimitStackSize, 8192);
-  size_t smem = sizeof(double) * (size_t)D.n * (2 + DG_CHOL_NB);
+  size_t smem = sizeof(double) * pl.smem;
+  CK(cudaFuncSetAttribute(units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   units_kernel<<<grid, threads, smem>>>(dG, dP, A);
   CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(Q, A.Q, 8 * B * n * n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(H, A.H, 8 * B * n * n, cudaMemcpyDeviceToHost));

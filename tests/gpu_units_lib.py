@@ -22,7 +22,7 @@ def build():
     return out
 
 
-def run_stages(game, params, x0, u, l, threads=128):
+def run_stages(game, params, x0, u, l, threads=128, smem_limit_doubles=0):
     """evaluate -> nearestPD -> QP at (u, l), and the LSQR dual initialisation at u, for a batch."""
     lib = C.CDLL(str(build()))
     B, n, m = x0.shape[0], game.n, game.m
@@ -33,7 +33,7 @@ def run_stages(game, params, x0, u, l, threads=128):
                lsqr_it=np.zeros(B, np.int32))
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     gs, ps = game.to_struct(), params_to_struct(params)
-    rc = lib.units_run(C.byref(gs), C.byref(ps), B, threads, p(x0), p(u), p(l), p(out["Q"]), p(out["q"]),
+    rc = lib.units_run(C.byref(gs), C.byref(ps), B, threads, C.c_long(smem_limit_doubles), p(x0), p(u), p(l), p(out["Q"]), p(out["q"]),
                        p(out["gtl"]), p(out["g"]), p(out["H"]), p(out["du"]), p(out["lam"]), p(out["l0"]),
                        p(out["nneg"]), p(out["qpst"]), p(out["qpit"]), p(out["lsqr_it"]))
     assert rc == 0, f"units_run failed: {rc}"

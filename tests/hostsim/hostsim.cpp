@@ -18,11 +18,12 @@ void* hs_create(const dgsqp_racing_game* g, const dgsqp_params* p) {
   if (dg_fill_game(g, &h->G) != 0 || dg_fill_params(p, &h->P) != 0) { delete h; return nullptr; }
   h->D = make_dims(h->G.M, h->G.N);
   Workspace tmp;
-  size_t cnt = carve_workspace(h->D, nullptr, tmp);
-  h->ws.assign(cnt, 0.0);
-  carve_workspace(h->D, h->ws.data(), h->W);
-  h->sh.assign(carve_shared(h->D, nullptr, tmp), 0.0);
-  carve_shared(h->D, h->sh.data(), h->W);
+  const char* lim = getenv("DG_HOSTSIM_SMEM_DOUBLES");      // tests cover both placements
+  size_t budget = lim ? (size_t)atol(lim) : 28000;
+  MemPlan pl = plan_memory(h->D, nullptr, nullptr, budget, tmp);
+  h->ws.assign(pl.gmem + 2, 0.0);
+  h->sh.assign(pl.smem + 2, 0.0);
+  plan_memory(h->D, h->ws.data(), h->sh.data(), budget, h->W);
   return h;
 }
 void hs_set_l0_perturb(void* hp, double v) { ((HsHandle*)hp)->P.dbg_l0_perturb = v; }
@@ -52,15 +53,17 @@ void hs_GT_times(void* hp, const double* w, double* y) { HsHandle* h = (HsHandle
 
 int hs_nearest_pd(void* hp, const double* Qin, double* Hout) {
   HsHandle* h = (HsHandle*)hp; Cta c;
-  int nn = nearest_pd(c, h->D.n, Qin, h->W.S.Hm, h->W.B, h->P.eig_floor, h->P.reg, h->P.conv_approx != 0);
-  memcpy(Hout, h->W.S.Hm, sizeof(double) * h->D.n * h->D.n);
+  int nn = nearest_pd(c, h->D.n, Qin, h->W.B, h->P.eig_floor, h->P.reg, h->P.conv_approx != 0);
+  for (int i = 0; i < h->D.n; ++i) memcpy(Hout + (size_t)i * h->D.n, h->W.B.matA + (size_t)i * h->D.ld, sizeof(double) * h->D.n);
   return nn;
 }
 // QP at the last evaluated point with the given H (n*n, destroyed) and q
 int hs_qp(void* hp, double* H, const double* q, double* du, double* lam, int* iters) {
   HsHandle* h = (HsHandle*)hp; Cta c;
   int na = 0;
-  int st = qp_solve_gi(c, h->D, h->W.E, H, q, h->W.Q, h->W.B, iters, &na);
+  for (int i = 0; i < h->D.n; ++i) memcpy(h->W.B.matA + (size_t)i * h->D.ld, H + (size_t)i * h->D.n, sizeof(double) * h->D.n);
+  std::vector<double> qc(q, q + h->D.n);      // q may alias workspace the solver reuses
+  int st = qp_solve_gi(c, h->D, h->W.E, qc.data(), h->W.Q, h->W.B, iters, &na);
   memcpy(du, h->W.Q.xq, sizeof(double) * h->D.n);
   memcpy(lam, h->W.Q.lam, sizeof(double) * h->D.m);
   return st;

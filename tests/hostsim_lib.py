@@ -111,7 +111,7 @@ class HostSim:
         u, l, x = np.zeros(n), np.zeros(m), np.zeros((self.game.N + 1, self.nq))
         cost, cond = np.zeros(self.game.M), np.zeros(3)
         it, st, qp = C.c_int(0), C.c_int(0), C.c_int(0)
-        diag = np.zeros(4, dtype=np.int32)
+        diag = np.zeros(8, dtype=np.int32)
         l_init = np.zeros(m)
         if l_ws is not None:
             l_ws = np.ascontiguousarray(l_ws, dtype=np.float64)
