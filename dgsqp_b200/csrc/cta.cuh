@@ -24,7 +24,11 @@ enum { PH_LIN_FULL = 0, PH_ADJ_FULL, PH_HESS, PH_PD_TRIDIAG, PH_PD_EIG, PH_CHOL,
 #define DG_CONST static const
 #define DG_RESTRICT
 struct Cta {
-  int tid = 0, nt = 1, lane = 0, warp = 0, nwarps = 1;
+  inline int tid() const { return 0; }
+  inline int nt() const { return 1; }
+  inline int lane() const { return 0; }
+  inline int warp() const { return 0; }
+  inline int nwarps() const { return 1; }
   static constexpr int wsz = 1;   // lanes per warp
   double* red = nullptr;
   inline void sync() {}
@@ -49,15 +53,24 @@ struct Cta {
 #define DG_DEVN __device__ __noinline__
 #define DG_CONST __device__ const
 #define DG_RESTRICT __restrict__
+// CTA-wide scratch of the reductions (2 buffers x 160 doubles) and the phase counters: file-scope shared
+// variables, so no pointer has to be fetched from the (local-memory resident) Cta object
+__shared__ double dg_s_red[320];
+__shared__ long long dg_s_ph[DG_NPHASE + 1];
+
 struct Cta {
-  int tid, nt, lane, warp, nwarps;
+  // thread coordinates come straight from the special registers: a Cta is passed by reference through
+  // non-inlined functions, so data members would be re-read from local memory all over the hot loops
+  __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
+  __device__ __forceinline__ int nt() const { return (int)blockDim.x; }
+  __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31u); }
+  __device__ __forceinline__ int warp() const { return (int)(threadIdx.x >> 5); }
+  __device__ __forceinline__ int nwarps() const { return (int)((blockDim.x + 31u) >> 5); }
   static constexpr int wsz = 32;  // lanes per warp
-  double* red;   // shared scratch: 2 buffers x 160 doubles
   // phase profile: cycles between consecutive lap() calls are charged to the phase named by the later call
   // (thread 0 only; counters live in shared memory: ph[0..DG_NPHASE) cycles, ph[DG_NPHASE] = time of the last lap)
-  long long* ph;
   __device__ __forceinline__ void lap(int id) {
-    if (tid == 0) { long long t = clock64(); ph[id] += t - ph[DG_NPHASE]; ph[DG_NPHASE] = t; }
+    if (tid() == 0) { long long t = clock64(); dg_s_ph[id] += t - dg_s_ph[DG_NPHASE]; dg_s_ph[DG_NPHASE] = t; }
   }
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ double warp_sum(double v) {
@@ -68,13 +81,13 @@ struct Cta {
   // Block reductions use two alternating scratch buffers, so one barrier per reduction suffices: a thread
   // can only reach the next reduction that reuses a buffer after passing the barrier of the one in between.
   int flip = 0;
-  __device__ __forceinline__ double* next_buf() { flip ^= 1; return red + flip * 160; }
+  __device__ __forceinline__ double* next_buf() { flip ^= 1; return dg_s_red + flip * 160; }
   __device__ __forceinline__ void syncwarp() { __syncwarp(); }
   // sum of the nwarps (<= 16) per-warp partials at b[0..]: fixed pairwise tree, identical in every thread
   __device__ __forceinline__ double tree16(const double* b) const {
     double t[16];
 #pragma unroll
-    for (int w = 0; w < 16; ++w) t[w] = w < nwarps ? b[w] : 0.0;
+    for (int w = 0; w < 16; ++w) t[w] = w < nwarps() ? b[w] : 0.0;
 #pragma unroll
     for (int s = 8; s > 0; s >>= 1)
 #pragma unroll
@@ -84,28 +97,28 @@ struct Cta {
   __device__ __forceinline__ double sum(double v) {
     v = warp_sum(v);
     double* b = next_buf();
-    if (lane == 0) b[warp] = v;
+    if (lane() == 0) b[warp()] = v;
     __syncthreads();
     return tree16(b);
   }
   __device__ __forceinline__ void sum2(double& a0, double& a1) {
     a0 = warp_sum(a0); a1 = warp_sum(a1);
     double* b = next_buf();
-    if (lane == 0) { b[warp] = a0; b[32 + warp] = a1; }
+    if (lane() == 0) { b[warp()] = a0; b[32 + warp()] = a1; }
     __syncthreads();
     a0 = tree16(b); a1 = tree16(b + 32);
   }
   __device__ __forceinline__ void sum3(double& a0, double& a1, double& a2) {
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     double* b = next_buf();
-    if (lane == 0) { b[warp] = a0; b[32 + warp] = a1; b[64 + warp] = a2; }
+    if (lane() == 0) { b[warp()] = a0; b[32 + warp()] = a1; b[64 + warp()] = a2; }
     __syncthreads();
     a0 = tree16(b); a1 = tree16(b + 32); a2 = tree16(b + 64);
   }
   __device__ __forceinline__ void sum4(double& a0, double& a1, double& a2, double& a3) {
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
     double* b = next_buf();
-    if (lane == 0) { b[warp] = a0; b[32 + warp] = a1; b[64 + warp] = a2; b[96 + warp] = a3; }
+    if (lane() == 0) { b[warp()] = a0; b[32 + warp()] = a1; b[64 + warp()] = a2; b[96 + warp()] = a3; }
     __syncthreads();
     a0 = tree16(b); a1 = tree16(b + 32); a2 = tree16(b + 64); a3 = tree16(b + 96);
   }
@@ -113,10 +126,10 @@ struct Cta {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     double* b = next_buf();
-    if (lane == 0) b[warp] = v;
+    if (lane() == 0) b[warp()] = v;
     __syncthreads();
     double r = b[0];
-    for (int w = 1; w < nwarps; ++w) r = fmax(r, b[w]);
+    for (int w = 1; w < nwarps(); ++w) r = fmax(r, b[w]);
     return r;
   }
   __device__ __forceinline__ void max3(double& a0, double& a1, double& a2) {
@@ -127,10 +140,10 @@ struct Cta {
       a2 = fmax(a2, __shfl_xor_sync(0xffffffffu, a2, o));
     }
     double* b = next_buf();
-    if (lane == 0) { b[warp] = a0; b[32 + warp] = a1; b[64 + warp] = a2; }
+    if (lane() == 0) { b[warp()] = a0; b[32 + warp()] = a1; b[64 + warp()] = a2; }
     __syncthreads();
     double r0 = b[0], r1 = b[32], r2 = b[64];
-    for (int w = 1; w < nwarps; ++w) { r0 = fmax(r0, b[w]); r1 = fmax(r1, b[32 + w]); r2 = fmax(r2, b[64 + w]); }
+    for (int w = 1; w < nwarps(); ++w) { r0 = fmax(r0, b[w]); r1 = fmax(r1, b[32 + w]); r2 = fmax(r2, b[64 + w]); }
     a0 = r0; a1 = r1; a2 = r2;
   }
   __device__ __forceinline__ double min(double v) { return -max(-v); }
@@ -138,20 +151,20 @@ struct Cta {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
     int* b = (int*)next_buf();
-    if (lane == 0) b[warp] = v;
+    if (lane() == 0) b[warp()] = v;
     __syncthreads();
     int r = b[0];
-    for (int w = 1; w < nwarps; ++w) { int t = b[w]; r = t < r ? t : r; }
+    for (int w = 1; w < nwarps(); ++w) { int t = b[w]; r = t < r ? t : r; }
     return r;
   }
   __device__ __forceinline__ int isum(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     int* b = (int*)next_buf();
-    if (lane == 0) b[warp] = v;
+    if (lane() == 0) b[warp()] = v;
     __syncthreads();
     int r = 0;
-    for (int w = 0; w < nwarps; ++w) r += b[w];
+    for (int w = 0; w < nwarps(); ++w) r += b[w];
     return r;
   }
   __device__ __forceinline__ void argmin(double v, int idx, double& ov, int& oi) {
@@ -162,10 +175,10 @@ struct Cta {
       if (v2 < v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
     }
     double* b = next_buf();
-    if (lane == 0) { b[warp] = v; ((int*)(b + 32))[warp] = idx; }
+    if (lane() == 0) { b[warp()] = v; ((int*)(b + 32))[warp()] = idx; }
     __syncthreads();
     ov = b[0]; oi = ((int*)(b + 32))[0];
-    for (int w = 1; w < nwarps; ++w) {
+    for (int w = 1; w < nwarps(); ++w) {
       double v2 = b[w]; int i2 = ((int*)(b + 32))[w];
       if (v2 < ov || (v2 == ov && i2 < oi)) { ov = v2; oi = i2; }
     }
@@ -173,10 +186,10 @@ struct Cta {
 };
 #endif
 
-#define DG_FOR(i, n) for (int i = c.tid; i < (n); i += c.nt)
+#define DG_FOR(i, n) for (int i = c.tid(); i < (n); i += c.nt())
 // same loop with the thread numbering rotated by `off`: lets independent phases inside one barrier interval run on
 // different warps instead of piling up on the low thread ids
-#define DG_FOR_OFF(i, n, off) for (int i = (c.tid + c.nt - ((off) % c.nt)) % c.nt; i < (n); i += c.nt)
+#define DG_FOR_OFF(i, n, off) for (int i = (c.tid() + c.nt() - ((off) % c.nt())) % c.nt(); i < (n); i += c.nt())
 
 // 2D decomposition of a (len columns) x (depth) iteration space over the CTA: consecutive threads own consecutive
 // columns (conflict-free / coalesced), the G column groups interleave the depth index.
@@ -184,10 +197,10 @@ struct Cta {
 struct Split2 { int i0, istep, g, G; };
 DG_DEV Split2 split2(const Cta& c, int len) {
   int cw = (len + Cta::wsz - 1) / Cta::wsz * Cta::wsz;
-  if (cw > c.nt) cw = c.nt;
+  if (cw > c.nt()) cw = c.nt();
   if (cw < 1) cw = 1;
   Split2 s;
-  s.G = c.nt / cw; s.g = c.tid / cw; s.i0 = c.tid - s.g * cw; s.istep = cw;
+  s.G = c.nt() / cw; s.g = c.tid() / cw; s.i0 = c.tid() - s.g * cw; s.istep = cw;
   if (s.g >= s.G) s.i0 = len;                  // leftover threads idle
   return s;
 }

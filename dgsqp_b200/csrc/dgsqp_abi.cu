@@ -39,10 +39,8 @@ struct KernelArgs {
 __global__ void __launch_bounds__(DG_MAX_THREADS, 1) dgsqp_solve_kernel(const GameDesc* __restrict__ Gp, const SolverParams* __restrict__ Pp, KernelArgs A) {
   __shared__ GameDesc sG;
   __shared__ SolverParams sP;
-  __shared__ double s_red[320];
   extern __shared__ double s_dyn[];
   __shared__ int s_inst;
-  __shared__ long long s_ph[DG_NPHASE + 1];
   {
     const int nw = (int)(sizeof(GameDesc) / sizeof(int));
     for (int i = threadIdx.x; i < nw; i += blockDim.x) ((int*)&sG)[i] = ((const int*)Gp)[i];
@@ -51,11 +49,16 @@ __global__ void __launch_bounds__(DG_MAX_THREADS, 1) dgsqp_solve_kernel(const Ga
   }
   __syncthreads();
   Cta c;
-  c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
-  c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red; c.flip = 0; c.ph = s_ph;
-  SolveCtx X;
-  X.G = &sG; X.P = &sP; X.D = make_dims(sG.M, sG.N);
-  plan_memory(X.D, A.ws + (size_t)blockIdx.x * A.ws_stride, s_dyn, A.smem_doubles, X.W);
+  c.flip = 0;
+  // the solve context (dimensions + the table of buffer pointers) lives in shared memory: in a per-thread
+  // local-memory copy every buffer access of the solver would start with a local load
+  __shared__ SolveCtx sX;
+  if (threadIdx.x == 0) {
+    sX.G = &sG; sX.P = &sP; sX.D = make_dims(sG.M, sG.N);
+    plan_memory(sX.D, A.ws + (size_t)blockIdx.x * A.ws_stride, s_dyn, A.smem_doubles, sX.W);
+  }
+  __syncthreads();
+  SolveCtx& X = sX;
   const Dims& D = X.D;
   while (true) {
     if (threadIdx.x == 0) s_inst = atomicAdd(A.counter, 1);
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(DG_MAX_THREADS, 1) dgsqp_solve_kernel(const Ga
     const int inst = s_inst;
     __syncthreads();
     if (inst >= A.B) break;
-    X.x0 = A.x0 + (size_t)inst * D.nq;
+    if (threadIdx.x == 0) X.x0 = A.x0 + (size_t)inst * D.nq;
     SolveOut O;
     O.u = A.u_out + (size_t)inst * D.n;
     O.l = A.l_out + (size_t)inst * D.m;
@@ -73,10 +76,10 @@ __global__ void __launch_bounds__(DG_MAX_THREADS, 1) dgsqp_solve_kernel(const Ga
     O.num_iters = A.num_iters + inst; O.status = A.status + inst; O.qp_solves = A.qp_solves + inst;
     O.diag = A.diag ? A.diag + (size_t)inst * DG_NDIAG : nullptr;
     O.l_init = nullptr;
-    if (threadIdx.x == 0) { for (int i = 0; i < DG_NPHASE; ++i) s_ph[i] = 0; s_ph[DG_NPHASE] = clock64(); }
+    if (threadIdx.x == 0) { for (int i = 0; i < DG_NPHASE; ++i) dg_s_ph[i] = 0; dg_s_ph[DG_NPHASE] = clock64(); }
     sqp_solve_v1(c, X, A.u_ws + (size_t)inst * D.n, A.l_ws ? A.l_ws + (size_t)inst * D.m : nullptr, O);
     c.lap(PH_OTHER);
-    if (threadIdx.x == 0 && A.phase) for (int i = 0; i < DG_NPHASE; ++i) A.phase[(size_t)inst * DG_NPHASE + i] = s_ph[i];
+    if (threadIdx.x == 0 && A.phase) for (int i = 0; i < DG_NPHASE; ++i) A.phase[(size_t)inst * DG_NPHASE + i] = dg_s_ph[i];
   }
 }
 

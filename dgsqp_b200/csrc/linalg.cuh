@@ -44,7 +44,9 @@ struct LinBuf {
 // to tridiagonal form; reflector k is stored in W[k+2.., k] (v[0] = 1 implicit) with tau[k].
 // Both O(len^2) parts of a step -- p = tau A22 v and A22 -= v w' + w v' -- are spread over the whole CTA with the 2D
 // decomposition (thread = column, column groups interleave the rows).  Four barriers per step.
-DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B) {
+DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const LinBuf B = B_;
   double* DG_RESTRICT W = B.matA;
   const int ld = B.ld;
   double* DG_RESTRICT pv = B.pv;
@@ -52,7 +54,7 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B) {
   double* DG_RESTRICT part = B.part;
   // norm of the first column below the sub-diagonal
   double nrm = 0.0;
-  for (int i = c.tid + 2; i < n; i += c.nt) { double xv = W[i * ld]; nrm += xv * xv; }
+  for (int i = c.tid() + 2; i < n; i += c.nt()) { double xv = W[i * ld]; nrm += xv * xv; }
   double xn2 = c.sum(nrm);
   for (int k = 0; k + 1 < n; ++k) {
     const int len = n - k - 1;            // x = W[k+1.., k]
@@ -64,11 +66,11 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B) {
       tauk = (beta - alpha) / beta;
       scale = 1.0 / (alpha - beta);
     }
-    if (c.tid == 0) { B.dg[k] = W[k * ld + k]; B.od[k] = beta; B.od2[k] = beta * beta; B.tau[k] = tauk; }
+    if (c.tid() == 0) { B.dg[k] = W[k * ld + k]; B.od[k] = beta; B.od2[k] = beta * beta; B.tau[k] = tauk; }
     if (tauk == 0.0) {
       // nothing to annihilate: next column norm straight from memory
       nrm = 0.0;
-      for (int i = c.tid + 2; i < len; i += c.nt) { double xv = W[(off + i) * ld + off]; nrm += xv * xv; }
+      for (int i = c.tid() + 2; i < len; i += c.nt()) { double xv = W[(off + i) * ld + off]; nrm += xv * xv; }
       xn2 = c.sum(nrm);
       continue;
     }
@@ -116,7 +118,7 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B) {
     }
     xn2 = c.sum(nrm);
   }
-  if (c.tid == 0) { B.dg[n - 1] = W[(n - 1) * ld + (n - 1)]; B.od[n - 1] = 0.0; B.od2[n - 1] = 0.0; }
+  if (c.tid() == 0) { B.dg[n - 1] = W[(n - 1) * ld + (n - 1)]; B.od[n - 1] = 0.0; B.od2[n - 1] = 0.0; }
   c.sync();
 }
 
@@ -190,25 +192,25 @@ DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, doubl
                                  double* lo, double* hi, int* cnts) {
   DG_FOR(j, nneg) { lo[j] = -tnorm * 1.0000001 - pivmin; hi[j] = 0.0; }
   c.sync();
-  int per = c.nt / nneg;                       // probes per eigenvalue per round
+  int per = c.nt() / nneg;                       // probes per eigenvalue per round
   if (per < 1) per = 1;
-  const int groups = c.nt / per;               // eigenvalues refined concurrently
+  const int groups = c.nt() / per;               // eigenvalues refined concurrently
   int rounds = (int)ceil(54.0 * 0.6931471805599453 / log((double)per + 1.0));
   if (rounds < 1) rounds = 1;
   for (int j0 = 0; j0 < nneg; j0 += groups) {
-    const int g = c.tid / per, t = c.tid - g * per, j = j0 + g;
+    const int g = c.tid() / per, t = c.tid() - g * per, j = j0 + g;
     const bool act = g < groups && j < nneg;
     for (int rd = 0; rd < rounds; ++rd) {
       double a = 0.0, b = 0.0, h = 0.0;
       if (act) {
         a = lo[j]; b = hi[j];
         h = (b - a) / (double)(per + 1);
-        cnts[c.tid] = sturm_count(n, B.dg, B.od2, a + h * (double)(t + 1), pivmin);
+        cnts[c.tid()] = sturm_count(n, B.dg, B.od2, a + h * (double)(t + 1), pivmin);
       }
       c.sync();
       if (act) {
         // the probe where the count first reaches j+1 narrows the bracket (exactly one thread per eigenvalue writes)
-        const bool mine = cnts[c.tid] >= j + 1, prev = t > 0 && cnts[c.tid - 1] >= j + 1;
+        const bool mine = cnts[c.tid()] >= j + 1, prev = t > 0 && cnts[c.tid() - 1] >= j + 1;
         if (mine && !prev) { if (t > 0) lo[j] = a + h * (double)t; hi[j] = a + h * (double)(t + 1); }
         else if (!mine && t == per - 1) lo[j] = a + h * (double)per;
       }
@@ -221,8 +223,10 @@ DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, doubl
 
 // matA <- nearestPD(Qraw) + reg*I  (n x n, leading dimension B.ld).  Qraw is row-major n x n (global memory, read
 // twice).  matB is scratch.  Returns the number of negative eigenvalues (uniform across threads).
-DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinBuf& B,
+DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinBuf& B_,
                        double floor_val, double reg, bool conv_approx) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const LinBuf B = B_;
   const int ld = B.ld;
   double* DG_RESTRICT Hm = B.matA;
   c.lap(PH_OTHER);
@@ -250,7 +254,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
       const int CH = DG_EIG_CHUNK;
       double* scr = B.matB;
       int* cnts = (int*)scr;
-      double* itw = scr + ((c.nt + 1) / 2 + 1);
+      double* itw = scr + ((c.nt() + 1) / 2 + 1);
       double* Zt = itw + 5 * n * CH;
       double* Zs = Zt + n * CH;
       const long cap = ((long)n * ld - (Zs - scr)) / n;    // eigenvectors that fit behind the scratch
@@ -276,7 +280,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
           }
           c.sync();
           if (cluster) {
-            if (c.warp == 0) {                   // modified Gram-Schmidt inside clusters, lanes along the vectors
+            if (c.warp() == 0) {                   // modified Gram-Schmidt inside clusters, lanes along the vectors
               for (int jj = 1; jj < kc; ++jj) {
                 double* z = Zt + jj;
                 bool changed = false;
@@ -284,17 +288,17 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
                   if (fabs(B.lam[j0 + jj] - B.lam[j0 + ii]) > 1e-3 * tnorm) continue;
                   const double* zi = Zt + ii;
                   double dt = 0.0;
-                  for (int i = c.lane; i < n; i += c.wsz) dt += zi[i * CH] * z[i * CH];
+                  for (int i = c.lane(); i < n; i += c.wsz) dt += zi[i * CH] * z[i * CH];
                   dt = c.warp_sum(dt);
-                  for (int i = c.lane; i < n; i += c.wsz) z[i * CH] -= dt * zi[i * CH];
+                  for (int i = c.lane(); i < n; i += c.wsz) z[i * CH] -= dt * zi[i * CH];
                   c.syncwarp();
                   changed = true;
                 }
                 if (changed) {
                   double nr = 0.0;
-                  for (int i = c.lane; i < n; i += c.wsz) nr += z[i * CH] * z[i * CH];
+                  for (int i = c.lane(); i < n; i += c.wsz) nr += z[i * CH] * z[i * CH];
                   nr = 1.0 / sqrt(c.warp_sum(nr));
-                  for (int i = c.lane; i < n; i += c.wsz) z[i * CH] *= nr;
+                  for (int i = c.lane(); i < n; i += c.wsz) z[i * CH] *= nr;
                   c.syncwarp();
                 }
               }
@@ -303,11 +307,11 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
           }
         }
         // de-interleave the chunk into the vector-major store
-        for (int e = c.tid; e < kc * n; e += c.nt) { int jj = e / n, i = e - jj * n; Z[(size_t)(j0 + jj) * n + i] = Zt[i * CH + jj]; }
+        for (int e = c.tid(); e < kc * n; e += c.nt()) { int jj = e / n, i = e - jj * n; Z[(size_t)(j0 + jj) * n + i] = Zt[i * CH + jj]; }
         c.sync();
       }
       // back-transform y = H_0 H_1 ... H_{n-2} z (last reflector first): one warp per eigenvector, no CTA barrier inside
-      for (int jv = c.warp; jv < nneg; jv += c.nwarps) {
+      for (int jv = c.warp(); jv < nneg; jv += c.nwarps()) {
         double* DG_RESTRICT z = Z + (size_t)jv * n;
         for (int k = n - 3; k >= 0; --k) {
           const double tk = B.tau[k];
@@ -315,9 +319,9 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
           const int len = n - k - 1;
           const double* DG_RESTRICT vcol = Hm + (k + 1) * ld + k;
           double pp = 0.0;
-          for (int i = c.lane; i < len; i += c.wsz) pp += (i == 0 ? 1.0 : vcol[i * ld]) * z[k + 1 + i];
+          for (int i = c.lane(); i < len; i += c.wsz) pp += (i == 0 ? 1.0 : vcol[i * ld]) * z[k + 1 + i];
           pp = c.warp_sum(pp) * tk;
-          for (int i = c.lane; i < len; i += c.wsz) z[k + 1 + i] -= pp * (i == 0 ? 1.0 : vcol[i * ld]);
+          for (int i = c.lane(); i < len; i += c.wsz) z[k + 1 + i] -= pp * (i == 0 ? 1.0 : vcol[i * ld]);
           c.syncwarp();
         }
       }
@@ -349,12 +353,12 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, doubl
     const int nb = n - k0 < NB ? n - k0 : NB;
     const int rows = n - k0;
     // stage panel rows k0.. : sp[(i-k0)*NB + t] = Hm[i][k0+t]
-    for (int e = c.tid; e < rows * NB; e += c.nt) {
+    for (int e = c.tid(); e < rows * NB; e += c.nt()) {
       int r = e / NB, t = e - r * NB;
       sp[e] = t < nb ? Hm[(k0 + r) * ld + k0 + t] : 0.0;
     }
     c.sync();
-    if (c.warp == 0) {
+    if (c.warp() == 0) {
       bool ok = true;
       for (int kk = 0; kk < nb; ++kk) {
         double piv = sp[kk * NB + kk];
@@ -362,7 +366,7 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, doubl
         if (!(piv > 0.0)) ok = false;
         const double inv = 1.0 / sqrt(piv);
         c.syncwarp();                               // pivot read by every lane before it is overwritten
-        for (int r = kk + c.lane; r < nb; r += c.wsz) {
+        for (int r = kk + c.lane(); r < nb; r += c.wsz) {
           double v;
           if (r == kk) { v = piv * inv; scr[kk] = inv; }          // sqrt(piv)
           else {
@@ -374,12 +378,12 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, doubl
         }
         c.syncwarp();
       }
-      if (c.lane == 0) scr[NB] = ok ? 1.0 : 0.0;
+      if (c.lane() == 0) scr[NB] = ok ? 1.0 : 0.0;
     }
     c.sync();
     if (scr[NB] == 0.0) return false;
     // panel rows below the diagonal block: x Ld' = a, row by row (thread = row)
-    for (int r = nb + c.tid; r < rows; r += c.nt) {
+    for (int r = nb + c.tid(); r < rows; r += c.nt()) {
       double x[NB];
 #pragma unroll
       for (int kk = 0; kk < NB; ++kk) {
@@ -393,7 +397,7 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, doubl
     }
     c.sync();
     // write the finished panel back (upper part of the diagonal block is left untouched: never read)
-    for (int e = c.tid; e < rows * NB; e += c.nt) {
+    for (int e = c.tid(); e < rows * NB; e += c.nt()) {
       int r = e / NB, t = e - r * NB;
       if (t < nb && t <= r) Hm[(k0 + r) * ld + k0 + t] = sp[e];
     }
@@ -402,9 +406,9 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, doubl
     const int j0 = k0 + nb;
     const int ncol = n - j0;
     if (ncol > 0) {
-      int groups = c.nt / ncol;
+      int groups = c.nt() / ncol;
       if (groups < 1) groups = 1;
-      for (int e = c.tid; e < ncol * groups; e += c.nt) {
+      for (int e = c.tid(); e < ncol * groups; e += c.nt()) {
         const int gi = e / ncol, j = j0 + (e - gi * ncol);
         double lj[NB];
 #pragma unroll
@@ -434,13 +438,13 @@ DG_DEVN void tri_inverse(Cta& c, int n, int ld, const double* DG_RESTRICT Lm, do
 #ifdef DG_HOSTSIM
   const int TG = 1;
 #else
-  const int TG = c.nt >= 4 * n ? 4 : (c.nt >= 2 * n ? 2 : 1);
+  const int TG = c.nt() >= 4 * n ? 4 : (c.nt() >= 2 * n ? 2 : 1);
 #endif
-  const int ngroups = c.nt / TG;
-  const int s = c.tid % TG;
-  const int wfirst = (c.tid - c.lane) / TG;        // first column group of this warp
+  const int ngroups = c.nt() / TG;
+  const int s = c.tid() % TG;
+  const int wfirst = (c.tid() - c.lane()) / TG;        // first column group of this warp
   for (int base = 0; base + wfirst < n; base += ngroups) {       // warp-uniform trip count
-    const int cc = base + c.tid / TG;
+    const int cc = base + c.tid() / TG;
     const bool act = cc < n;
     if (act) {
       for (int i = s; i < cc; i += TG) Y[i * ld + cc] = 0.0;

@@ -59,12 +59,12 @@ DG_DEV double vec_norm(Cta& c, int len, const double* v) {
 DG_DEV void lsqr_reorth(Cta& c, int m, const double* basis, int nb, double* vec, double* cf) {
   for (int pass = 0; pass < 2; ++pass) {
     c.sync();
-    for (int j = c.warp; j < nb; j += c.nwarps) {
+    for (int j = c.warp(); j < nb; j += c.nwarps()) {
       const double* b = basis + (size_t)j * m;
       double p = 0.0;
-      for (int i = c.lane; i < m; i += c.wsz) p += b[i] * vec[i];
+      for (int i = c.lane(); i < m; i += c.wsz) p += b[i] * vec[i];
       p = c.warp_sum(p);
-      if (c.lane == 0) cf[j] = p;
+      if (c.lane() == 0) cf[j] = p;
     }
     c.sync();
     DG_FOR(i, m) {
@@ -77,7 +77,9 @@ DG_DEV void lsqr_reorth(Cta& c, int m, const double* basis, int nb, double* vec,
 }
 
 // l_out[m] = max(0, -x_lsqr).  Returns the iteration count.
-DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D, const EvalBuf& E, const LsqrBuf& L, const double* qv, double* l_out) {
+DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D_, const EvalBuf& E_, const LsqrBuf& L_, const double* qv, double* l_out) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; const LsqrBuf L = L_; const Dims D = D_;
   const int m = D.m;
   const double atol = 1e-6, btol = 1e-6, conlim = 1e8, eps = 2.220446049250313e-16;
   const int iter_lim = 2 * m;

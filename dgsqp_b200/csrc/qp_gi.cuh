@@ -62,8 +62,10 @@ DG_DEV void gi_cols_times(Cta& c, int n, int ld, const double* DG_RESTRICT Y, co
 
 // H (symmetric positive definite) is expected in B.matA and is destroyed.
 // returns 0 ok, 1 not PD, 2 infeasible, 3 iteration limit.  Output: Q.xq (du), Q.lam (l_hat).
-DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, const double* DG_RESTRICT qv,
-                        const QpBuf& Q, const LinBuf& B, int* n_iter_out, int* n_active_out) {
+DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double* DG_RESTRICT qv,
+                        const QpBuf& Q_, const LinBuf& B_, int* n_iter_out, int* n_active_out) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; const QpBuf Q = Q_; const LinBuf B = B_; const Dims D = D_;
   const int n = D.n, m = D.m, ld = B.ld;
   double* DG_RESTRICT Y = B.matB;
   double* DG_RESTRICT Rm = B.matA;
@@ -71,12 +73,12 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, const double* D
   c.lap(PH_CHOL);
   tri_inverse(c, n, ld, B.matA, Y);
   // x = -J J' q = -Y' (Y q):   t = Y q (warp per row), x_i = -sum_j Y[j][i] t_j
-  for (int j = c.warp; j < n; j += c.nwarps) {
+  for (int j = c.warp(); j < n; j += c.nwarps()) {
     const double* DG_RESTRICT Yj = Y + j * ld;
     double p = 0.0;
-    for (int i = c.lane; i <= j; i += c.wsz) p += Yj[i] * qv[i];
+    for (int i = c.lane(); i <= j; i += c.wsz) p += Yj[i] * qv[i];
     p = c.warp_sum(p);
-    if (c.lane == 0) Q.dv[j] = p;
+    if (c.lane() == 0) Q.dv[j] = p;
   }
   DG_FOR(r, m) { Q.is_act[r] = 0; Q.lam[r] = 0.0; }
   c.sync();
@@ -106,12 +108,12 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, const double* D
       if (++it > max_iter) { status = 3; break; }
       // d = J' n_p = -Y npv   (warp per row);  also npv . x
       double dd_tail = 0.0, dd_all = 0.0, gx = 0.0;
-      for (int j = c.warp; j < n; j += c.nwarps) {
+      for (int j = c.warp(); j < n; j += c.nwarps()) {
         const double* DG_RESTRICT Yj = Y + j * ld;
         double pp = 0.0;
-        for (int i = c.lane; i < n; i += c.wsz) pp += Yj[i] * Q.npv[i];
+        for (int i = c.lane(); i < n; i += c.wsz) pp += Yj[i] * Q.npv[i];
         pp = -c.warp_sum(pp);
-        if (c.lane == 0) {
+        if (c.lane() == 0) {
           Q.dv[j] = pp;
           dd_all += pp * pp;
           if (j >= iq) dd_tail += pp * pp;
@@ -142,14 +144,14 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, const double* D
             }
           }
         }
-        if (c.warp == c.nwarps - 1) {
-          for (int i = c.lane; i < iq; i += c.wsz) Q.rv[i] = Q.dv[i];
+        if (c.warp() == c.nwarps() - 1) {
+          for (int i = c.lane(); i < iq; i += c.wsz) Q.rv[i] = Q.dv[i];
           c.syncwarp();
           for (int i = iq - 1; i >= 0; --i) {
             const double ri = Q.rv[i] / Rm[i * ld + i];
             c.syncwarp();
-            if (c.lane == 0) Q.rv[i] = ri;
-            for (int j = c.lane; j < i; j += c.wsz) Q.rv[j] -= Rm[j * ld + i] * ri;
+            if (c.lane() == 0) Q.rv[i] = ri;
+            for (int j = c.lane(); j < i; j += c.wsz) Q.rv[j] -= Rm[j * ld + i] * ri;
             c.syncwarp();
           }
         }
@@ -190,7 +192,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, const double* D
           }
         }
         DG_FOR(i, iq) Rm[i * ld + iq] = Q.dv[i];
-        if (c.tid == 0) {
+        if (c.tid() == 0) {
           Rm[iq * ld + iq] = alpha;
           Q.act[iq] = p; Q.is_act[p] = 1; Q.lam_act[iq] = lam_p;
         }
@@ -200,7 +202,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, const double* D
       } else {
         c.sync();
         // partial step: drop active constraint ldrop (Givens re-triangularisation), keep p
-        if (c.tid == 0) {
+        if (c.tid() == 0) {
           Q.is_act[Q.act[ldrop]] = 0;
           for (int k = ldrop; k < iq - 1; ++k) { Q.act[k] = Q.act[k + 1]; Q.lam_act[k] = Q.lam_act[k + 1]; }
         }
@@ -215,7 +217,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, const double* D
           c.sync();                               // rotation parameters read before rows change
           if (h != 0.0) {
             double cs = a / h, sn = b / h;
-            for (int col = j + c.tid; col < iq - 1; col += c.nt) {
+            for (int col = j + c.tid(); col < iq - 1; col += c.nt()) {
               double r0 = Rm[j * ld + col], r1 = Rm[(j + 1) * ld + col];
               Rm[j * ld + col] = cs * r0 + sn * r1;
               Rm[(j + 1) * ld + col] = -sn * r0 + cs * r1;

@@ -139,7 +139,9 @@ struct EvalBuf {
 };
 
 // x_{k+1} = x_k + dt f(x_k,u_k): agents are dynamically decoupled, thread a rolls out agent a.
-DG_DEVN void game_rollout(Cta& c, const GameDesc& G, const Dims& D, const double* u, const double* x0, double* x) {
+DG_DEVN void game_rollout(Cta& c, const GameDesc& G, const Dims& D_, const double* u, const double* x0, double* x) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const Dims D = D_;
   DG_FOR(a, D.M) {
     double qk[DG_NQA];
     for (int i = 0; i < DG_NQA; ++i) { qk[i] = x0[a * DG_NQA + i]; x[a * DG_NQA + i] = qk[i]; }
@@ -152,7 +154,9 @@ DG_DEVN void game_rollout(Cta& c, const GameDesc& G, const Dims& D, const double
   }
 }
 
-DG_DEVN void game_linearize(Cta& c, const GameDesc& G, const Dims& D, const double* u, const EvalBuf& E, bool second) {
+DG_DEVN void game_linearize(Cta& c, const GameDesc& G, const Dims& D_, const double* u, const EvalBuf& E_, bool second) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; const Dims D = D_;
   DG_FOR(t, D.N * D.M) {
     int k = t / D.M, a = t - k * D.M;
     const double* qk = E.x + k * D.nq + a * DG_NQA;
@@ -165,8 +169,10 @@ DG_DEVN void game_linearize(Cta& c, const GameDesc& G, const Dims& D, const doub
 }
 
 // f_Cxu: one thread per row
-DG_DEVN void game_constraints(Cta& c, const GameDesc& G, const Dims& D, const double* u, const double* up,
+DG_DEVN void game_constraints(Cta& c, const GameDesc& G, const Dims& D_, const double* u, const double* up,
                               const double* x, double* g) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const Dims D = D_;
   DG_FOR(r, D.m) {
     int k, kind, a, b;
     decode_row(D, r, k, kind, a, b);
@@ -194,7 +200,9 @@ DG_DEVN void game_constraints(Cta& c, const GameDesc& G, const Dims& D, const do
 DG_DEV int sens_off(const Dims& D, int a, int k, int r) { return a * D.sens_sz + 3 * k * (k - 1) + r * 2 * k; }
 
 // Sensitivity rows (f_Du_x restricted to x, y, e_y): thread per input column (a, j).
-DG_DEVN void game_sens(Cta& c, const Dims& D, const EvalBuf& E) {
+DG_DEVN void game_sens(Cta& c, const Dims& D_, const EvalBuf& E_) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; const Dims D = D_;
   const int twoN = D.twoN;
   DG_FOR(t, D.M * twoN) {
     int a = t / twoN, j = t - a * twoN, kj = j >> 1, cc = j & 1;
@@ -226,7 +234,9 @@ DG_DEV double sens_dot(const Dims& D, const EvalBuf& E, int a, int k, int row, c
 }
 
 // y = G v   (v in R^n agent-major, y in R^m).  Two phases with one sync.
-DG_DEVN void game_G_times(Cta& c, const Dims& D, const EvalBuf& E, const double* v, double* y) {
+DG_DEVN void game_G_times(Cta& c, const Dims& D_, const EvalBuf& E_, const double* v, double* y) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; const Dims D = D_;
   c.sync();
   DG_FOR(t, D.M * D.N * 3) {
     int a = t / (D.N * 3), rem = t - a * D.N * 3, k1 = rem / 3, row = rem - k1 * 3;
@@ -284,7 +294,9 @@ DG_DEV double game_GT_direct(const Dims& D, const double* w, int a, int k, int c
 }
 
 // y = G' w  (w in R^m, y in R^n)
-DG_DEVN void game_GT_times(Cta& c, const Dims& D, const EvalBuf& E, const double* w, double* y) {
+DG_DEVN void game_GT_times(Cta& c, const Dims& D_, const EvalBuf& E_, const double* w, double* y) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; const Dims D = D_;
   c.sync();
   game_state_coefs(c, D, E, w, E.cf);
   c.sync();
@@ -302,7 +314,9 @@ DG_DEVN void game_GT_times(Cta& c, const Dims& D, const EvalBuf& E, const double
 }
 
 // dense row r of G into out[n] (all threads cooperate)
-DG_DEVN void game_G_row(Cta& c, const Dims& D, const EvalBuf& E, int r, double* out) {
+DG_DEVN void game_G_row(Cta& c, const Dims& D_, const EvalBuf& E_, int r, double* out) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; const Dims D = D_;
   int k, kind, a, b;
   decode_row(D, r, k, kind, a, b);
   DG_FOR(t, D.n) {
@@ -399,7 +413,9 @@ DG_DEV double con_lxx(const Dims& D, const double* l, int k, int i1, int i2) {
 
 // Costate chains  p_k = l_x,k + A_k' p_{k+1}:  thread per (function f, agent block b).
 // f < M: cost of agent f (state cost only at the terminal stage); f == M: l'C.
-DG_DEVN void game_costates(Cta& c, const GameDesc& G, const Dims& D, const EvalBuf& E, const double* l) {
+DG_DEVN void game_costates(Cta& c, const GameDesc& G, const Dims& D_, const EvalBuf& E_, const double* l) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; const Dims D = D_;
   DG_FOR(t, (D.M + 1) * D.M) {
     int f = t / D.M, b = t - f * D.M;
     double p[DG_NQA];
@@ -423,8 +439,10 @@ DG_DEVN void game_costates(Cta& c, const GameDesc& G, const Dims& D, const EvalB
 }
 
 // q (cost gradient, f_q) and G'l from the costates: thread per input (a,k,cc)
-DG_DEVN void game_gradients(Cta& c, const GameDesc& G, const Dims& D, const EvalBuf& E, const double* u,
+DG_DEVN void game_gradients(Cta& c, const GameDesc& G, const Dims& D_, const EvalBuf& E_, const double* u,
                             const double* up, const double* l) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; const Dims D = D_;
   DG_FOR(t, D.n) {
     int a = t / D.twoN, j = t - a * D.twoN, k = j >> 1, cc = j & 1;
     const double* Bk = E.AB + (k * D.M + a) * 48;
@@ -442,7 +460,9 @@ DG_DEVN void game_gradients(Cta& c, const GameDesc& G, const Dims& D, const Eval
 }
 
 // Hc[f][k][a][0..14] = sum_i p^f_{k+1}[a,i] * T2[k][a][i][:]
-DG_DEVN void game_contract(Cta& c, const Dims& D, const EvalBuf& E) {
+DG_DEVN void game_contract(Cta& c, const Dims& D_, const EvalBuf& E_) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; const Dims D = D_;
   DG_FOR(t, (D.M + 1) * D.N * D.M * 15) {
     int e = t % 15, r = t / 15;
     int a = r % D.M; r /= D.M;
@@ -472,7 +492,9 @@ DG_DEV double hc_uu(const double* hc, int c1, int c2) { return (c1 == 1 && c2 ==
 // E.Wrow[(f*nq + q)*n + r] (coalesced).  At stage k < k_r it emits H^f[r, (k,b,cc)] = w^f[b] . B^b_k[:,cc] and
 // stores  Q[r][(k,b,cc)] = H^{a_r} + H^M  and, by symmetry of each H^f,  Q[(k,b,cc)][r] = H^b + H^M.
 // Every entry of Q is written exactly once, so Q needs no zero-fill and no read-modify-write.
-DG_DEVN void game_hessian(Cta& c, const GameDesc& G, const Dims& D, const EvalBuf& E, const double* DG_RESTRICT l) {
+DG_DEVN void game_hessian(Cta& c, const GameDesc& G, const Dims& D_, const EvalBuf& E_, const double* DG_RESTRICT l) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; const Dims D = D_;
   const int n = D.n, nq = D.nq, N = D.N, M = D.M, F = D.M + 1;
   const double* xN = E.x + N * nq;
   double* Vcur = E.Vbuf;
@@ -484,7 +506,7 @@ DG_DEVN void game_hessian(Cta& c, const GameDesc& G, const Dims& D, const EvalBu
   c.sync();
   double* DG_RESTRICT Qm = E.Q;
   for (int k = N - 1; k >= 0; --k) {
-    for (int r = c.tid; r < n; r += c.nt) {
+    for (int r = c.tid(); r < n; r += c.nt()) {
       const int kr = r / D.nu, ar = (r - kr * D.nu) >> 1, cr = r & 1;
       const int rowQ = uidx(D, ar, kr, cr);
       double* DG_RESTRICT wr = E.Wrow + r;                     // w^f[q] at wr[(f*nq + q)*n]

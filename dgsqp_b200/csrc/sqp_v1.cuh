@@ -108,13 +108,13 @@ struct SolveCtx {
   Dims D;
   Workspace W;
   const double* x0;
-  // counters (uniform across threads)
+  // work counters (maintained by thread 0: the context is shared by the CTA)
   int n_evals_full, n_evals_grad, n_gi_iters, n_neg_max, n_qp_indef, n_neg_sum, n_act_sum, n_ls_trials;
 };
 
 // _evaluate(u, l, hessian=True)
 DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l) {
-  const Dims& D = X.D; const EvalBuf& E = X.W.E;
+  const Dims D = X.D; const EvalBuf E = X.W.E;
   c.sync();
   c.lap(PH_OTHER);
   game_rollout(c, *X.G, D, u, X.x0, E.x);
@@ -132,12 +132,12 @@ DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l) {
   c.lap(PH_ADJ_FULL);
   game_hessian(c, *X.G, D, E, l);
   c.lap(PH_HESS);
-  ++X.n_evals_full;
+  if (c.tid() == 0) ++X.n_evals_full;
 }
 
 // _evaluate(u, l, hessian=False): x, g, q, G'l only (sensitivities optional)
 DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l, bool with_sens) {
-  const Dims& D = X.D; const EvalBuf& E = X.W.E;
+  const Dims D = X.D; const EvalBuf E = X.W.E;
   c.sync();
   c.lap(PH_OTHER);
   game_rollout(c, *X.G, D, u, X.x0, E.x);
@@ -152,13 +152,13 @@ DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l, bo
   game_gradients(c, *X.G, D, E, u, X.W.S.up, l);
   c.sync();
   c.lap(PH_ADJ_GRAD);
-  ++X.n_evals_grad;
+  if (c.tid() == 0) ++X.n_evals_grad;
 }
 
 // phi at the currently evaluated point:  1/2 |q+G'l|^2 + 1/2 (l.g)^2 + mu * sum(g - (s + alpha*ds))
 DG_DEV double merit_here(Cta& c, SolveCtx& X, const double* l, const double* s, const double* ds, double alpha,
                          double mu) {
-  const Dims& D = X.D; const EvalBuf& E = X.W.E;
+  const Dims D = X.D; const EvalBuf E = X.W.E;
   double p1 = 0.0, p2 = 0.0, p3 = 0.0;
   DG_FOR(i, D.n) { double d = E.q[i] + E.gtl[i]; p1 += d * d; }
   DG_FOR(r, D.m) { p2 += l[r] * E.g[r]; p3 += E.g[r] - (s[r] + (ds ? alpha * ds[r] : 0.0)); }
@@ -174,7 +174,7 @@ DG_DEV double merit_here(Cta& c, SolveCtx& X, const double* l, const double* s, 
 // phi, dphi (and mu when compute_mu) -- f_phi / f_dphi / _get_mu.
 DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du, const double* l_hat,
                         double* dl, double* s, double* ds, bool compute_mu, double& mu, double& phi, double& dphi) {
-  const Dims& D = X.D; const EvalBuf& E = X.W.E; SqpBuf& S = X.W.S;
+  const Dims D = X.D; const EvalBuf E = X.W.E; const SqpBuf S = X.W.S;
   const int n = D.n, m = D.m;
   c.lap(PH_OTHER);
   game_G_times(c, D, E, du, S.Gdu);
@@ -188,12 +188,12 @@ DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du
   game_GT_times(c, D, E, dl, S.tn2);
   // tn = Q du (raw, unsymmetrised Q -- DGSQP.py:416 passes Q_i)
   // (Q streams from global memory: warp per row, lanes along the row)
-  for (int i = c.warp; i < n; i += c.nwarps) {
+  for (int i = c.warp(); i < n; i += c.nwarps()) {
     const double* DG_RESTRICT Qi = E.Q + (size_t)i * n;
     double acc = 0.0;
-    for (int j = c.lane; j < n; j += c.wsz) acc += Qi[j] * du[j];
+    for (int j = c.lane(); j < n; j += c.wsz) acc += Qi[j] * du[j];
     acc = c.warp_sum(acc);
-    if (c.lane == 0) S.tn[i] = acc;
+    if (c.lane() == 0) S.tn[i] = acc;
   }
   c.sync();
   double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0, p5 = 0.0, p6 = 0.0;
@@ -217,27 +217,29 @@ DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du
 
 // _solve_qp at the currently evaluated point.  Result in W.Q.xq / W.Q.lam.  Returns 0 on success.
 DG_DEVN int solve_qp_here(Cta& c, SolveCtx& X) {
-  const Dims& D = X.D;
+  const Dims D = X.D;
   int nneg = nearest_pd(c, D.n, X.W.E.Q, X.W.B, X.P->eig_floor, X.P->reg, X.P->conv_approx != 0);
-  if (nneg > X.n_neg_max) X.n_neg_max = nneg;
-  if (nneg > 0) { ++X.n_qp_indef; X.n_neg_sum += nneg; }
+  if (c.tid() == 0) {
+    if (nneg > X.n_neg_max) X.n_neg_max = nneg;
+    if (nneg > 0) { ++X.n_qp_indef; X.n_neg_sum += nneg; }
+  }
   int it = 0, na = 0;
   int st = qp_solve_gi(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na);
-  X.n_gi_iters += it; X.n_act_sum += na;
+  if (c.tid() == 0) { X.n_gi_iters += it; X.n_act_sum += na; }
   return st;
 }
 
 // _line_search_3: base (u,du,l,dl,s,ds) with phi0/dphi0; result left in (u_c, l_c); returns phi_trial
 DG_DEVN double line_search_3(Cta& c, SolveCtx& X, const double* u, const double* du, const double* l, const double* dl,
                              const double* s, const double* ds, double phi0, double dphi0, double mu) {
-  const Dims& D = X.D; SqpBuf& S = X.W.S;
+  const Dims D = X.D; const SqpBuf S = X.W.S;
   double alpha = 1.0, phi_t = 0.0;
   for (int i = 0; i < X.P->line_search_iters; ++i) {
     c.sync();
     DG_FOR(j, D.n) S.u_c[j] = u[j] + alpha * du[j];
     DG_FOR(r, D.m) S.l_c[r] = l[r] + alpha * dl[r];
     eval_grad(c, X, S.u_c, S.l_c, false);
-    ++X.n_ls_trials;
+    if (c.tid() == 0) ++X.n_ls_trials;
     phi_t = merit_here(c, X, S.l_c, s, ds, alpha, mu);
     if (phi_t <= phi0 + X.P->beta * alpha * dphi0) break;
     alpha *= X.P->tau;
@@ -249,7 +251,7 @@ DG_DEV void vcopy(Cta& c, int len, double* dst, const double* src) { DG_FOR(i, l
 
 // _watchdog_line_search_4.  On return the accepted iterate is in (S.u, S.l); returns extra QP count.
 DG_DEVN int watchdog_4(Cta& c, SolveCtx& X, double phi_k, double dphi_k, double mu) {
-  const Dims& D = X.D; SqpBuf& S = X.W.S; const SolverParams& P = *X.P;
+  const Dims D = X.D; const SqpBuf S = X.W.S; const SolverParams P = *X.P;
   const int n = D.n, m = D.m;
   int qp = 0;
   const double target = phi_k + P.beta * dphi_k;
@@ -260,7 +262,7 @@ DG_DEVN int watchdog_4(Cta& c, SolveCtx& X, double phi_k, double dphi_k, double 
   eval_grad(c, X, S.u_c, S.l_c, false);
   double phi1 = merit_here(c, X, S.l_c, S.s, S.ds, 1.0, mu);
 #ifdef DG_TRACE
-  if (c.tid == 0) printf("      full step phi1 %.12e  (accept %d)\n", phi1, (int)(phi1 <= target));
+  if (c.tid() == 0) printf("      full step phi1 %.12e  (accept %d)\n", phi1, (int)(phi1 <= target));
 #endif
   if (phi1 <= target) { c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync(); return qp; }
   bool fail = false;
@@ -342,9 +344,9 @@ struct SolveOut {
 
 // l_ws: optional dual warm start (nullptr = the reference's LSQR initialisation, DGSQP.py:312-326)
 DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double* l_ws, const SolveOut& O) {
-  const Dims& D = X.D; SqpBuf& S = X.W.S; const EvalBuf& E = X.W.E; const SolverParams& P = *X.P;
+  const Dims D = X.D; const SqpBuf S = X.W.S; const EvalBuf E = X.W.E; const SolverParams P = *X.P;
   const int n = D.n, m = D.m;
-  X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0;
+  if (c.tid() == 0) X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0;
   DG_FOR(j, n) S.u[j] = u_ws[j];
   DG_FOR(r, m) S.l[r] = 0.0;
   DG_FOR(j, D.nu) S.up[j] = 0.0;
@@ -388,7 +390,7 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
     double mu = 0.0, phi_k, dphi_k;
     step_merit(c, X, S.l, S.du, X.W.Q.lam, S.dl, S.s, S.ds, true, mu, phi_k, dphi_k);
 #ifdef DG_TRACE
-    if (c.tid == 0) printf("it %2d pf %.6e comp %.6e stat %.6e | mu %.12e phi_k %.12e dphi_k %.12e target %.12e\n", sqp_it, p_feas, comp, stat, mu, phi_k, dphi_k, phi_k + P.beta * dphi_k);
+    if (c.tid() == 0) printf("it %2d pf %.6e comp %.6e stat %.6e | mu %.12e phi_k %.12e dphi_k %.12e target %.12e\n", sqp_it, p_feas, comp, stat, mu, phi_k, dphi_k, phi_k + P.beta * dphi_k);
 #endif
     if (P.nonmono_ls) total_qp += watchdog_4(c, X, phi_k, dphi_k, mu);
     else {
@@ -427,7 +429,7 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
     for (int b = 0; b < D.M; ++b) if (b != a) J += X.G->c_comp * atan(xN[b * DG_NQA + 4] - xN[a * DG_NQA + 4]);
     O.cost[a] = J;
   }
-  if (c.tid == 0) {
+  if (c.tid() == 0) {
     O.cond[0] = p_feas; O.cond[1] = comp; O.cond[2] = stat;
     *O.num_iters = sqp_it; *O.status = status; *O.qp_solves = total_qp;
     if (O.diag) {

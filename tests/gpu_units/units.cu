@@ -13,16 +13,20 @@ struct UnitArgs {
 };
 
 __global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArgs A) {
-  __shared__ double s_red[320];
-  __shared__ long long s_ph[DG_NPHASE + 1];
   extern __shared__ double s_dyn[];
-  Cta c; c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
-  c.nwarps = (blockDim.x + 31) >> 5; c.red = s_red; c.flip = 0; c.ph = s_ph;
-  SolveCtx X; X.G = Gp; X.P = Pp; X.D = make_dims(Gp->M, Gp->N);
-  plan_memory(X.D, A.ws + (size_t)blockIdx.x * A.ws_stride, s_dyn, A.smem_doubles, X.W);
+  Cta c;
+  c.flip = 0;
+  __shared__ SolveCtx sX;
+  if (threadIdx.x == 0) {
+    sX.G = Gp; sX.P = Pp; sX.D = make_dims(Gp->M, Gp->N);
+    plan_memory(sX.D, A.ws + (size_t)blockIdx.x * A.ws_stride, s_dyn, A.smem_doubles, sX.W);
+  }
+  __syncthreads();
+  SolveCtx& X = sX;
   const Dims& D = X.D; const int n = D.n, m = D.m;
   for (int inst = blockIdx.x; inst < A.B; inst += gridDim.x) {
-    X.x0 = A.x0 + (size_t)inst * D.nq;
+    c.sync();
+    if (threadIdx.x == 0) X.x0 = A.x0 + (size_t)inst * D.nq;
     const double* u = A.u + (size_t)inst * n; const double* l = A.l + (size_t)inst * m;
     DG_FOR(j, D.nu) X.W.S.up[j] = 0.0;
     c.sync();
@@ -44,7 +48,7 @@ __global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArg
     eval_grad(c, X, u, X.W.S.l, true);
     int li = lsqr_dual_init(c, D, X.W.E, X.W.L, X.W.E.q, X.W.S.l);
     DG_FOR(t, m) A.l0[(size_t)inst * m + t] = X.W.S.l[t];
-    if (c.tid == 0) { A.nneg[inst] = nneg; A.qpst[inst] = st; A.qpit[inst] = it; A.lsqr_it[inst] = li; }
+    if (c.tid() == 0) { A.nneg[inst] = nneg; A.qpst[inst] = st; A.qpit[inst] = it; A.lsqr_it[inst] = li; }
     c.sync();
   }
 }
