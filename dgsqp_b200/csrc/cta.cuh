@@ -186,6 +186,14 @@ struct Cta {
 };
 #endif
 
+// Address-space hint: in the SM = true instantiation of the solver every hot buffer is known to be shared-memory
+// resident (plan_memory), which lets the compiler emit LDS/STS with 32-bit addressing instead of generic accesses.
+#ifdef DG_HOSTSIM
+#define DG_ASSUME_SHARED(p) do { } while (0)
+#else
+#define DG_ASSUME_SHARED(p) do { if (SM) __builtin_assume(__isShared((const void*)(p))); } while (0)
+#endif
+
 #define DG_FOR(i, n) for (int i = c.tid(); i < (n); i += c.nt())
 // same loop with the thread numbering rotated by `off`: lets independent phases inside one barrier interval run on
 // different warps instead of piling up on the low thread ids

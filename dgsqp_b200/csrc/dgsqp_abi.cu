@@ -36,6 +36,8 @@ struct KernelArgs {
   int* counter;
 };
 
+// SM = true: every hot buffer of the memory plan is shared-memory resident (plan.hot_in_smem)
+template <bool SM>
 __global__ void __launch_bounds__(DG_MAX_THREADS, 1) dgsqp_solve_kernel(const GameDesc* __restrict__ Gp, const SolverParams* __restrict__ Pp, KernelArgs A) {
   __shared__ GameDesc sG;
   __shared__ SolverParams sP;
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(DG_MAX_THREADS, 1) dgsqp_solve_kernel(const Ga
     O.diag = A.diag ? A.diag + (size_t)inst * DG_NDIAG : nullptr;
     O.l_init = nullptr;
     if (threadIdx.x == 0) { for (int i = 0; i < DG_NPHASE; ++i) dg_s_ph[i] = 0; dg_s_ph[DG_NPHASE] = clock64(); }
-    sqp_solve_v1(c, X, A.u_ws + (size_t)inst * D.n, A.l_ws ? A.l_ws + (size_t)inst * D.m : nullptr, O);
+    sqp_solve_v1<SM>(c, X, A.u_ws + (size_t)inst * D.n, A.l_ws ? A.l_ws + (size_t)inst * D.m : nullptr, O);
     c.lap(PH_OTHER);
     if (threadIdx.x == 0 && A.phase) for (int i = 0; i < DG_NPHASE; ++i) A.phase[(size_t)inst * DG_NPHASE + i] = dg_s_ph[i];
   }
@@ -123,7 +125,10 @@ static int ensure_grid(dgsqp_handle* h) {
     int optin = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, dgsqp_solve_kernel));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, dgsqp_solve_kernel<true>));
+    cudaFuncAttributes fb;
+    CUDA_TRY(cudaFuncGetAttributes(&fb, dgsqp_solve_kernel<false>));
+    if (fb.sharedSizeBytes > fa.sharedSizeBytes) fa.sharedSizeBytes = fb.sharedSizeBytes;
     size_t avail = (size_t)optin > fa.sharedSizeBytes + 64 ? ((size_t)optin - fa.sharedSizeBytes - 64) / sizeof(double) : 0;
     if (h->smem_limit && h->smem_limit < avail) avail = h->smem_limit;
     h->smem_budget = avail;
@@ -132,8 +137,13 @@ static int ensure_grid(dgsqp_handle* h) {
     h->ws_doubles = h->plan.gmem;
     h->smem_bytes = sizeof(double) * h->plan.smem;
   }
-  CUDA_TRY(cudaFuncSetAttribute(dgsqp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dgsqp_solve_kernel, h->threads, h->smem_bytes));
+  if (h->plan.hot_in_smem) {
+    CUDA_TRY(cudaFuncSetAttribute(dgsqp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dgsqp_solve_kernel<true>, h->threads, h->smem_bytes));
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(dgsqp_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dgsqp_solve_kernel<false>, h->threads, h->smem_bytes));
+  }
   if (occ < 1) return set_err(DGSQP_ECUDA, "kernel does not fit on an SM");
   int per_sm = h->ctas_per_sm > 0 ? (h->ctas_per_sm < occ ? h->ctas_per_sm : occ) : occ;
   int cap = per_sm * h->sm_count;
@@ -234,7 +244,8 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
   A.cond_out = cond_out; A.num_iters = num_iters; A.status = status; A.qp_solves = qp_solves; A.diag = h->d_diag; A.phase = h->d_phase;
   A.ws = h->d_ws; A.ws_stride = h->ws_doubles; A.smem_doubles = h->smem_budget; A.counter = h->d_counter;
   int grid = B < h->grid_cap ? B : h->grid_cap;
-  dgsqp_solve_kernel<<<grid, h->threads, h->smem_bytes, st>>>(h->d_G, h->d_P, A);
+  if (h->plan.hot_in_smem) dgsqp_solve_kernel<true><<<grid, h->threads, h->smem_bytes, st>>>(h->d_G, h->d_P, A);
+  else dgsqp_solve_kernel<false><<<grid, h->threads, h->smem_bytes, st>>>(h->d_G, h->d_P, A);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return DGSQP_OK;
@@ -338,7 +349,7 @@ int dgsqp_set_smem_limit(dgsqp_handle* h, int64_t bytes) {
 int dgsqp_memory_plan(const dgsqp_handle* h, int64_t out[4]) {
   if (!h || !out) return set_err(DGSQP_EINVAL, "NULL argument");
   out[0] = (int64_t)(h->plan.smem * sizeof(double)); out[1] = (int64_t)(h->plan.gmem * sizeof(double));
-  out[2] = h->plan.mats_in_smem; out[3] = h->plan.sens_in_smem;
+  out[2] = h->plan.mats_in_smem; out[3] = h->plan.sens_in_smem + 2 * h->plan.hot_in_smem;
   return DGSQP_OK;
 }
 

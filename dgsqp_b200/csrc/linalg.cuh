@@ -40,13 +40,18 @@ struct LinBuf {
   double* part;   // max(DG_MAX_THREADS, n)  partial sums of the 2D-decomposed products
 };
 
+#define DG_SH_LIN(B) do { DG_ASSUME_SHARED((B).matA); DG_ASSUME_SHARED((B).matB); DG_ASSUME_SHARED((B).dg); DG_ASSUME_SHARED((B).od); \
+  DG_ASSUME_SHARED((B).od2); DG_ASSUME_SHARED((B).tau); DG_ASSUME_SHARED((B).lam); DG_ASSUME_SHARED((B).pv); DG_ASSUME_SHARED((B).wv); \
+  DG_ASSUME_SHARED((B).sp); DG_ASSUME_SHARED((B).part); } while (0)
+
 // Householder reduction of the symmetric matrix W = B.matA (full storage, both triangles kept consistent)
 // to tridiagonal form; reflector k is stored in W[k+2.., k] (v[0] = 1 implicit) with tau[k].
 // Both O(len^2) parts of a step -- p = tau A22 v and A22 -= v w' + w v' -- are spread over the whole CTA with the 2D
 // decomposition (thread = column, column groups interleave the rows).  Four barriers per step.
+template <bool SM>
 DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const LinBuf B = B_;
+  const LinBuf B = B_; DG_SH_LIN(B);
   double* DG_RESTRICT W = B.matA;
   const int ld = B.ld;
   double* DG_RESTRICT pv = B.pv;
@@ -188,8 +193,10 @@ DG_DEV void tridiag_shift_solve(int n, const double* dg, const double* od, doubl
 // Negative eigenvalues of the tridiagonal matrix into B.lam[0..nneg): Sturm-count multisection.  All
 // eigenvalues are refined together: each round spends the CTA's nt probes evenly over the brackets.
 // lo/hi: nneg doubles each; cnts: nt ints of scratch.
+template <bool SM>
 DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, double tnorm, double pivmin,
                                  double* lo, double* hi, int* cnts) {
+  DG_ASSUME_SHARED(B.dg); DG_ASSUME_SHARED(B.od2); DG_ASSUME_SHARED(B.lam); DG_ASSUME_SHARED(lo); DG_ASSUME_SHARED(hi); DG_ASSUME_SHARED(cnts);
   DG_FOR(j, nneg) { lo[j] = -tnorm * 1.0000001 - pivmin; hi[j] = 0.0; }
   c.sync();
   int per = c.nt() / nneg;                       // probes per eigenvalue per round
@@ -223,10 +230,11 @@ DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, doubl
 
 // matA <- nearestPD(Qraw) + reg*I  (n x n, leading dimension B.ld).  Qraw is row-major n x n (global memory, read
 // twice).  matB is scratch.  Returns the number of negative eigenvalues (uniform across threads).
+template <bool SM>
 DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinBuf& B_,
                        double floor_val, double reg, bool conv_approx) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const LinBuf B = B_;
+  const LinBuf B = B_; DG_SH_LIN(B);
   const int ld = B.ld;
   double* DG_RESTRICT Hm = B.matA;
   c.lap(PH_OTHER);
@@ -239,7 +247,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
       Hm[i * ld + j] = 0.5 * (Qraw[i * n + j] + Qraw[j * n + i]);
     }
     c.sync();
-    sym_tridiag(c, n, B);
+    sym_tridiag<SM>(c, n, B);
     c.lap(PH_PD_TRIDIAG);
     double tn = 0.0;
     DG_FOR(i, n) {
@@ -259,7 +267,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
       double* Zs = Zt + n * CH;
       const long cap = ((long)n * ld - (Zs - scr)) / n;    // eigenvectors that fit behind the scratch
       double* Z = nneg <= cap ? Zs : B.Zg;
-      negative_eigenvalues(c, n, B, nneg, tnorm, pivmin, B.pv, B.wv, cnts);
+      negative_eigenvalues<SM>(c, n, B, nneg, tnorm, pivmin, B.pv, B.wv, cnts);
       // --- eigenvectors in chunks: inverse iteration (thread per vector), Gram-Schmidt inside clusters
       const double tiny = fmax(tnorm, 1.0) * 1.1e-16;
       for (int j0 = 0; j0 < nneg; j0 += CH) {
@@ -347,7 +355,9 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
 // synchronisation only), then thread r solves its own panel row against it, then the trailing lower triangle is
 // updated by the whole CTA.  Four barriers per panel.  scr: NB + 1 doubles of scratch.
 // Returns false (uniformly) on a non-positive pivot.
+template <bool SM>
 DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, double* DG_RESTRICT sp, double* DG_RESTRICT scr) {
+  DG_ASSUME_SHARED(Hm); DG_ASSUME_SHARED(sp); DG_ASSUME_SHARED(scr);
   constexpr int NB = DG_CHOL_NB;
   for (int k0 = 0; k0 < n; k0 += NB) {
     const int nb = n - k0 < NB ? n - k0 : NB;
@@ -434,7 +444,9 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, doubl
 // the whole inverse runs without a CTA barrier; lane s of a group stores (and later re-reads) the rows i with
 // (i - c) mod TG == s, i.e. it only ever reads what it wrote itself.
 // The GI solver uses J = L^{-T} = Y' through the accessor J(i,j) = Y[j*ld+i].
+template <bool SM>
 DG_DEVN void tri_inverse(Cta& c, int n, int ld, const double* DG_RESTRICT Lm, double* DG_RESTRICT Y) {
+  DG_ASSUME_SHARED(Lm); DG_ASSUME_SHARED(Y);
 #ifdef DG_HOSTSIM
   const int TG = 1;
 #else

@@ -43,11 +43,13 @@ DG_DEV void sym_ortho(double a, double b, double& cs, double& sn, double& r) {
 }
 
 // out = G (G' in)
+template <bool SM>
 DG_DEV void lsqr_A(Cta& c, const Dims& D, const EvalBuf& E, const LsqrBuf& L, const double* in, double* out) {
-  game_GT_times(c, D, E, in, L.tn);
-  game_G_times(c, D, E, L.tn, out);
+  game_GT_times<SM>(c, D, E, in, L.tn);
+  game_G_times<SM>(c, D, E, L.tn, out);
 }
 
+template <bool SM>
 DG_DEV double vec_norm(Cta& c, int len, const double* v) {
   double p = 0.0;
   DG_FOR(i, len) p += v[i] * v[i];
@@ -56,6 +58,7 @@ DG_DEV double vec_norm(Cta& c, int len, const double* v) {
 
 // vec <- (I - B B') vec, twice; B = first nb rows of basis (orthonormal).  Warp per basis vector for the
 // dot products, thread per element for the update.
+template <bool SM>
 DG_DEV void lsqr_reorth(Cta& c, int m, const double* basis, int nb, double* vec, double* cf) {
   for (int pass = 0; pass < 2; ++pass) {
     c.sync();
@@ -77,9 +80,10 @@ DG_DEV void lsqr_reorth(Cta& c, int m, const double* basis, int nb, double* vec,
 }
 
 // l_out[m] = max(0, -x_lsqr).  Returns the iteration count.
+template <bool SM>
 DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D_, const EvalBuf& E_, const LsqrBuf& L_, const double* qv, double* l_out) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; const LsqrBuf L = L_; const Dims D = D_;
+  const EvalBuf E = E_; DG_SH_EVAL(E); const LsqrBuf L = L_; const Dims D = D_;
   const int m = D.m;
   const double atol = 1e-6, btol = 1e-6, conlim = 1e8, eps = 2.220446049250313e-16;
   const int iter_lim = 2 * m;
@@ -87,9 +91,9 @@ DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D_, const EvalBuf& E_, const Lsqr
   int itn = 0, istop = 0;
   double anorm = 0, acond = 0, ddnorm = 0, res2 = 0, xnorm = 0, xxnorm = 0, z = 0, cs2 = -1, sn2 = 0;
   // b = G q -> u
-  game_G_times(c, D, E, qv, L.u);
+  game_G_times<SM>(c, D, E, qv, L.u);
   DG_FOR(i, m) L.x[i] = 0.0;
-  double bnorm = vec_norm(c, m, L.u);
+  double bnorm = vec_norm<SM>(c, m, L.u);
   double beta = bnorm, alfa = 0.0;
   int nU = 0, nV = 0;
   if (beta > 0.0) {
@@ -97,8 +101,8 @@ DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D_, const EvalBuf& E_, const Lsqr
     DG_FOR(i, m) { L.u[i] *= 1.0 / beta; L.Ub[i] = L.u[i]; }
     nU = 1;
     c.sync();
-    lsqr_A(c, D, E, L, L.u, L.v);
-    alfa = vec_norm(c, m, L.v);
+    lsqr_A<SM>(c, D, E, L, L.u, L.v);
+    alfa = vec_norm<SM>(c, m, L.v);
   } else {
     DG_FOR(i, m) L.v[i] = 0.0;
   }
@@ -112,10 +116,10 @@ DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D_, const EvalBuf& E_, const Lsqr
     while (itn < iter_lim) {
       ++itn;
       // u = A v - alfa u
-      lsqr_A(c, D, E, L, L.v, L.tm);
+      lsqr_A<SM>(c, D, E, L, L.v, L.tm);
       DG_FOR(i, m) L.u[i] = L.tm[i] - alfa * L.u[i];
-      lsqr_reorth(c, m, L.Ub, nU, L.u, L.cf);
-      beta = vec_norm(c, m, L.u);
+      lsqr_reorth<SM>(c, m, L.Ub, nU, L.u, L.cf);
+      beta = vec_norm<SM>(c, m, L.u);
       if (beta > 0.0) {
         c.sync();
         const bool keepU = nU < DG_LSQR_BASIS;
@@ -123,10 +127,10 @@ DG_DEVN int lsqr_dual_init(Cta& c, const Dims& D_, const EvalBuf& E_, const Lsqr
         if (keepU) ++nU;
         c.sync();
         anorm = sqrt(anorm * anorm + alfa * alfa + beta * beta);
-        lsqr_A(c, D, E, L, L.u, L.tm);
+        lsqr_A<SM>(c, D, E, L, L.u, L.tm);
         DG_FOR(i, m) L.v[i] = L.tm[i] - beta * L.v[i];
-        lsqr_reorth(c, m, L.Vb, nV, L.v, L.cf);
-        alfa = vec_norm(c, m, L.v);
+        lsqr_reorth<SM>(c, m, L.Vb, nV, L.v, L.cf);
+        alfa = vec_norm<SM>(c, m, L.v);
         c.sync();
         if (alfa > 0.0) {
           const bool keepV = nV < DG_LSQR_BASIS;

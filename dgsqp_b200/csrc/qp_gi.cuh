@@ -35,9 +35,14 @@ struct QpBuf {
   int* is_act;    // m   flags
 };
 
+#define DG_SH_QP(Q) do { DG_ASSUME_SHARED((Q).xq); DG_ASSUME_SHARED((Q).dv); DG_ASSUME_SHARED((Q).zv); DG_ASSUME_SHARED((Q).rv); \
+  DG_ASSUME_SHARED((Q).npv); DG_ASSUME_SHARED((Q).lam_act); DG_ASSUME_SHARED((Q).sl); DG_ASSUME_SHARED((Q).act); DG_ASSUME_SHARED((Q).is_act); } while (0)
+
 // out[i] = scale * sum_{j in [j0, n)} Y[j][i] * d[j],  i < n.  All threads; ends with a barrier.
+template <bool SM>
 DG_DEV void gi_cols_times(Cta& c, int n, int ld, const double* DG_RESTRICT Y, const double* DG_RESTRICT d, int j0,
                           double* DG_RESTRICT part, double* DG_RESTRICT out, double scale) {
+  DG_ASSUME_SHARED(Y); DG_ASSUME_SHARED(d); DG_ASSUME_SHARED(part); DG_ASSUME_SHARED(out);
   const Split2 sp = split2(c, n);
   for (int i = sp.i0; i < n; i += sp.istep) {
     double a0 = 0.0, a1 = 0.0;
@@ -62,16 +67,18 @@ DG_DEV void gi_cols_times(Cta& c, int n, int ld, const double* DG_RESTRICT Y, co
 
 // H (symmetric positive definite) is expected in B.matA and is destroyed.
 // returns 0 ok, 1 not PD, 2 infeasible, 3 iteration limit.  Output: Q.xq (du), Q.lam (l_hat).
+template <bool SM>
 DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double* DG_RESTRICT qv,
                         const QpBuf& Q_, const LinBuf& B_, int* n_iter_out, int* n_active_out) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; const QpBuf Q = Q_; const LinBuf B = B_; const Dims D = D_;
+  const EvalBuf E = E_; DG_SH_EVAL(E); const QpBuf Q = Q_; DG_SH_QP(Q); const LinBuf B = B_; DG_SH_LIN(B); const Dims D = D_;
   const int n = D.n, m = D.m, ld = B.ld;
   double* DG_RESTRICT Y = B.matB;
   double* DG_RESTRICT Rm = B.matA;
-  if (!cholesky_lower(c, n, ld, B.matA, B.sp, B.part)) return 1;
+  DG_ASSUME_SHARED(Y); DG_ASSUME_SHARED(Rm); DG_ASSUME_SHARED(qv);
+  if (!cholesky_lower<SM>(c, n, ld, B.matA, B.sp, B.part)) return 1;
   c.lap(PH_CHOL);
-  tri_inverse(c, n, ld, B.matA, Y);
+  tri_inverse<SM>(c, n, ld, B.matA, Y);
   // x = -J J' q = -Y' (Y q):   t = Y q (warp per row), x_i = -sum_j Y[j][i] t_j
   for (int j = c.warp(); j < n; j += c.nwarps()) {
     const double* DG_RESTRICT Yj = Y + j * ld;
@@ -82,14 +89,14 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
   }
   DG_FOR(r, m) { Q.is_act[r] = 0; Q.lam[r] = 0.0; }
   c.sync();
-  gi_cols_times(c, n, ld, Y, Q.dv, 0, B.part, Q.xq, -1.0);
+  gi_cols_times<SM>(c, n, ld, Y, Q.dv, 0, B.part, Q.xq, -1.0);
   c.lap(PH_TRINV);
   int iq = 0, it = 0;
   const int max_iter = 10 * (n + m);
   int status = 0;
   while (true) {
     // slacks of all constraints, most violated one
-    game_G_times(c, D, E, Q.xq, Q.sl);
+    game_G_times<SM>(c, D, E, Q.xq, Q.sl);
     double best; int bi;
     {
       double bv = 1e300; int bidx = 0x7fffffff;
@@ -101,7 +108,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
     }
     if (!(best < -DG_QP_FEAS_TOL)) break;
     const int p = bi;
-    game_G_row(c, D, E, p, Q.npv);                 // npv = G[p,:]  (normal is -npv)
+    game_G_row<SM>(c, D, E, p, Q.npv);                 // npv = G[p,:]  (normal is -npv)
     double lam_p = 0.0;
     bool added = false;
     while (!added) {

@@ -138,10 +138,18 @@ struct EvalBuf {
   double* cf;    // M*N*3   per (a,k) coefficients for G' w
 };
 
+
+// shared-memory residency hints for the buffer tables (SM instantiation only)
+#define DG_SH_EVAL(E) do { DG_ASSUME_SHARED((E).x); DG_ASSUME_SHARED((E).g); DG_ASSUME_SHARED((E).q); DG_ASSUME_SHARED((E).gtl); \
+  DG_ASSUME_SHARED((E).tmpS); DG_ASSUME_SHARED((E).cf); DG_ASSUME_SHARED((E).AB); DG_ASSUME_SHARED((E).cst); DG_ASSUME_SHARED((E).Hc); \
+  DG_ASSUME_SHARED((E).Vbuf); DG_ASSUME_SHARED((E).Wrow); DG_ASSUME_SHARED((E).T2); DG_ASSUME_SHARED((E).S); } while (0)
+
 // x_{k+1} = x_k + dt f(x_k,u_k): agents are dynamically decoupled, thread a rolls out agent a.
+template <bool SM>
 DG_DEVN void game_rollout(Cta& c, const GameDesc& G, const Dims& D_, const double* u, const double* x0, double* x) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
   const Dims D = D_;
+  DG_ASSUME_SHARED(x);
   DG_FOR(a, D.M) {
     double qk[DG_NQA];
     for (int i = 0; i < DG_NQA; ++i) { qk[i] = x0[a * DG_NQA + i]; x[a * DG_NQA + i] = qk[i]; }
@@ -154,9 +162,10 @@ DG_DEVN void game_rollout(Cta& c, const GameDesc& G, const Dims& D_, const doubl
   }
 }
 
+template <bool SM>
 DG_DEVN void game_linearize(Cta& c, const GameDesc& G, const Dims& D_, const double* u, const EvalBuf& E_, bool second) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; const Dims D = D_;
+  const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
   DG_FOR(t, D.N * D.M) {
     int k = t / D.M, a = t - k * D.M;
     const double* qk = E.x + k * D.nq + a * DG_NQA;
@@ -169,10 +178,12 @@ DG_DEVN void game_linearize(Cta& c, const GameDesc& G, const Dims& D_, const dou
 }
 
 // f_Cxu: one thread per row
+template <bool SM>
 DG_DEVN void game_constraints(Cta& c, const GameDesc& G, const Dims& D_, const double* u, const double* up,
                               const double* x, double* g) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
   const Dims D = D_;
+  DG_ASSUME_SHARED(x); DG_ASSUME_SHARED(g); DG_ASSUME_SHARED(up);
   DG_FOR(r, D.m) {
     int k, kind, a, b;
     decode_row(D, r, k, kind, a, b);
@@ -200,9 +211,10 @@ DG_DEVN void game_constraints(Cta& c, const GameDesc& G, const Dims& D_, const d
 DG_DEV int sens_off(const Dims& D, int a, int k, int r) { return a * D.sens_sz + 3 * k * (k - 1) + r * 2 * k; }
 
 // Sensitivity rows (f_Du_x restricted to x, y, e_y): thread per input column (a, j).
+template <bool SM>
 DG_DEVN void game_sens(Cta& c, const Dims& D_, const EvalBuf& E_) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; const Dims D = D_;
+  const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
   const int twoN = D.twoN;
   DG_FOR(t, D.M * twoN) {
     int a = t / twoN, j = t - a * twoN, kj = j >> 1, cc = j & 1;
@@ -226,6 +238,7 @@ DG_DEVN void game_sens(Cta& c, const Dims& D_, const EvalBuf& E_) {
   }
 }
 
+template <bool SM>
 DG_DEV double sens_dot(const Dims& D, const EvalBuf& E, int a, int k, int row, const double* va) {
   const double* DG_RESTRICT Sk = E.S + sens_off(D, a, k, row);
   double a0 = 0.0, a1 = 0.0;
@@ -234,13 +247,14 @@ DG_DEV double sens_dot(const Dims& D, const EvalBuf& E, int a, int k, int row, c
 }
 
 // y = G v   (v in R^n agent-major, y in R^m).  Two phases with one sync.
+template <bool SM>
 DG_DEVN void game_G_times(Cta& c, const Dims& D_, const EvalBuf& E_, const double* v, double* y) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; const Dims D = D_;
+  const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
   c.sync();
   DG_FOR(t, D.M * D.N * 3) {
     int a = t / (D.N * 3), rem = t - a * D.N * 3, k1 = rem / 3, row = rem - k1 * 3;
-    E.tmpS[t] = sens_dot(D, E, a, k1 + 1, row, v + a * D.twoN);
+    E.tmpS[t] = sens_dot<SM>(D, E, a, k1 + 1, row, v + a * D.twoN);
   }
   c.sync();
   DG_FOR(r, D.m) {
@@ -267,6 +281,7 @@ DG_DEVN void game_G_times(Cta& c, const Dims& D_, const EvalBuf& E_, const doubl
 }
 
 // per (a,k>=1) coefficients of the state rows in  G' w:  cf = [c_x, c_y, c_ey]
+template <bool SM>
 DG_DEV void game_state_coefs(Cta& c, const Dims& D, const EvalBuf& E, const double* w, double* cf) {
   DG_FOR(t, D.M * D.N) {
     int a = t / D.N, k = t - a * D.N + 1;
@@ -294,11 +309,12 @@ DG_DEV double game_GT_direct(const Dims& D, const double* w, int a, int k, int c
 }
 
 // y = G' w  (w in R^m, y in R^n)
+template <bool SM>
 DG_DEVN void game_GT_times(Cta& c, const Dims& D_, const EvalBuf& E_, const double* w, double* y) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; const Dims D = D_;
+  const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
   c.sync();
-  game_state_coefs(c, D, E, w, E.cf);
+  game_state_coefs<SM>(c, D, E, w, E.cf);
   c.sync();
   DG_FOR(t, D.n) {
     int a = t / D.twoN, j = t - a * D.twoN, kj = j >> 1, cc = j & 1;
@@ -314,9 +330,10 @@ DG_DEVN void game_GT_times(Cta& c, const Dims& D_, const EvalBuf& E_, const doub
 }
 
 // dense row r of G into out[n] (all threads cooperate)
+template <bool SM>
 DG_DEVN void game_G_row(Cta& c, const Dims& D_, const EvalBuf& E_, int r, double* out) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; const Dims D = D_;
+  const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
   int k, kind, a, b;
   decode_row(D, r, k, kind, a, b);
   DG_FOR(t, D.n) {
@@ -413,9 +430,10 @@ DG_DEV double con_lxx(const Dims& D, const double* l, int k, int i1, int i2) {
 
 // Costate chains  p_k = l_x,k + A_k' p_{k+1}:  thread per (function f, agent block b).
 // f < M: cost of agent f (state cost only at the terminal stage); f == M: l'C.
+template <bool SM>
 DG_DEVN void game_costates(Cta& c, const GameDesc& G, const Dims& D_, const EvalBuf& E_, const double* l) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; const Dims D = D_;
+  const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
   DG_FOR(t, (D.M + 1) * D.M) {
     int f = t / D.M, b = t - f * D.M;
     double p[DG_NQA];
@@ -439,10 +457,11 @@ DG_DEVN void game_costates(Cta& c, const GameDesc& G, const Dims& D_, const Eval
 }
 
 // q (cost gradient, f_q) and G'l from the costates: thread per input (a,k,cc)
+template <bool SM>
 DG_DEVN void game_gradients(Cta& c, const GameDesc& G, const Dims& D_, const EvalBuf& E_, const double* u,
                             const double* up, const double* l) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; const Dims D = D_;
+  const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
   DG_FOR(t, D.n) {
     int a = t / D.twoN, j = t - a * D.twoN, k = j >> 1, cc = j & 1;
     const double* Bk = E.AB + (k * D.M + a) * 48;
@@ -460,9 +479,10 @@ DG_DEVN void game_gradients(Cta& c, const GameDesc& G, const Dims& D_, const Eva
 }
 
 // Hc[f][k][a][0..14] = sum_i p^f_{k+1}[a,i] * T2[k][a][i][:]
+template <bool SM>
 DG_DEVN void game_contract(Cta& c, const Dims& D_, const EvalBuf& E_) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; const Dims D = D_;
+  const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
   DG_FOR(t, (D.M + 1) * D.N * D.M * 15) {
     int e = t % 15, r = t / 15;
     int a = r % D.M; r /= D.M;
@@ -492,9 +512,10 @@ DG_DEV double hc_uu(const double* hc, int c1, int c2) { return (c1 == 1 && c2 ==
 // E.Wrow[(f*nq + q)*n + r] (coalesced).  At stage k < k_r it emits H^f[r, (k,b,cc)] = w^f[b] . B^b_k[:,cc] and
 // stores  Q[r][(k,b,cc)] = H^{a_r} + H^M  and, by symmetry of each H^f,  Q[(k,b,cc)][r] = H^b + H^M.
 // Every entry of Q is written exactly once, so Q needs no zero-fill and no read-modify-write.
+template <bool SM>
 DG_DEVN void game_hessian(Cta& c, const GameDesc& G, const Dims& D_, const EvalBuf& E_, const double* DG_RESTRICT l) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; const Dims D = D_;
+  const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
   const int n = D.n, nq = D.nq, N = D.N, M = D.M, F = D.M + 1;
   const double* xN = E.x + N * nq;
   double* Vcur = E.Vbuf;

@@ -31,7 +31,7 @@ struct SqpBuf {
 
 struct Workspace { EvalBuf E; LinBuf B; QpBuf Q; LsqrBuf L; SqpBuf S; };
 
-struct MemPlan { size_t smem, gmem; int mats_in_smem, sens_in_smem; };   // doubles used in each space
+struct MemPlan { size_t smem, gmem; int mats_in_smem, sens_in_smem, hot_in_smem; };   // doubles used in each space
 
 // Memory plan of one CTA (= one game instance in flight).  Everything a latency-bound phase walks through
 // lives in shared memory when it fits (budget `sbudget` doubles), the rest in the CTA's slice of global
@@ -69,6 +69,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   PLACE(W.Q.sl, m);
   PLACE(W.B.part, (n > DG_MAX_THREADS ? n : DG_MAX_THREADS));
   { double* t; PLACE(t, (n + 1) / 2 + 1); W.Q.act = (int*)t; PLACE(t, (m + 1) / 2 + 1); W.Q.is_act = (int*)t; }
+  const bool pool_ok = go == 0;                 // nothing of the pool fell back to global memory
   // ---- ARENA
   const size_t ev_a = rnd(N * M * 48) + rnd((M + 1) * (N + 1) * nq) + rnd((M + 1) * N * M * 15) + rnd(2 * (M + 1) * nq * nq) +
                       rnd((M + 1) * nq * n) + rnd(N * M * 90);
@@ -99,6 +100,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
 #undef STAKE
 #undef PLACE
   P.smem = so; P.gmem = go;
+  P.hot_in_smem = pool_ok && P.mats_in_smem && P.sens_in_smem;
   return P;
 }
 
@@ -113,52 +115,55 @@ struct SolveCtx {
 };
 
 // _evaluate(u, l, hessian=True)
+template <bool SM>
 DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l) {
-  const Dims D = X.D; const EvalBuf E = X.W.E;
+  const Dims D = X.D; const EvalBuf E = X.W.E; DG_SH_EVAL(E);
   c.sync();
   c.lap(PH_OTHER);
-  game_rollout(c, *X.G, D, u, X.x0, E.x);
+  game_rollout<SM>(c, *X.G, D, u, X.x0, E.x);
   c.sync();
-  game_linearize(c, *X.G, D, u, E, true);
+  game_linearize<SM>(c, *X.G, D, u, E, true);
   c.sync();
   c.lap(PH_LIN_FULL);
-  game_constraints(c, *X.G, D, u, X.W.S.up, E.x, E.g);
-  game_costates(c, *X.G, D, E, l);
-  game_sens(c, D, E);
+  game_constraints<SM>(c, *X.G, D, u, X.W.S.up, E.x, E.g);
+  game_costates<SM>(c, *X.G, D, E, l);
+  game_sens<SM>(c, D, E);
   c.sync();
-  game_contract(c, D, E);
-  game_gradients(c, *X.G, D, E, u, X.W.S.up, l);
+  game_contract<SM>(c, D, E);
+  game_gradients<SM>(c, *X.G, D, E, u, X.W.S.up, l);
   c.sync();
   c.lap(PH_ADJ_FULL);
-  game_hessian(c, *X.G, D, E, l);
+  game_hessian<SM>(c, *X.G, D, E, l);
   c.lap(PH_HESS);
   if (c.tid() == 0) ++X.n_evals_full;
 }
 
 // _evaluate(u, l, hessian=False): x, g, q, G'l only (sensitivities optional)
+template <bool SM>
 DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l, bool with_sens) {
-  const Dims D = X.D; const EvalBuf E = X.W.E;
+  const Dims D = X.D; const EvalBuf E = X.W.E; DG_SH_EVAL(E);
   c.sync();
   c.lap(PH_OTHER);
-  game_rollout(c, *X.G, D, u, X.x0, E.x);
+  game_rollout<SM>(c, *X.G, D, u, X.x0, E.x);
   c.sync();
-  game_linearize(c, *X.G, D, u, E, false);
+  game_linearize<SM>(c, *X.G, D, u, E, false);
   c.sync();
   c.lap(PH_LIN_GRAD);
-  game_constraints(c, *X.G, D, u, X.W.S.up, E.x, E.g);
-  game_costates(c, *X.G, D, E, l);
-  if (with_sens) game_sens(c, D, E);
+  game_constraints<SM>(c, *X.G, D, u, X.W.S.up, E.x, E.g);
+  game_costates<SM>(c, *X.G, D, E, l);
+  if (with_sens) game_sens<SM>(c, D, E);
   c.sync();
-  game_gradients(c, *X.G, D, E, u, X.W.S.up, l);
+  game_gradients<SM>(c, *X.G, D, E, u, X.W.S.up, l);
   c.sync();
   c.lap(PH_ADJ_GRAD);
   if (c.tid() == 0) ++X.n_evals_grad;
 }
 
 // phi at the currently evaluated point:  1/2 |q+G'l|^2 + 1/2 (l.g)^2 + mu * sum(g - (s + alpha*ds))
+template <bool SM>
 DG_DEV double merit_here(Cta& c, SolveCtx& X, const double* l, const double* s, const double* ds, double alpha,
                          double mu) {
-  const Dims D = X.D; const EvalBuf E = X.W.E;
+  const Dims D = X.D; const EvalBuf E = X.W.E; DG_SH_EVAL(E);
   double p1 = 0.0, p2 = 0.0, p3 = 0.0;
   DG_FOR(i, D.n) { double d = E.q[i] + E.gtl[i]; p1 += d * d; }
   DG_FOR(r, D.m) { p2 += l[r] * E.g[r]; p3 += E.g[r] - (s[r] + (ds ? alpha * ds[r] : 0.0)); }
@@ -172,12 +177,13 @@ DG_DEV double merit_here(Cta& c, SolveCtx& X, const double* l, const double* s, 
 
 // After a QP at the currently (fully) evaluated point (u_b, l_b): fills dl, s, ds, Gdu and returns
 // phi, dphi (and mu when compute_mu) -- f_phi / f_dphi / _get_mu.
+template <bool SM>
 DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du, const double* l_hat,
                         double* dl, double* s, double* ds, bool compute_mu, double& mu, double& phi, double& dphi) {
-  const Dims D = X.D; const EvalBuf E = X.W.E; const SqpBuf S = X.W.S;
+  const Dims D = X.D; const EvalBuf E = X.W.E; DG_SH_EVAL(E); const SqpBuf S = X.W.S;
   const int n = D.n, m = D.m;
   c.lap(PH_OTHER);
-  game_G_times(c, D, E, du, S.Gdu);
+  game_G_times<SM>(c, D, E, du, S.Gdu);
   DG_FOR(r, m) {
     dl[r] = l_hat[r] - l_b[r];
     double sv = E.g[r] < 0.0 ? E.g[r] : 0.0;
@@ -185,7 +191,7 @@ DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du
     ds[r] = E.g[r] + S.Gdu[r] - sv;
   }
   c.sync();
-  game_GT_times(c, D, E, dl, S.tn2);
+  game_GT_times<SM>(c, D, E, dl, S.tn2);
   // tn = Q du (raw, unsymmetrised Q -- DGSQP.py:416 passes Q_i)
   // (Q streams from global memory: warp per row, lanes along the row)
   for (int i = c.warp(); i < n; i += c.nwarps()) {
@@ -216,20 +222,22 @@ DG_DEVN void step_merit(Cta& c, SolveCtx& X, const double* l_b, const double* du
 }
 
 // _solve_qp at the currently evaluated point.  Result in W.Q.xq / W.Q.lam.  Returns 0 on success.
+template <bool SM>
 DG_DEVN int solve_qp_here(Cta& c, SolveCtx& X) {
   const Dims D = X.D;
-  int nneg = nearest_pd(c, D.n, X.W.E.Q, X.W.B, X.P->eig_floor, X.P->reg, X.P->conv_approx != 0);
+  int nneg = nearest_pd<SM>(c, D.n, X.W.E.Q, X.W.B, X.P->eig_floor, X.P->reg, X.P->conv_approx != 0);
   if (c.tid() == 0) {
     if (nneg > X.n_neg_max) X.n_neg_max = nneg;
     if (nneg > 0) { ++X.n_qp_indef; X.n_neg_sum += nneg; }
   }
   int it = 0, na = 0;
-  int st = qp_solve_gi(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na);
+  int st = qp_solve_gi<SM>(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na);
   if (c.tid() == 0) { X.n_gi_iters += it; X.n_act_sum += na; }
   return st;
 }
 
 // _line_search_3: base (u,du,l,dl,s,ds) with phi0/dphi0; result left in (u_c, l_c); returns phi_trial
+template <bool SM>
 DG_DEVN double line_search_3(Cta& c, SolveCtx& X, const double* u, const double* du, const double* l, const double* dl,
                              const double* s, const double* ds, double phi0, double dphi0, double mu) {
   const Dims D = X.D; const SqpBuf S = X.W.S;
@@ -238,18 +246,20 @@ DG_DEVN double line_search_3(Cta& c, SolveCtx& X, const double* u, const double*
     c.sync();
     DG_FOR(j, D.n) S.u_c[j] = u[j] + alpha * du[j];
     DG_FOR(r, D.m) S.l_c[r] = l[r] + alpha * dl[r];
-    eval_grad(c, X, S.u_c, S.l_c, false);
+    eval_grad<SM>(c, X, S.u_c, S.l_c, false);
     if (c.tid() == 0) ++X.n_ls_trials;
-    phi_t = merit_here(c, X, S.l_c, s, ds, alpha, mu);
+    phi_t = merit_here<SM>(c, X, S.l_c, s, ds, alpha, mu);
     if (phi_t <= phi0 + X.P->beta * alpha * dphi0) break;
     alpha *= X.P->tau;
   }
   return phi_t;
 }
 
+template <bool SM>
 DG_DEV void vcopy(Cta& c, int len, double* dst, const double* src) { DG_FOR(i, len) dst[i] = src[i]; }
 
 // _watchdog_line_search_4.  On return the accepted iterate is in (S.u, S.l); returns extra QP count.
+template <bool SM>
 DG_DEVN int watchdog_4(Cta& c, SolveCtx& X, double phi_k, double dphi_k, double mu) {
   const Dims D = X.D; const SqpBuf S = X.W.S; const SolverParams P = *X.P;
   const int n = D.n, m = D.m;
@@ -259,75 +269,75 @@ DG_DEVN int watchdog_4(Cta& c, SolveCtx& X, double phi_k, double dphi_k, double 
   c.sync();
   DG_FOR(j, n) S.u_c[j] = S.u[j] + S.du[j];
   DG_FOR(r, m) S.l_c[r] = S.l[r] + S.dl[r];
-  eval_grad(c, X, S.u_c, S.l_c, false);
-  double phi1 = merit_here(c, X, S.l_c, S.s, S.ds, 1.0, mu);
+  eval_grad<SM>(c, X, S.u_c, S.l_c, false);
+  double phi1 = merit_here<SM>(c, X, S.l_c, S.s, S.ds, 1.0, mu);
 #ifdef DG_TRACE
   if (c.tid() == 0) printf("      full step phi1 %.12e  (accept %d)\n", phi1, (int)(phi1 <= target));
 #endif
-  if (phi1 <= target) { c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync(); return qp; }
+  if (phi1 <= target) { c.sync(); vcopy<SM>(c, n, S.u, S.u_c); vcopy<SM>(c, m, S.l, S.l_c); c.sync(); return qp; }
   bool fail = false;
   c.sync();
-  vcopy(c, n, S.u_t, S.u_c); vcopy(c, m, S.l_t, S.l_c);
+  vcopy<SM>(c, n, S.u_t, S.u_c); vcopy<SM>(c, m, S.l_t, S.l_c);
   for (int t = 0; t < P.t_hat; ++t) {
-    eval_full(c, X, S.u_t, S.l_t);
-    int st = solve_qp_here(c, X);
+    eval_full<SM>(c, X, S.u_t, S.l_t);
+    int st = solve_qp_here<SM>(c, X);
     ++qp;
     if (st != 0) { fail = true; break; }
     c.sync();
-    vcopy(c, n, S.du_t, X.W.Q.xq);
+    vcopy<SM>(c, n, S.du_t, X.W.Q.xq);
     double mu_d = mu, ph, dph;
-    step_merit(c, X, S.l_t, S.du_t, X.W.Q.lam, S.dl_t, S.s_t, S.ds_t, false, mu_d, ph, dph);
+    step_merit<SM>(c, X, S.l_t, S.du_t, X.W.Q.lam, S.dl_t, S.s_t, S.ds_t, false, mu_d, ph, dph);
     c.sync();
     DG_FOR(j, n) S.u_c[j] = S.u_t[j] + S.du_t[j];
     DG_FOR(r, m) S.l_c[r] = X.W.Q.lam[r];
-    eval_grad(c, X, S.u_c, S.l_c, false);
-    double phi_n = merit_here(c, X, S.l_c, S.s_t, S.ds_t, 1.0, mu);
+    eval_grad<SM>(c, X, S.u_c, S.l_c, false);
+    double phi_n = merit_here<SM>(c, X, S.l_c, S.s_t, S.ds_t, 1.0, mu);
     if (phi_n > P.merit_max) break;
-    if (phi_n <= target) { c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync(); return qp; }
+    if (phi_n <= target) { c.sync(); vcopy<SM>(c, n, S.u, S.u_c); vcopy<SM>(c, m, S.l, S.l_c); c.sync(); return qp; }
     c.sync();
-    vcopy(c, n, S.u_t, S.u_c); vcopy(c, m, S.l_t, S.l_c);
+    vcopy<SM>(c, n, S.u_t, S.u_c); vcopy<SM>(c, m, S.l_t, S.l_c);
   }
   // insist on merit decrease
   double phi_n = 0.0;
   {
-    eval_full(c, X, S.u_t, S.l_t);
-    int st = solve_qp_here(c, X);
+    eval_full<SM>(c, X, S.u_t, S.l_t);
+    int st = solve_qp_here<SM>(c, X);
     ++qp;
     if (st != 0) fail = true;
     else {
       c.sync();
-      vcopy(c, n, S.du_t, X.W.Q.xq);
+      vcopy<SM>(c, n, S.du_t, X.W.Q.xq);
       double mu_d = mu, ph, dph;
-      step_merit(c, X, S.l_t, S.du_t, X.W.Q.lam, S.dl_t, S.s_t, S.ds_t, false, mu_d, ph, dph);
-      phi_n = line_search_3(c, X, S.u_t, S.du_t, S.l_t, S.dl_t, S.s_t, S.ds_t, ph, dph, mu);
+      step_merit<SM>(c, X, S.l_t, S.du_t, X.W.Q.lam, S.dl_t, S.s_t, S.ds_t, false, mu_d, ph, dph);
+      phi_n = line_search_3<SM>(c, X, S.u_t, S.du_t, S.l_t, S.dl_t, S.s_t, S.ds_t, ph, dph, mu);
     }
   }
   if (!fail) {
-    if (phi_n <= target) { c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync(); return qp; }
+    if (phi_n <= target) { c.sync(); vcopy<SM>(c, n, S.u, S.u_c); vcopy<SM>(c, m, S.l, S.l_c); c.sync(); return qp; }
     else if (phi_n > phi_k) fail = true;
     else {
       c.sync();
-      vcopy(c, n, S.u_t, S.u_c); vcopy(c, m, S.l_t, S.l_c);
-      eval_full(c, X, S.u_t, S.l_t);
-      int st = solve_qp_here(c, X);
+      vcopy<SM>(c, n, S.u_t, S.u_c); vcopy<SM>(c, m, S.l_t, S.l_c);
+      eval_full<SM>(c, X, S.u_t, S.l_t);
+      int st = solve_qp_here<SM>(c, X);
       if (st != 0) {
-        line_search_3(c, X, S.u, S.du, S.l, S.dl, S.s, S.ds, phi_k, dphi_k, mu);
-        c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync();
+        line_search_3<SM>(c, X, S.u, S.du, S.l, S.dl, S.s, S.ds, phi_k, dphi_k, mu);
+        c.sync(); vcopy<SM>(c, n, S.u, S.u_c); vcopy<SM>(c, m, S.l, S.l_c); c.sync();
         return qp;
       }
       ++qp;
       c.sync();
-      vcopy(c, n, S.du_t, X.W.Q.xq);
+      vcopy<SM>(c, n, S.du_t, X.W.Q.xq);
       double mu_d = mu, ph, dph;
-      step_merit(c, X, S.l_t, S.du_t, X.W.Q.lam, S.dl_t, S.s_t, S.ds_t, false, mu_d, ph, dph);
-      line_search_3(c, X, S.u_t, S.du_t, S.l_t, S.dl_t, S.s_t, S.ds_t, ph, dph, mu);
-      c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync();
+      step_merit<SM>(c, X, S.l_t, S.du_t, X.W.Q.lam, S.dl_t, S.s_t, S.ds_t, false, mu_d, ph, dph);
+      line_search_3<SM>(c, X, S.u_t, S.du_t, S.l_t, S.dl_t, S.s_t, S.ds_t, ph, dph, mu);
+      c.sync(); vcopy<SM>(c, n, S.u, S.u_c); vcopy<SM>(c, m, S.l, S.l_c); c.sync();
       return qp;
     }
   }
   // fail: search along the original step
-  line_search_3(c, X, S.u, S.du, S.l, S.dl, S.s, S.ds, phi_k, dphi_k, mu);
-  c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync();
+  line_search_3<SM>(c, X, S.u, S.du, S.l, S.dl, S.s, S.ds, phi_k, dphi_k, mu);
+  c.sync(); vcopy<SM>(c, n, S.u, S.u_c); vcopy<SM>(c, m, S.l, S.l_c); c.sync();
   return qp;
 }
 
@@ -343,8 +353,9 @@ struct SolveOut {
 };
 
 // l_ws: optional dual warm start (nullptr = the reference's LSQR initialisation, DGSQP.py:312-326)
+template <bool SM>
 DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double* l_ws, const SolveOut& O) {
-  const Dims D = X.D; const SqpBuf S = X.W.S; const EvalBuf E = X.W.E; const SolverParams P = *X.P;
+  const Dims D = X.D; const SqpBuf S = X.W.S; const EvalBuf E = X.W.E; DG_SH_EVAL(E); const SolverParams P = *X.P;
   const int n = D.n, m = D.m;
   if (c.tid() == 0) X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0;
   DG_FOR(j, n) S.u[j] = u_ws[j];
@@ -356,8 +367,8 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
     DG_FOR(r, m) S.l[r] = l_ws[r];
     c.sync();
   } else {
-    eval_grad(c, X, S.u, S.l, true);
-    lsqr_dual_init(c, D, E, X.W.L, E.q, S.l);
+    eval_grad<SM>(c, X, S.u, S.l, true);
+    lsqr_dual_init<SM>(c, D, E, X.W.L, E.q, S.l);
     c.lap(PH_LSQR);
   }
   if (P.dbg_l0_perturb != 0.0) {
@@ -368,7 +379,7 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
   int sqp_it = 0, rel_its = 0, total_qp = 0, status = ST_MAX_IT;
   double p_feas = 0.0, comp = 0.0, stat = 0.0;
   while (true) {
-    eval_full(c, X, S.u, S.l);
+    eval_full<SM>(c, X, S.u, S.l);
     double a1 = -1e300, a2 = 0.0, a3 = 0.0;
     // NaN must not look like convergence (fmax drops NaNs): map it to +inf -> 'diverged'
     DG_FOR(r, m) {
@@ -379,23 +390,23 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
     c.max3(a1, a2, a3);
     p_feas = fmax(0.0, a1); comp = a2; stat = a3;
     c.sync();
-    vcopy(c, n, S.u_im1, S.u); vcopy(c, m, S.l_im1, S.l);
+    vcopy<SM>(c, n, S.u_im1, S.u); vcopy<SM>(c, m, S.l_im1, S.l);
     if (stat > P.diverge_tol) { status = ST_DIVERGED; break; }
     if (p_feas < P.p_tol && comp < P.d_tol && stat < P.d_tol) { status = ST_CONV_ABS; break; }
-    int st = solve_qp_here(c, X);
+    int st = solve_qp_here<SM>(c, X);
     ++total_qp;
     if (st != 0) { status = ST_QP_FAIL; break; }
     c.sync();
-    vcopy(c, n, S.du, X.W.Q.xq);
+    vcopy<SM>(c, n, S.du, X.W.Q.xq);
     double mu = 0.0, phi_k, dphi_k;
-    step_merit(c, X, S.l, S.du, X.W.Q.lam, S.dl, S.s, S.ds, true, mu, phi_k, dphi_k);
+    step_merit<SM>(c, X, S.l, S.du, X.W.Q.lam, S.dl, S.s, S.ds, true, mu, phi_k, dphi_k);
 #ifdef DG_TRACE
     if (c.tid() == 0) printf("it %2d pf %.6e comp %.6e stat %.6e | mu %.12e phi_k %.12e dphi_k %.12e target %.12e\n", sqp_it, p_feas, comp, stat, mu, phi_k, dphi_k, phi_k + P.beta * dphi_k);
 #endif
-    if (P.nonmono_ls) total_qp += watchdog_4(c, X, phi_k, dphi_k, mu);
+    if (P.nonmono_ls) total_qp += watchdog_4<SM>(c, X, phi_k, dphi_k, mu);
     else {
-      line_search_3(c, X, S.u, S.du, S.l, S.dl, S.s, S.ds, phi_k, dphi_k, mu);
-      c.sync(); vcopy(c, n, S.u, S.u_c); vcopy(c, m, S.l, S.l_c); c.sync();
+      line_search_3<SM>(c, X, S.u, S.du, S.l, S.dl, S.s, S.ds, phi_k, dphi_k, mu);
+      c.sync(); vcopy<SM>(c, n, S.u, S.u_c); vcopy<SM>(c, m, S.l, S.l_c); c.sync();
     }
     double q1 = 0.0, q2 = 0.0;
     DG_FOR(j, n) { double d = S.u[j] - S.u_im1[j]; q1 += d * d; }
@@ -411,7 +422,7 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
   }
   // outputs: x_bar = evaluate_dynamics(u), costs f_J  (DGSQP.py:476-498)
   c.sync();
-  game_rollout(c, *X.G, D, S.u, X.x0, E.x);
+  game_rollout<SM>(c, *X.G, D, S.u, X.x0, E.x);
   c.sync();
   DG_FOR(j, n) O.u[j] = S.u[j];
   DG_FOR(r, m) O.l[r] = S.l[r];

@@ -12,6 +12,7 @@ struct UnitArgs {
   double* ws; size_t ws_stride; size_t smem_doubles;
 };
 
+template <bool SM>
 __global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArgs A) {
   extern __shared__ double s_dyn[];
   Cta c;
@@ -30,23 +31,23 @@ __global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArg
     const double* u = A.u + (size_t)inst * n; const double* l = A.l + (size_t)inst * m;
     DG_FOR(j, D.nu) X.W.S.up[j] = 0.0;
     c.sync();
-    eval_full(c, X, u, l);
+    eval_full<SM>(c, X, u, l);
     c.sync();
     DG_FOR(t, n * n) A.Q[(size_t)inst * n * n + t] = X.W.E.Q[t];
     DG_FOR(t, n) { A.q[(size_t)inst * n + t] = X.W.E.q[t]; A.gtl[(size_t)inst * n + t] = X.W.E.gtl[t]; }
     DG_FOR(t, m) A.g[(size_t)inst * m + t] = X.W.E.g[t];
-    int nneg = nearest_pd(c, n, X.W.E.Q, X.W.B, Pp->eig_floor, Pp->reg, Pp->conv_approx != 0);
+    int nneg = nearest_pd<SM>(c, n, X.W.E.Q, X.W.B, Pp->eig_floor, Pp->reg, Pp->conv_approx != 0);
     DG_FOR(t, n * n) A.H[(size_t)inst * n * n + t] = X.W.B.matA[(t / n) * D.ld + (t % n)];
     c.sync();
     int it = 0, na = 0;
-    int st = qp_solve_gi(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na);
+    int st = qp_solve_gi<SM>(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na);
     DG_FOR(t, n) A.du[(size_t)inst * n + t] = X.W.Q.xq[t];
     DG_FOR(t, m) A.lam[(size_t)inst * m + t] = X.W.Q.lam[t];
     c.sync();
     DG_FOR(t, m) X.W.S.l[t] = 0.0;
     c.sync();
-    eval_grad(c, X, u, X.W.S.l, true);
-    int li = lsqr_dual_init(c, D, X.W.E, X.W.L, X.W.E.q, X.W.S.l);
+    eval_grad<SM>(c, X, u, X.W.S.l, true);
+    int li = lsqr_dual_init<SM>(c, D, X.W.E, X.W.L, X.W.E.q, X.W.S.l);
     DG_FOR(t, m) A.l0[(size_t)inst * m + t] = X.W.S.l[t];
     if (c.tid() == 0) { A.nneg[inst] = nneg; A.qpst[inst] = st; A.qpit[inst] = it; A.lsqr_it[inst] = li; }
     c.sync();
@@ -62,7 +63,7 @@ extern "C" int units_run(const dgsqp_racing_game* game, const dgsqp_params* para
   if (dg_fill_game(game, &G) || dg_fill_params(params, &P)) return -1;
   Dims D = make_dims(G.M, G.N);
   int optin = 0; CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0));
-  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, units_kernel));
+  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, units_kernel<true>));
   size_t budget = ((size_t)optin - fa.sharedSizeBytes - 64) / sizeof(double);
   if (smem_limit_doubles > 0 && (size_t)smem_limit_doubles < budget) budget = (size_t)smem_limit_doubles;
   Workspace tmp; MemPlan pl = plan_memory(D, nullptr, nullptr, budget, tmp);
@@ -84,8 +85,13 @@ extern "C" int units_run(const dgsqp_racing_game* game, const dgsqp_params* para
   CK(cudaMalloc(&A.nneg, 4 * B)); CK(cudaMalloc(&A.qpst, 4 * B)); CK(cudaMalloc(&A.qpit, 4 * B)); CK(cudaMalloc(&A.lsqr_it, 4 * B));
   cudaDeviceSetLimit(cudaLimitStackSize, 8192);
   size_t smem = sizeof(double) * pl.smem;
-  CK(cudaFuncSetAttribute(units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  units_kernel<<<grid, threads, smem>>>(dG, dP, A);
+  if (pl.hot_in_smem) {
+    CK(cudaFuncSetAttribute(units_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    units_kernel<true><<<grid, threads, smem>>>(dG, dP, A);
+  } else {
+    CK(cudaFuncSetAttribute(units_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    units_kernel<false><<<grid, threads, smem>>>(dG, dP, A);
+  }
   CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(Q, A.Q, 8 * B * n * n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(H, A.H, 8 * B * n * n, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(q, A.q, 8 * B * n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(gtl, A.gtl, 8 * B * n, cudaMemcpyDeviceToHost));

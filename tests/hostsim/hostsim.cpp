@@ -36,7 +36,7 @@ void hs_evaluate(void* hp, const double* x0, const double* u, const double* l, d
   HsHandle* h = (HsHandle*)hp; Cta c;
   SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0;
   for (int i = 0; i < h->D.nu; ++i) h->W.S.up[i] = 0.0;
-  eval_full(c, X, u, l);
+  eval_full<false>(c, X, u, l);
   memcpy(Q, h->W.E.Q, sizeof(double) * h->D.n * h->D.n);
   memcpy(q, h->W.E.q, sizeof(double) * h->D.n);
   memcpy(gtl, h->W.E.gtl, sizeof(double) * h->D.n);
@@ -46,14 +46,14 @@ void hs_evaluate(void* hp, const double* x0, const double* u, const double* l, d
 // dense G (m x n) at the last evaluated point, via row extraction; plus G v and G' w products
 void hs_G_dense(void* hp, double* Gd) {
   HsHandle* h = (HsHandle*)hp; Cta c;
-  for (int r = 0; r < h->D.m; ++r) game_G_row(c, h->D, h->W.E, r, Gd + (size_t)r * h->D.n);
+  for (int r = 0; r < h->D.m; ++r) game_G_row<false>(c, h->D, h->W.E, r, Gd + (size_t)r * h->D.n);
 }
-void hs_G_times(void* hp, const double* v, double* y) { HsHandle* h = (HsHandle*)hp; Cta c; game_G_times(c, h->D, h->W.E, v, y); }
-void hs_GT_times(void* hp, const double* w, double* y) { HsHandle* h = (HsHandle*)hp; Cta c; game_GT_times(c, h->D, h->W.E, w, y); }
+void hs_G_times(void* hp, const double* v, double* y) { HsHandle* h = (HsHandle*)hp; Cta c; game_G_times<false>(c, h->D, h->W.E, v, y); }
+void hs_GT_times(void* hp, const double* w, double* y) { HsHandle* h = (HsHandle*)hp; Cta c; game_GT_times<false>(c, h->D, h->W.E, w, y); }
 
 int hs_nearest_pd(void* hp, const double* Qin, double* Hout) {
   HsHandle* h = (HsHandle*)hp; Cta c;
-  int nn = nearest_pd(c, h->D.n, Qin, h->W.B, h->P.eig_floor, h->P.reg, h->P.conv_approx != 0);
+  int nn = nearest_pd<false>(c, h->D.n, Qin, h->W.B, h->P.eig_floor, h->P.reg, h->P.conv_approx != 0);
   for (int i = 0; i < h->D.n; ++i) memcpy(Hout + (size_t)i * h->D.n, h->W.B.matA + (size_t)i * h->D.ld, sizeof(double) * h->D.n);
   return nn;
 }
@@ -63,7 +63,7 @@ int hs_qp(void* hp, double* H, const double* q, double* du, double* lam, int* it
   int na = 0;
   for (int i = 0; i < h->D.n; ++i) memcpy(h->W.B.matA + (size_t)i * h->D.ld, H + (size_t)i * h->D.n, sizeof(double) * h->D.n);
   std::vector<double> qc(q, q + h->D.n);      // q may alias workspace the solver reuses
-  int st = qp_solve_gi(c, h->D, h->W.E, qc.data(), h->W.Q, h->W.B, iters, &na);
+  int st = qp_solve_gi<false>(c, h->D, h->W.E, qc.data(), h->W.Q, h->W.B, iters, &na);
   memcpy(du, h->W.Q.xq, sizeof(double) * h->D.n);
   memcpy(lam, h->W.Q.lam, sizeof(double) * h->D.m);
   return st;
@@ -73,8 +73,8 @@ int hs_lsqr(void* hp, const double* x0, const double* u, double* l_out) {
   SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0;
   for (int i = 0; i < h->D.nu; ++i) h->W.S.up[i] = 0.0;
   std::vector<double> l0(h->D.m, 0.0);
-  eval_grad(c, X, u, l0.data(), true);
-  return lsqr_dual_init(c, h->D, h->W.E, h->W.L, h->W.E.q, l_out);
+  eval_grad<false>(c, X, u, l0.data(), true);
+  return lsqr_dual_init<false>(c, h->D, h->W.E, h->W.L, h->W.E.q, l_out);
 }
 void hs_solve(void* hp, const double* x0, const double* u_ws, const double* l_ws, double* u, double* l, double* x, double* cost, double* cond,
               int* num_iters, int* status, int* qp_solves, int* diag, double* l_init) {
@@ -82,6 +82,6 @@ void hs_solve(void* hp, const double* x0, const double* u_ws, const double* l_ws
   SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0;
   SolveOut O; O.u = u; O.l = l; O.x = x; O.cost = cost; O.cond = cond; O.num_iters = num_iters; O.status = status;
   O.qp_solves = qp_solves; O.diag = diag; O.l_init = l_init;
-  sqp_solve_v1(c, X, u_ws, l_ws, O);
+  sqp_solve_v1<false>(c, X, u_ws, l_ws, O);
 }
 }
