@@ -52,7 +52,11 @@ struct Cta {
 #define DG_HD __host__ __device__ __forceinline__
 #define DG_DEVN __device__ __noinline__
 #define DG_CONST __device__ const
+#ifdef DG_NO_RESTRICT
+#define DG_RESTRICT
+#else
 #define DG_RESTRICT __restrict__
+#endif
 // CTA-wide scratch of the reductions (2 buffers x 160 doubles) and the phase counters: file-scope shared
 // variables, so no pointer has to be fetched from the (local-memory resident) Cta object
 __shared__ double dg_s_red[320];
@@ -188,6 +192,8 @@ struct Cta {
 
 // Address-space hint: in the SM = true instantiation of the solver every hot buffer is known to be shared-memory
 // resident (plan_memory), which lets the compiler emit LDS/STS with 32-bit addressing instead of generic accesses.
+// RULE: state a hint once per pointer and only at the top of a non-inlined (DG_DEVN) function.  nvcc 12.9 silently
+// drops code when the same pointer value is hinted twice inside one function body (e.g. caller + inlined callee).
 #ifdef DG_HOSTSIM
 #define DG_ASSUME_SHARED(p) do { } while (0)
 #else

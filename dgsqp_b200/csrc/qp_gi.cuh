@@ -42,7 +42,7 @@ struct QpBuf {
 template <bool SM>
 DG_DEV void gi_cols_times(Cta& c, int n, int ld, const double* DG_RESTRICT Y, const double* DG_RESTRICT d, int j0,
                           double* DG_RESTRICT part, double* DG_RESTRICT out, double scale) {
-  DG_ASSUME_SHARED(Y); DG_ASSUME_SHARED(d); DG_ASSUME_SHARED(part); DG_ASSUME_SHARED(out);
+  // (inlined: the caller carries the address-space hints)
   const Split2 sp = split2(c, n);
   for (int i = sp.i0; i < n; i += sp.istep) {
     double a0 = 0.0, a1 = 0.0;
@@ -75,7 +75,6 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
   const int n = D.n, m = D.m, ld = B.ld;
   double* DG_RESTRICT Y = B.matB;
   double* DG_RESTRICT Rm = B.matA;
-  DG_ASSUME_SHARED(Y); DG_ASSUME_SHARED(Rm); DG_ASSUME_SHARED(qv);
   if (!cholesky_lower<SM>(c, n, ld, B.matA, B.sp, B.part)) return 1;
   c.lap(PH_CHOL);
   tri_inverse<SM>(c, n, ld, B.matA, Y);

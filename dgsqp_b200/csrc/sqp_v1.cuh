@@ -161,7 +161,7 @@ DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l, bo
 
 // phi at the currently evaluated point:  1/2 |q+G'l|^2 + 1/2 (l.g)^2 + mu * sum(g - (s + alpha*ds))
 template <bool SM>
-DG_DEV double merit_here(Cta& c, SolveCtx& X, const double* l, const double* s, const double* ds, double alpha,
+DG_DEVN double merit_here(Cta& c, SolveCtx& X, const double* l, const double* s, const double* ds, double alpha,
                          double mu) {
   const Dims D = X.D; const EvalBuf E = X.W.E; DG_SH_EVAL(E);
   double p1 = 0.0, p2 = 0.0, p3 = 0.0;

@@ -24,7 +24,8 @@ def build():
 
 def run_stages(game, params, x0, u, l, threads=128, smem_limit_doubles=0):
     """evaluate -> nearestPD -> QP at (u, l), and the LSQR dual initialisation at u, for a batch."""
-    lib = C.CDLL(str(build()))
+    import os
+    lib = C.CDLL(os.environ.get("DG_UNITS_LIB") or str(build()))
     B, n, m = x0.shape[0], game.n, game.m
     x0, u, l = (np.ascontiguousarray(a, dtype=np.float64) for a in (x0, u, l))
     out = dict(Q=np.zeros((B, n, n)), H=np.zeros((B, n, n)), q=np.zeros((B, n)), gtl=np.zeros((B, n)),
