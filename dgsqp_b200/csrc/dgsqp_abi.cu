@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <new>
 
@@ -32,8 +33,9 @@ struct KernelArgs {
   const double* x0; const double* u_ws; const double* l_ws;
   double* u_out; double* l_out; double* x_out; double* cost_out; double* cond_out;
   int* num_iters; int* status; int* qp_solves; int* diag; long long* phase;
-  double* ws; size_t ws_stride; size_t smem_doubles;
+  double* ws; size_t ws_stride; size_t smem_doubles; size_t smem_used;
   int* counter;
+  int poison;     // debug (DGSQP_POISON=1): NaN-fill the CTA's whole workspace before every instance
 };
 
 // SM = true: every hot buffer of the memory plan is shared-memory resident (plan.hot_in_smem)
@@ -68,6 +70,13 @@ __global__ void __launch_bounds__(DG_MAX_THREADS, 1) dgsqp_solve_kernel(const Ga
     const int inst = s_inst;
     __syncthreads();
     if (inst >= A.B) break;
+    if (A.poison) {
+      const double qnan = __longlong_as_double(0x7ff8dead0000beefLL);
+      for (size_t i = threadIdx.x; i < A.smem_used; i += blockDim.x) s_dyn[i] = qnan;
+      double* wsl = A.ws + (size_t)blockIdx.x * A.ws_stride;
+      for (size_t i = threadIdx.x; i < A.ws_stride; i += blockDim.x) wsl[i] = qnan;
+      __syncthreads();
+    }
     if (threadIdx.x == 0) X.x0 = A.x0 + (size_t)inst * D.nq;
     SolveOut O;
     O.u = A.u_out + (size_t)inst * D.n;
@@ -243,6 +252,8 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
   A.B = B; A.x0 = x0; A.u_ws = u_ws; A.l_ws = l_ws; A.u_out = u_out; A.l_out = l_out; A.x_out = x_out; A.cost_out = cost_out;
   A.cond_out = cond_out; A.num_iters = num_iters; A.status = status; A.qp_solves = qp_solves; A.diag = h->d_diag; A.phase = h->d_phase;
   A.ws = h->d_ws; A.ws_stride = h->ws_doubles; A.smem_doubles = h->smem_budget; A.counter = h->d_counter;
+  A.smem_used = h->plan.smem;
+  { const char* e = getenv("DGSQP_POISON"); A.poison = (e && e[0] == '1') ? 1 : 0; }
   int grid = B < h->grid_cap ? B : h->grid_cap;
   if (h->plan.hot_in_smem) dgsqp_solve_kernel<true><<<grid, h->threads, h->smem_bytes, st>>>(h->d_G, h->d_P, A);
   else dgsqp_solve_kernel<false><<<grid, h->threads, h->smem_bytes, st>>>(h->d_G, h->d_P, A);

@@ -507,19 +507,25 @@ DG_DEV double hc_ux(const double* hc, int cu, int j) { return (cu == 1 && j >= 2
 DG_DEV double hc_uu(const double* hc, int c1, int c2) { return (c1 == 1 && c2 == 1) ? hc[14] : 0.0; }
 
 // Game Hessian Q (f_Q): ONE backward sweep over the stages carrying all M+1 functions (the M costs and
-// l'C); rows of Q are owned by threads.   row block a of Q = grad_{u^a} grad_u (J^a + l'C)   (DGSQP.py:920-934)
-// Thread r (stage-major input index (k_r, a_r, c_r)) keeps w^f = row r of Dxu_Q^f for every function f in
-// E.Wrow[(f*nq + q)*n + r] (coalesced).  At stage k < k_r it emits H^f[r, (k,b,cc)] = w^f[b] . B^b_k[:,cc] and
-// stores  Q[r][(k,b,cc)] = H^{a_r} + H^M  and, by symmetry of each H^f,  Q[(k,b,cc)][r] = H^b + H^M.
+// l'C).   row block a of Q = grad_{u^a} grad_u (J^a + l'C)   (DGSQP.py:920-934)
+// Row r (stage-major input index (k_r, a_r, c_r)) of Dxu_Q^f is kept as w^f in E.Wrow[(f*nq + q)*n + r] for every
+// function f.  At stage k < k_r the row emits H^f[r, (k,b,cc)] = w^f[b] . B^b_k[:,cc] and
+// Q[r][(k,b,cc)] = H^{a_r} + H^M  and, by symmetry of each H^f,  Q[(k,b,cc)][r] = H^b + H^M.
 // Every entry of Q is written exactly once, so Q needs no zero-fill and no read-modify-write.
+// Per stage, two barrier intervals whose work items are spread over the whole CTA:
+//   A: (row r with k_r > k, agent block b): propagate w through A_k^b and emit the two Q entries       [n_later*M items]
+//      (function f, new row (a_r,c_r), column j): tv = B_k' V^f  (first half of the same-stage products) [F*nu*nq items]
+//      (function f, i1, i2): V_k = lxx_k + A'VA + E.p                                                      [F*nq*nq items]
+//   B: (f, new row, b, j): w = tv A_k + (G.p)   and   (new row, b, cc): same-stage block luu + B'VB + F.p
 template <bool SM>
 DG_DEVN void game_hessian(Cta& c, const GameDesc& G, const Dims& D_, const EvalBuf& E_, const double* DG_RESTRICT l) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
   const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
-  const int n = D.n, nq = D.nq, N = D.N, M = D.M, F = D.M + 1;
+  const int n = D.n, nq = D.nq, nu = D.nu, N = D.N, M = D.M, F = D.M + 1;
   const double* xN = E.x + N * nq;
   double* Vcur = E.Vbuf;
   double* Vnext = E.Vbuf + F * nq * nq;
+  double* DG_RESTRICT TV = E.Vbuf + 2 * F * nq * nq;            // [(f*nu + rr)*nq + j]
   DG_FOR(t, F * nq * nq) {
     int f = t / (nq * nq), e = t - f * nq * nq, i1 = e / nq, i2 = e - i1 * nq;
     Vcur[t] = f < M ? term_hess(G, D, xN, f, i1, i2) : con_lxx(D, l, N, i1, i2);
@@ -527,98 +533,99 @@ DG_DEVN void game_hessian(Cta& c, const GameDesc& G, const Dims& D_, const EvalB
   c.sync();
   double* DG_RESTRICT Qm = E.Q;
   for (int k = N - 1; k >= 0; --k) {
-    for (int r = c.tid(); r < n; r += c.nt()) {
-      const int kr = r / D.nu, ar = (r - kr * D.nu) >> 1, cr = r & 1;
-      const int rowQ = uidx(D, ar, kr, cr);
-      double* DG_RESTRICT wr = E.Wrow + r;                     // w^f[q] at wr[(f*nq + q)*n]
-      if (kr > k) {
-        for (int b = 0; b < M; ++b) {
-          const double* DG_RESTRICT ABk = E.AB + (k * M + b) * 48;
-          double hM[2] = {0.0, 0.0}, hA[2] = {0.0, 0.0}, hB[2] = {0.0, 0.0};
-          for (int f = 0; f < F; ++f) {
-            if (f != M && f != ar && f != b) {
-              // this function's row is only propagated
-            }
-            double wv6[DG_NQA];
-            for (int i = 0; i < DG_NQA; ++i) wv6[i] = wr[(f * nq + b * DG_NQA + i) * n];
-            if (f == M || f == ar || f == b) {
-              for (int cc = 0; cc < 2; ++cc) {
-                double val = 0.0;
-                for (int i = 0; i < DG_NQA; ++i) val += wv6[i] * ABk[i * 8 + 6 + cc];
-                if (f < M && kr == k + 1 && b == ar && f == ar && cc == cr) val -= G.w_du[cc];
-                if (f == M) hM[cc] = val;
-                if (f == ar) hA[cc] = val;
-                if (f == b) hB[cc] = val;
-              }
-            }
-            for (int j = 0; j < DG_NQA; ++j) {
-              double acc = 0.0;
-              for (int i = 0; i < DG_NQA; ++i) acc += wv6[i] * ABk[i * 8 + j];
-              wr[(f * nq + b * DG_NQA + j) * n] = acc;
-            }
-          }
-          for (int cc = 0; cc < 2; ++cc) {
-            const int colQ = uidx(D, b, k, cc);
-            Qm[rowQ * n + colQ] = hA[cc] + hM[cc];
-            Qm[colQ * n + rowQ] = hB[cc] + hM[cc];
-          }
-        }
-      } else if (kr == k) {
-        const double* DG_RESTRICT ABa = E.AB + (k * M + ar) * 48;
-        double a1M[2 * DG_MAX_AGENTS], a1A[2 * DG_MAX_AGENTS];
+    const int nlater = n - (k + 1) * nu;                          // rows with k_r > k
+    const int nA1 = nlater * M, nA2 = F * nu * nq, nA3 = F * nq * nq;
+    for (int t = c.tid(); t < nA1 + nA2 + nA3; t += c.nt()) {
+      if (t < nA1) {
+        const int b = t / nlater, r = (k + 1) * nu + (t - b * nlater);
+        const int kr = r / nu, ar = (r - kr * nu) >> 1, cr = r & 1;
+        const int rowQ = uidx(D, ar, kr, cr);
+        double* DG_RESTRICT wr = E.Wrow + r;                     // w^f[q] at wr[(f*nq + q)*n]
+        const double* DG_RESTRICT ABk = E.AB + (k * M + b) * 48;
+        double hM0 = 0.0, hM1 = 0.0, hA0 = 0.0, hA1 = 0.0, hB0 = 0.0, hB1 = 0.0;
         for (int f = 0; f < F; ++f) {
-          const double* DG_RESTRICT Vf = Vcur + f * nq * nq;
-          const double* DG_RESTRICT hc = E.Hc + ((f * N + k) * M + ar) * 15;
-          double tv[DG_MAX_NQ];
-          for (int j = 0; j < nq; ++j) {
+          double wv6[DG_NQA];
+#pragma unroll
+          for (int i = 0; i < DG_NQA; ++i) wv6[i] = wr[(f * nq + b * DG_NQA + i) * n];
+          if (f == M || f == ar || f == b) {
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < DG_NQA; ++i) { v0 += wv6[i] * ABk[i * 8 + 6]; v1 += wv6[i] * ABk[i * 8 + 7]; }
+            if (f < M && kr == k + 1 && b == ar && f == ar) { if (cr == 0) v0 -= G.w_du[0]; else v1 -= G.w_du[1]; }
+            if (f == M) { hM0 = v0; hM1 = v1; }
+            if (f == ar) { hA0 = v0; hA1 = v1; }
+            if (f == b) { hB0 = v0; hB1 = v1; }
+          }
+#pragma unroll
+          for (int j = 0; j < DG_NQA; ++j) {
             double acc = 0.0;
-            for (int i = 0; i < DG_NQA; ++i) acc += ABa[i * 8 + 6 + cr] * Vf[(ar * DG_NQA + i) * nq + j];
-            tv[j] = acc;
-          }
-          if (f == M || f == ar) {
-            // same-stage block A1 = luu + B'VB + F.p
-            for (int b = 0; b < M; ++b) {
-              const double* DG_RESTRICT ABb = E.AB + (k * M + b) * 48;
-              for (int cc = 0; cc < 2; ++cc) {
-                double val = 0.0;
-                for (int i = 0; i < DG_NQA; ++i) val += tv[b * DG_NQA + i] * ABb[i * 8 + 6 + cc];
-                if (b == ar) {
-                  val += hc_uu(hc, cr, cc);
-                  if (f < M && cc == cr) val += G.w_u[cc] + G.w_du[cc] + (k + 1 < N ? G.w_du[cc] : 0.0);
-                }
-                if (f == M) a1M[b * 2 + cc] = val; else a1A[b * 2 + cc] = val;
-              }
-            }
-          }
-          // w = t A_k + (G.p)[(ar,cr), ar-block]
-          for (int b = 0; b < M; ++b) {
-            const double* DG_RESTRICT ABb = E.AB + (k * M + b) * 48;
-            for (int j = 0; j < DG_NQA; ++j) {
-              double acc = b == ar ? hc_ux(hc, cr, j) : 0.0;
-              for (int i = 0; i < DG_NQA; ++i) acc += tv[b * DG_NQA + i] * ABb[i * 8 + j];
-              wr[(f * nq + b * DG_NQA + j) * n] = acc;
-            }
+#pragma unroll
+            for (int i = 0; i < DG_NQA; ++i) acc += wv6[i] * ABk[i * 8 + j];
+            wr[(f * nq + b * DG_NQA + j) * n] = acc;
           }
         }
-        for (int b = 0; b < M; ++b)
-          for (int cc = 0; cc < 2; ++cc) Qm[rowQ * n + uidx(D, b, k, cc)] = a1A[b * 2 + cc] + a1M[b * 2 + cc];
+        const int colQ = uidx(D, b, k, 0);
+        Qm[rowQ * n + colQ] = hA0 + hM0;  Qm[rowQ * n + colQ + 1] = hA1 + hM1;
+        Qm[colQ * n + rowQ] = hB0 + hM0;  Qm[(colQ + 1) * n + rowQ] = hB1 + hM1;
+      } else if (t < nA1 + nA2) {
+        const int e = t - nA1, f = e / (nu * nq), rem = e - f * nu * nq, rr = rem / nq, j = rem - rr * nq;
+        const int ar = rr >> 1, cr = rr & 1;
+        const double* DG_RESTRICT ABa = E.AB + (k * M + ar) * 48;
+        const double* DG_RESTRICT Vf = Vcur + f * nq * nq;
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < DG_NQA; ++i) acc += ABa[i * 8 + 6 + cr] * Vf[(ar * DG_NQA + i) * nq + j];
+        TV[e] = acc;
+      } else {
+        // V_k = lxx_k + A'VA + E.p  for every function (into the other buffer)
+        const int tt = t - nA1 - nA2;
+        const int f = tt / (nq * nq), e = tt - f * nq * nq;
+        const int i1 = e / nq, i2 = e - i1 * nq, b1 = i1 / DG_NQA, b2 = i2 / DG_NQA, c1 = i1 - b1 * DG_NQA, c2 = i2 - b2 * DG_NQA;
+        const double* DG_RESTRICT A1 = E.AB + (k * M + b1) * 48;
+        const double* DG_RESTRICT A2 = E.AB + (k * M + b2) * 48;
+        const double* DG_RESTRICT Vf = Vcur + f * nq * nq;
+        double acc = (f == M && k >= 1) ? con_lxx(D, l, k, i1, i2) : 0.0;
+        if (b1 == b2) acc += hc_xx(E.Hc + ((f * N + k) * M + b1) * 15, c1, c2);
+#pragma unroll
+        for (int i = 0; i < DG_NQA; ++i) {
+          double rowacc = 0.0;
+#pragma unroll
+          for (int j = 0; j < DG_NQA; ++j) rowacc += Vf[(b1 * DG_NQA + i) * nq + b2 * DG_NQA + j] * A2[j * 8 + c2];
+          acc += A1[i * 8 + c1] * rowacc;
+        }
+        Vnext[tt] = acc;
       }
     }
-    // V_k = lxx_k + A'VA + E.p  for every function (into the other buffer)
-    DG_FOR(t, F * nq * nq) {
-      int f = t / (nq * nq), e = t - f * nq * nq;
-      int i1 = e / nq, i2 = e - i1 * nq, b1 = i1 / DG_NQA, b2 = i2 / DG_NQA, c1 = i1 - b1 * DG_NQA, c2 = i2 - b2 * DG_NQA;
-      const double* DG_RESTRICT A1 = E.AB + (k * M + b1) * 48;
-      const double* DG_RESTRICT A2 = E.AB + (k * M + b2) * 48;
-      const double* DG_RESTRICT Vf = Vcur + f * nq * nq;
-      double acc = (f == M && k >= 1) ? con_lxx(D, l, k, i1, i2) : 0.0;
-      if (b1 == b2) acc += hc_xx(E.Hc + ((f * N + k) * M + b1) * 15, c1, c2);
-      for (int i = 0; i < DG_NQA; ++i) {
-        double rowacc = 0.0;
-        for (int j = 0; j < DG_NQA; ++j) rowacc += Vf[(b1 * DG_NQA + i) * nq + b2 * DG_NQA + j] * A2[j * 8 + c2];
-        acc += A1[i * 8 + c1] * rowacc;
+    c.sync();
+    const int nB1 = F * nu * nq, nB2 = nu * M * 2;
+    for (int t = c.tid(); t < nB1 + nB2; t += c.nt()) {
+      if (t < nB1) {
+        // w = tv A_k + (G.p)[(ar,cr), ar-block]
+        const int f = t / (nu * nq), rem = t - f * nu * nq, rr = rem / nq, q = rem - rr * nq, b = q / DG_NQA, j = q - b * DG_NQA;
+        const int ar = rr >> 1, cr = rr & 1;
+        const double* DG_RESTRICT ABb = E.AB + (k * M + b) * 48;
+        const double* DG_RESTRICT tv = TV + (f * nu + rr) * nq + b * DG_NQA;
+        double acc = b == ar ? hc_ux(E.Hc + ((f * N + k) * M + ar) * 15, cr, j) : 0.0;
+#pragma unroll
+        for (int i = 0; i < DG_NQA; ++i) acc += tv[i] * ABb[i * 8 + j];
+        E.Wrow[(f * nq + q) * n + k * nu + rr] = acc;
+      } else {
+        // same-stage block A1 = luu + B'VB + F.p  of the functions M and a_r
+        const int e = t - nB1, rr = e / (M * 2), rem = e - rr * M * 2, b = rem >> 1, cc = rem & 1;
+        const int ar = rr >> 1, cr = rr & 1;
+        const double* DG_RESTRICT ABb = E.AB + (k * M + b) * 48;
+        double vM = 0.0, vA = 0.0;
+        const double* DG_RESTRICT tvM = TV + (M * nu + rr) * nq + b * DG_NQA;
+        const double* DG_RESTRICT tvA = TV + (ar * nu + rr) * nq + b * DG_NQA;
+#pragma unroll
+        for (int i = 0; i < DG_NQA; ++i) { vM += tvM[i] * ABb[i * 8 + 6 + cc]; vA += tvA[i] * ABb[i * 8 + 6 + cc]; }
+        if (b == ar) {
+          vM += hc_uu(E.Hc + ((M * N + k) * M + ar) * 15, cr, cc);
+          vA += hc_uu(E.Hc + ((ar * N + k) * M + ar) * 15, cr, cc);
+          if (cc == cr) vA += G.w_u[cc] + G.w_du[cc] + (k + 1 < N ? G.w_du[cc] : 0.0);
+        }
+        Qm[uidx(D, ar, k, cr) * n + uidx(D, b, k, cc)] = vA + vM;
       }
-      Vnext[t] = acc;
     }
     c.sync();
     double* tmp = Vcur; Vcur = Vnext; Vnext = tmp;

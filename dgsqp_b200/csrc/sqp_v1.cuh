@@ -71,7 +71,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   { double* t; PLACE(t, (n + 1) / 2 + 1); W.Q.act = (int*)t; PLACE(t, (m + 1) / 2 + 1); W.Q.is_act = (int*)t; }
   const bool pool_ok = go == 0;                 // nothing of the pool fell back to global memory
   // ---- ARENA
-  const size_t ev_a = rnd(N * M * 48) + rnd((M + 1) * (N + 1) * nq) + rnd((M + 1) * N * M * 15) + rnd(2 * (M + 1) * nq * nq) +
+  const size_t ev_a = rnd(N * M * 48) + rnd((M + 1) * (N + 1) * nq) + rnd((M + 1) * N * M * 15) + rnd(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq) +
                       rnd((M + 1) * nq * n) + rnd(N * M * 90);
   const size_t mats = 2 * rnd(n * ld);
   const size_t arena = ev_a > mats ? ev_a : mats;
@@ -81,7 +81,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
     size_t o = 0;
     auto sub = [&](size_t cnt) { double* r = ar ? ar + o : nullptr; o += rnd(cnt); return r; };
     W.E.AB = sub(N * M * 48); W.E.cst = sub((M + 1) * (N + 1) * nq); W.E.Hc = sub((M + 1) * N * M * 15);
-    W.E.Vbuf = sub(2 * (M + 1) * nq * nq); W.E.Wrow = sub((M + 1) * nq * n); W.E.T2 = sub(N * M * 90);
+    W.E.Vbuf = sub(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq); W.E.Wrow = sub((M + 1) * nq * n); W.E.T2 = sub(N * M * 90);
     W.B.ld = (int)ld; W.B.matA = ar; W.B.matB = ar ? ar + rnd(n * ld) : nullptr;
   }
   // ---- SENS

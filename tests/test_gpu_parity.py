@@ -156,15 +156,17 @@ def test_full_size_deterministic_and_batch_independent(big_batch):
     game, params, solver, x0, u_ws, res = big_batch
     again = solver.solve_batch(x0, u_ws)
     assert np.array_equal(again.status, res.status) and np.array_equal(again.num_iters, res.num_iters)
-    assert np.array_equal(again.u, res.u) and np.array_equal(again.l, res.l)
+    # bit patterns: an instance that ends in 'qp_fail' / 'diverged' may legitimately carry NaNs (NaN != NaN)
+    bits = lambda a: np.ascontiguousarray(a).view(np.int64)
+    assert np.array_equal(bits(again.u), bits(res.u)) and np.array_equal(bits(again.l), bits(res.l))
     # an instance's result does not depend on its position or on its batch mates
     idx = np.array([7, 4242, 9999, 123, 5000])
     sub = solver.solve_batch(x0[idx], u_ws[idx])
     assert np.array_equal(sub.status, res.status[idx]) and np.array_equal(sub.num_iters, res.num_iters[idx])
-    assert np.array_equal(sub.u, res.u[idx])
+    assert np.array_equal(bits(sub.u), bits(res.u[idx]))
     perm = np.random.default_rng(0).permutation(2000)
     p = solver.solve_batch(x0[perm], u_ws[perm])
-    assert np.array_equal(p.u, res.u[perm]) and np.array_equal(p.status, res.status[perm])
+    assert np.array_equal(bits(p.u), bits(res.u[perm])) and np.array_equal(p.status, res.status[perm])
 
 
 def test_device_path_equals_host_path(big_batch):
