@@ -18,6 +18,8 @@ enum { PH_LIN_FULL = 0, PH_ADJ_FULL, PH_HESS, PH_PD_TRIDIAG, PH_PD_EIG, PH_CHOL,
        PH_LIN_GRAD, PH_ADJ_GRAD, PH_MERIT, PH_OTHER, DG_NPHASE };
 
 #ifdef DG_HOSTSIM
+#define DG_RSQRT(x) (1.0 / sqrt(x))
+#define DG_ATOMIC_MIN(p, v) do { if ((v) < *(p)) *(p) = (v); } while (0)
 #define DG_DEV static inline
 #define DG_HD static inline
 #define DG_DEVN static
@@ -48,6 +50,8 @@ struct Cta {
   inline void lap(int) {}
 };
 #else
+#define DG_RSQRT(x) rsqrt(x)
+#define DG_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define DG_DEV __device__ __forceinline__
 #define DG_HD __host__ __device__ __forceinline__
 #define DG_DEVN __device__ __noinline__

@@ -14,7 +14,6 @@
 #include "sqp_v1.cuh"
 #include "host_setup.h"
 
-#define DG_MAX_THREADS 512
 #define DGSQP_VERSION_STR "dgsqp_b200 0.1.0 (sm_100a)"
 
 static thread_local std::string g_last_error;
@@ -223,7 +222,7 @@ int dgsqp_dims(const dgsqp_handle* h, int32_t dims[4]) {
 
 int dgsqp_configure(dgsqp_handle* h, int32_t ctas_per_sm, int32_t threads) {
   if (!h) return set_err(DGSQP_EINVAL, "NULL handle");
-  if (threads != 0 && (threads < 32 || threads > DG_MAX_THREADS || (threads & 31))) return set_err(DGSQP_EINVAL, "threads must be a multiple of 32 in [32,512]");
+  if (threads != 0 && (threads < 32 || threads > DG_MAX_THREADS || (threads & 31))) return set_err(DGSQP_EINVAL, "threads must be a multiple of 32 in [32,256]");
   CUDA_TRY(cudaSetDevice(h->device));
   h->ctas_per_sm = ctas_per_sm;
   if (threads) h->threads = threads;

@@ -20,8 +20,9 @@
 #define DG_EIG_INVIT 3      // inverse-iteration sweeps per eigenvector (shifts are accurate to ~1 ulp of |T|)
 #define DG_CHOL_NB 8        // Cholesky panel width
 #ifndef DG_MAX_THREADS
-#define DG_MAX_THREADS 512
+#define DG_MAX_THREADS 256
 #endif
+#define DG_PART_SZ 512      // doubles in LinBuf::part
 
 struct LinBuf {
   int ld;         // leading dimension of matA / matB
@@ -37,7 +38,7 @@ struct LinBuf {
   double* pv;     // n
   double* wv;     // n
   double* sp;     // n*DG_CHOL_NB  Cholesky panel (aliases the seven vectors above)
-  double* part;   // max(DG_MAX_THREADS, n)  partial sums of the 2D-decomposed products
+  double* part;   // max(DG_PART_SZ, n)  partial sums of the 2D-decomposed products, scratch vectors
 };
 
 #ifdef DG_NO_SH_LIN
@@ -138,6 +139,132 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_) {
   c.sync();
 }
 
+#ifndef DG_HOSTSIM
+// Register-resident variant of sym_tridiag for 256-thread CTAs and n <= 2*RMAX <= 128: the trailing matrix never
+// touches shared memory.  Thread (i = tid & 127, g = tid >> 7) owns column i of the rows j = g, g+2, ... in
+// a[r] (j = g + 2r); the Householder vector / the rank-2 vectors are broadcast from shared memory in a parity-split
+// layout (element j at (j&1)*XS + (j>>1)) so that a thread fetches two of its rows' coefficients per 128-bit load.
+// Per step: partial products  sum_j A[j][i] u_j  (u = v / scale, u_off = alpha - beta)  ->  barrier  ->  p, v, p.v
+// (block sum)  ->  w = p - hk v  ->  barrier  ->  A -= v w' + w v' in registers, the next row (= next column, by
+// symmetry) and the next diagonal entry are peeled off on the fly  ->  block sum of the next column norm.
+// Same outputs as sym_tridiag: dg, od, od2, tau and the reflectors in W[k+2.., k].
+template <int RMAX, bool SM>
+DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
+  const LinBuf B = B_; DG_SH_LIN_T(B);
+  double* DG_RESTRICT W = B.matA;
+  const int ld = B.ld;
+  const int i = c.tid() & 127, g = c.tid() >> 7;
+  const int XS = (((n + 1) >> 1) + 1) & ~1;                       // even stride of the parity-split layout
+  double* DG_RESTRICT part = B.part;                              // [2][128] partial products
+  double* DG_RESTRICT xs = B.part + 256;                          // u  (parity-split, 2*XS <= 256)
+  double* DG_RESTRICT pv = B.pv;                                  // v  (parity-split)
+  double* DG_RESTRICT wv = B.pv + (((3 * n) >> 1) + 1 & ~1);      // w  (parity-split; pv..pv+3n is one region)
+#define DG_PS(j) ((((j) & 1) * XS) + ((j) >> 1))
+  const int r_end = (n - g + 1) >> 1;                             // rows owned: j = g + 2r < n
+  const bool col_ok = i < n;
+  double a[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) { const int j = g + 2 * r; a[r] = (r < r_end && col_ok) ? W[j * ld + i] : 0.0; }
+  // row 0 -> u, |x[1:]|^2, first diagonal entry
+  double nrm = 0.0;
+  if (g == 0 && col_ok) {
+    if (i >= 1) xs[DG_PS(i)] = a[0];
+    if (i >= 2) nrm = a[0] * a[0];
+    if (i == 0) B.dg[0] = a[0];
+  }
+  double xn2 = c.sum(nrm);
+  for (int k = 0; k + 1 < n; ++k) {
+    const int off = k + 1;
+    const double alpha = xs[DG_PS(off)];
+    double tauk = 0.0, beta = alpha, scale = 0.0;
+    if (xn2 > 0.0) {
+      beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+      tauk = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
+    }
+    if (c.tid() == 0) { B.od[k] = beta; B.od2[k] = beta * beta; B.tau[k] = tauk; }
+    const int r_first = (off - g + 1) >> 1;                       // first owned row with j >= off
+    const bool colact = col_ok && i >= off;
+    double vi = 0.0, wi = 0.0;
+    if (tauk != 0.0) {
+      const double amb = alpha - beta;
+      const double* DG_RESTRICT xg = xs + g * XS;
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int cb = 0; cb < RMAX; cb += 4) {
+        if (cb + 4 > r_first && cb < r_end) {
+          const double2 x01 = *reinterpret_cast<const double2*>(xg + cb);
+          const double2 x23 = *reinterpret_cast<const double2*>(xg + cb + 2);
+          const double xq[4] = {x01.x, x01.y, x23.x, x23.y};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = cb + q;
+            {
+              const int j = g + 2 * r;
+              const double uv = j == off ? amb : xq[q];
+              if (r >= r_first && r < r_end) { if (q & 1) acc1 += a[r] * uv; else acc0 += a[r] * uv; }
+            }
+          }
+        }
+      }
+      part[g * 128 + i] = acc0 + acc1;
+      c.sync();
+      double pdot = 0.0, pi = 0.0;
+      if (g == 0 && colact) {
+        pi = (part[i] + part[128 + i]) * (tauk * scale);
+        vi = i == off ? 1.0 : xs[DG_PS(i)] * scale;
+        pv[DG_PS(i)] = vi;
+        pdot = pi * vi;
+      }
+      const double hk = 0.5 * tauk * c.sum(pdot);
+      if (g == 0 && colact) {
+        wv[DG_PS(i)] = pi - hk * vi;
+        if (i > off) W[i * ld + k] = vi;                           // keep the reflector
+      }
+      c.sync();
+      if (colact) { vi = pv[DG_PS(i)]; wi = wv[DG_PS(i)]; }
+    }
+    // rank-2 update of the owned rows j >= off; row off (= the next column) and the next diagonal entry peel off
+    nrm = 0.0;
+    {
+      const double* DG_RESTRICT pg = pv + g * XS;
+      const double* DG_RESTRICT wg = wv + g * XS;
+#pragma unroll
+      for (int cb = 0; cb < RMAX; cb += 4) {
+        if (cb + 4 > r_first && cb < r_end) {
+          double vq[4] = {0.0, 0.0, 0.0, 0.0}, wq[4] = {0.0, 0.0, 0.0, 0.0};
+          if (tauk != 0.0) {
+            const double2 v01 = *reinterpret_cast<const double2*>(pg + cb), v23 = *reinterpret_cast<const double2*>(pg + cb + 2);
+            const double2 w01 = *reinterpret_cast<const double2*>(wg + cb), w23 = *reinterpret_cast<const double2*>(wg + cb + 2);
+            vq[0] = v01.x; vq[1] = v01.y; vq[2] = v23.x; vq[3] = v23.y;
+            wq[0] = w01.x; wq[1] = w01.y; wq[2] = w23.x; wq[3] = w23.y;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = cb + q;
+            {
+              const int j = g + 2 * r;
+              if (r >= r_first && r < r_end && colact) {
+                if (tauk != 0.0) a[r] -= vq[q] * wi + wq[q] * vi;
+                if (j == off) {
+                  if (i >= off + 1) xs[DG_PS(i)] = a[r];
+                  if (i >= off + 2) nrm += a[r] * a[r];
+                  if (i == off) B.dg[off] = a[r];
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    xn2 = c.sum(nrm);
+  }
+  if (c.tid() == 0) { B.od[n - 1] = 0.0; B.od2[n - 1] = 0.0; }
+  c.sync();
+#undef DG_PS
+}
+#endif
+
 // number of eigenvalues of tridiag(dg, od) that are < x   (od2 = od^2).
 // Sturm sequence in product form  p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}  (sign changes = negative pivots of
 // the ratio form q_i = p_i / p_{i-1} that LAPACK's dstebz counts): one dependent FMA per row instead of a
@@ -161,55 +288,68 @@ DG_DEV int sturm_count(int n, const double* DG_RESTRICT dg, const double* DG_RES
   return cnt;
 }
 
-// Solve (T - lam I) y = b in place (y overwrites b) by Gaussian elimination with partial pivoting.
-// fw: 5 arrays of n (diag, sup1, sup2, mult, swapped) and y are INTERLEAVED over the vectors of a chunk:
+// Solve (T - lam I) y = b in place (y overwrites b) by Gaussian elimination with partial pivoting; returns |y|^2.
+// fw: 5 arrays of n (reciprocal pivot, sup1, sup2, mult, swapped) and y are INTERLEAVED over the vectors of a chunk:
 // element i of this thread's vector sits at [i * st] (st = chunk width), so that the threads of a warp
 // touch consecutive words.
-DG_DEV void tridiag_shift_solve(int n, const double* dg, const double* od, double lam, double tiny,
-                                double* fw, double* y, int st, bool refactor) {
-  double* a = fw; double* b1 = fw + n * st; double* b2 = fw + 2 * n * st; double* ml = fw + 3 * n * st; double* sw = fw + 4 * n * st;
+// One thread walks the whole chain, so the recurrences are arranged to keep as little as possible on it: pivots are
+// stored as reciprocals (the back substitution multiplies), the running entries of y stay in registers (no
+// store -> load round trip through shared memory per row) and |y|^2 is accumulated beside the chain.
+DG_DEV double tridiag_shift_solve(int n, const double* dg, const double* od, double lam, double tiny,
+                                  double* fw, double* y, int st, bool refactor) {
+  double* ra = fw; double* b1 = fw + n * st; double* b2 = fw + 2 * n * st; double* ml = fw + 3 * n * st; double* sw = fw + 4 * n * st;
+  const double rtiny = 1.0 / tiny;
   if (refactor) {
     // work row "cur" = (p, q, r) starting at column i
     double p = dg[0] - lam, q = n > 1 ? od[0] : 0.0, r = 0.0;
     for (int i = 0; i + 1 < n; ++i) {
-      double sub = od[i], nd = dg[i + 1] - lam, ns = i + 2 < n ? od[i + 1] : 0.0;
+      const double sub = od[i], nd = dg[i + 1] - lam, ns = i + 2 < n ? od[i + 1] : 0.0;
       if (fabs(sub) > fabs(p)) {
-        double m = p / sub;                       // pivot row is the next row (sub, nd, ns)
-        a[i * st] = sub; b1[i * st] = nd; b2[i * st] = ns; ml[i * st] = m; sw[i * st] = 1.0;
+        const double rs = 1.0 / sub;                // pivot row is the next row (sub, nd, ns); sub is off the chain
+        const double m = p * rs;
+        ra[i * st] = fabs(sub) < tiny ? (sub < 0.0 ? -rtiny : rtiny) : rs;
+        b1[i * st] = nd; b2[i * st] = ns; ml[i * st] = m; sw[i * st] = 1.0;
         p = q - m * nd; q = r - m * ns; r = 0.0;
       } else {
         if (p == 0.0) p = tiny;
-        double m = sub / p;
-        a[i * st] = p; b1[i * st] = q; b2[i * st] = r; ml[i * st] = m; sw[i * st] = 0.0;
+        const double rp = 1.0 / p;
+        const double m = sub * rp;
+        ra[i * st] = fabs(p) < tiny ? (p < 0.0 ? -rtiny : rtiny) : rp;
+        b1[i * st] = q; b2[i * st] = r; ml[i * st] = m; sw[i * st] = 0.0;
         p = nd - m * q; q = ns - m * r; r = 0.0;
       }
     }
     if (fabs(p) < tiny) p = p < 0.0 ? -tiny : tiny;
-    a[(n - 1) * st] = p; b1[(n - 1) * st] = 0.0; b2[(n - 1) * st] = 0.0;
+    ra[(n - 1) * st] = 1.0 / p; b1[(n - 1) * st] = 0.0; b2[(n - 1) * st] = 0.0;
   }
+  // forward elimination of the right-hand side: one fused multiply-add per row on the chain
+  double yc = y[0];
   for (int i = 0; i + 1 < n; ++i) {
-    if (sw[i * st] != 0.0) { double t = y[i * st]; y[i * st] = y[(i + 1) * st]; y[(i + 1) * st] = t - ml[i * st] * y[i * st]; }
-    else y[(i + 1) * st] -= ml[i * st] * y[i * st];
+    const double yn = y[(i + 1) * st], m = ml[i * st];
+    if (sw[i * st] != 0.0) { y[i * st] = yn; yc = yc - m * yn; }
+    else { y[i * st] = yc; yc = yn - m * yc; }
   }
-  for (int i = n - 1; i >= 0; --i) {
-    double t = y[i * st];
-    if (i + 1 < n) t -= b1[i * st] * y[(i + 1) * st];
-    if (i + 2 < n) t -= b2[i * st] * y[(i + 2) * st];
-    double piv = a[i * st];
-    if (fabs(piv) < tiny) piv = piv < 0.0 ? -tiny : tiny;
-    y[i * st] = t / piv;
+  // back substitution
+  double y1 = yc * ra[(n - 1) * st], y2 = 0.0, nr = y1 * y1;
+  y[(n - 1) * st] = y1;
+  for (int i = n - 2; i >= 0; --i) {
+    const double t = (y[i * st] - b2[i * st] * y2 - b1[i * st] * y1) * ra[i * st];
+    y[i * st] = t;
+    nr += t * t;
+    y2 = y1; y1 = t;
   }
+  return nr;
 }
 
 // Negative eigenvalues of the tridiagonal matrix into B.lam[0..nneg): Sturm-count multisection.  All
 // eigenvalues are refined together: each round spends the CTA's nt probes evenly over the brackets.
-// lo/hi: nneg doubles each; cnts: nt ints of scratch.
+// lo/hi: nneg doubles each; first: nneg ints of scratch.
 template <bool SM>
 DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, double tnorm, double pivmin,
-                                 double* lo, double* hi, int* cnts) {
+                                 double* lo, double* hi, int* first) {
   // (inlined into nearest_pd, which carries the address-space hints: repeating a hint on the same pointer inside an
   //  inlined callee makes nvcc 12.9 drop the guarded code)
-  DG_FOR(j, nneg) { lo[j] = -tnorm * 1.0000001 - pivmin; hi[j] = 0.0; }
+  DG_FOR(j, nneg) { lo[j] = -tnorm * 1.0000001 - pivmin; hi[j] = 0.0; first[j] = 0x7fffffff; }
   c.sync();
   int per = c.nt() / nneg;                       // probes per eigenvalue per round
   if (per < 1) per = 1;
@@ -220,18 +360,21 @@ DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, doubl
     const int g = c.tid() / per, t = c.tid() - g * per, j = j0 + g;
     const bool act = g < groups && j < nneg;
     for (int rd = 0; rd < rounds; ++rd) {
-      double a = 0.0, b = 0.0, h = 0.0;
+      double a = 0.0, h = 0.0;
       if (act) {
-        a = lo[j]; b = hi[j];
-        h = (b - a) / (double)(per + 1);
-        cnts[c.tid()] = sturm_count(n, B.dg, B.od2, a + h * (double)(t + 1), pivmin);
+        a = lo[j];
+        h = (hi[j] - a) / (double)(per + 1);
+        // first[j] = smallest probe index whose count reaches j+1.  (In floating point the counts of the product-form
+        // Sturm sequence need not be monotone in the shift, so "count reached here but not at the previous probe"
+        // can hold for several probes: the minimum makes the choice unique.)
+        if (sturm_count(n, B.dg, B.od2, a + h * (double)(t + 1), pivmin) >= j + 1) DG_ATOMIC_MIN(&first[j], t);
       }
       c.sync();
-      if (act) {
-        // the probe where the count first reaches j+1 narrows the bracket (exactly one thread per eigenvalue writes)
-        const bool mine = cnts[c.tid()] >= j + 1, prev = t > 0 && cnts[c.tid() - 1] >= j + 1;
-        if (mine && !prev) { if (t > 0) lo[j] = a + h * (double)t; hi[j] = a + h * (double)(t + 1); }
-        else if (!mine && t == per - 1) lo[j] = a + h * (double)per;
+      if (act && t == 0) {
+        const int f = first[j];
+        first[j] = 0x7fffffff;
+        if (f == 0x7fffffff) lo[j] = a + h * (double)per;
+        else { if (f > 0) lo[j] = a + h * (double)f; hi[j] = a + h * (double)(f + 1); }
       }
       c.sync();
     }
@@ -259,6 +402,11 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
       Hm[i * ld + j] = 0.5 * (Qraw[i * n + j] + Qraw[j * n + i]);
     }
     c.sync();
+#ifndef DG_HOSTSIM
+    if (SM && c.nt() == 256 && n <= 104 && n >= 8) sym_tridiag_regs<52, SM>(c, n, B);
+    else if (SM && c.nt() == 256 && n <= 128 && n >= 8) sym_tridiag_regs<64, SM>(c, n, B);
+    else
+#endif
     sym_tridiag<SM>(c, n, B);
     c.lap(PH_PD_TRIDIAG);
     double tn = 0.0;
@@ -270,11 +418,11 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
     const double pivmin = 2.2250738585072014e-308 * fmax(1.0, tnorm * tnorm);
     nneg = sturm_count(n, B.dg, B.od2, 0.0, pivmin);      // every thread computes the same count
     if (nneg > 0) {
-      // scratch carved from matB: [cnts | itw (5 n CH, interleaved) | Zt (n CH, interleaved) | Z (nneg n, vector major)]
+      // scratch carved from matB: [first (n ints) | itw (5 n CH, interleaved) | Zt (n CH, interleaved) | Z (nneg n, vector major)]
       const int CH = DG_EIG_CHUNK;
       double* scr = B.matB;
       int* cnts = (int*)scr;
-      double* itw = scr + ((c.nt() + 1) / 2 + 1);
+      double* itw = scr + ((n + 1) / 2 + 1);
       double* Zt = itw + 5 * n * CH;
       double* Zs = Zt + n * CH;
       const long cap = ((long)n * ld - (Zs - scr)) / n;    // eigenvectors that fit behind the scratch
@@ -292,10 +440,8 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
             double* z = Zt + jj;
             if (itn == 0)
               for (int i = 0; i < n; ++i) z[i * CH] = 1.0 + 0.37 * (double)(((i + 1) * 7919 + (j0 + jj) * 104729) % 97) / 97.0;
-            tridiag_shift_solve(n, B.dg, B.od, B.lam[j0 + jj], tiny, itw + jj, z, CH, itn == 0);
-            double nr = 0.0;
-            for (int i = 0; i < n; ++i) nr += z[i * CH] * z[i * CH];
-            nr = 1.0 / sqrt(nr);
+            double nr = tridiag_shift_solve(n, B.dg, B.od, B.lam[j0 + jj], tiny, itw + jj, z, CH, itn == 0);
+            nr = DG_RSQRT(nr);
             for (int i = 0; i < n; ++i) z[i * CH] *= nr;
           }
           c.sync();
@@ -386,7 +532,7 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, doubl
         double piv = sp[kk * NB + kk];
         for (int t = 0; t < kk; ++t) piv -= sp[kk * NB + t] * sp[kk * NB + t];
         if (!(piv > 0.0)) ok = false;
-        const double inv = 1.0 / sqrt(piv);
+        const double inv = DG_RSQRT(piv);
         c.syncwarp();                               // pivot read by every lane before it is overwritten
         for (int r = kk + c.lane(); r < nb; r += c.wsz) {
           double v;
@@ -450,47 +596,52 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, doubl
   return true;
 }
 
-// Y = L^{-1} (lower triangular; L and Y row-major with leading dimension ld: Y[i][c]).  Columns are independent:
-//   Y[c][c] = 1/L[c][c];  Y[i][c] = -(sum_{j=c}^{i-1} L[i][j] Y[j][c]) / L[i][i]
-// Each column is owned by a group of TG adjacent lanes that split the dot product and combine it with shuffles, so
-// the whole inverse runs without a CTA barrier; lane s of a group stores (and later re-reads) the rows i with
-// (i - c) mod TG == s, i.e. it only ever reads what it wrote itself.
-// The GI solver uses J = L^{-T} = Y' through the accessor J(i,j) = Y[j*ld+i].
+// Y = L^{-1} (lower triangular; L and Y row-major with leading dimension ld: Y[i][c]; the strict upper triangle of Y
+// is zero-filled because the active-set solver treats Y as dense).  Blocked by NB = 8 rows:
+//   diagonal blocks   Y_bb = L_bb^{-1}                       thread per column, 8-step chains, reciprocals hoisted
+//   block row i >= 1  M = Y_ii L_i,0:i   (8 x 8i)            item per entry, <= 8 FMAs
+//                     Y_i,0:i = -M Y_0:i,0:i                 item per entry: dot product over the rows c..8i of column c
+// Two barriers per block row; every O(n^3) product is spread over the whole CTA (the column-recursive form it
+// replaces kept one lane pair per column busy for n dependent dot products).
+// Mi: 8*n doubles of scratch, rdiag: n doubles.  The GI solver uses J = L^{-T} = Y' through J(i,j) = Y[j*ld+i].
 template <bool SM>
-DG_DEVN void tri_inverse(Cta& c, int n, int ld, const double* DG_RESTRICT Lm, double* DG_RESTRICT Y) {
-  DG_ASSUME_SHARED(Lm); DG_ASSUME_SHARED(Y);
-#ifdef DG_HOSTSIM
-  const int TG = 1;
-#else
-  const int TG = c.nt() >= 4 * n ? 4 : (c.nt() >= 2 * n ? 2 : 1);
-#endif
-  const int ngroups = c.nt() / TG;
-  const int s = c.tid() % TG;
-  const int wfirst = (c.tid() - c.lane()) / TG;        // first column group of this warp
-  for (int base = 0; base + wfirst < n; base += ngroups) {       // warp-uniform trip count
-    const int cc = base + c.tid() / TG;
-    const bool act = cc < n;
-    if (act) {
-      for (int i = s; i < cc; i += TG) Y[i * ld + cc] = 0.0;
-      if (s == 0) Y[cc * ld + cc] = 1.0 / Lm[cc * ld + cc];
-    }
-    for (int i = base + wfirst + 1; i < n; ++i) {                // warp-uniform: the shuffles need every lane
-      const double* DG_RESTRICT Li = Lm + i * ld;
+DG_DEVN void tri_inverse(Cta& c, int n, int ld, const double* DG_RESTRICT Lm, double* DG_RESTRICT Y,
+                         double* DG_RESTRICT Mi, double* DG_RESTRICT rdiag) {
+  DG_ASSUME_SHARED(Lm); DG_ASSUME_SHARED(Y); DG_ASSUME_SHARED(Mi); DG_ASSUME_SHARED(rdiag);
+  constexpr int NB = 8;
+  const int nblk = (n + NB - 1) / NB;
+  DG_FOR(i, n) rdiag[i] = 1.0 / Lm[i * ld + i];
+  DG_FOR(t, n * n) { const int i = t / n, j = t - i * n; if (j > i) Y[i * ld + j] = 0.0; }
+  c.sync();
+  DG_FOR(cc, n) {
+    const int b = cc / NB, end = (b + 1) * NB < n ? (b + 1) * NB : n;
+    Y[cc * ld + cc] = rdiag[cc];
+    for (int i = cc + 1; i < end; ++i) {
       double acc = 0.0;
-      const bool on = act && i > cc;
-      if (on) {
-        double a0 = 0.0, a1 = 0.0;
-        int j = cc + s;
-        for (; j + TG < i; j += 2 * TG) { a0 += Li[j] * Y[j * ld + cc]; a1 += Li[j + TG] * Y[(j + TG) * ld + cc]; }
-        if (j < i) a0 += Li[j] * Y[j * ld + cc];
-        acc = a0 + a1;
-      }
-#ifndef DG_HOSTSIM
-      if (TG >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (TG >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-#endif
-      if (on && (i - cc) % TG == s) Y[i * ld + cc] = -acc / Li[i];
+      for (int j = cc; j < i; ++j) acc += Lm[i * ld + j] * Y[j * ld + cc];
+      Y[i * ld + cc] = -acc * rdiag[i];
     }
   }
   c.sync();
+  for (int ib = 1; ib < nblk; ++ib) {
+    const int r0 = ib * NB, nb = n - r0 < NB ? n - r0 : NB, w = r0;
+    for (int e = c.tid(); e < nb * w; e += c.nt()) {
+      const int r = e / w, t = e - r * w;
+      const double* DG_RESTRICT Yr = Y + (r0 + r) * ld + r0;
+      double acc = 0.0;
+      for (int s2 = 0; s2 <= r; ++s2) acc += Yr[s2] * Lm[(r0 + s2) * ld + t];
+      Mi[e] = acc;
+    }
+    c.sync();
+    for (int e = c.tid(); e < nb * w; e += c.nt()) {
+      const int r = e / w, cc = e - r * w;
+      const double* DG_RESTRICT Mr = Mi + r * w;
+      double a0 = 0.0, a1 = 0.0;
+      int t = w - 1;
+      for (; t - 1 >= cc; t -= 2) { a0 += Mr[t] * Y[t * ld + cc]; a1 += Mr[t - 1] * Y[(t - 1) * ld + cc]; }
+      if (t >= cc) a0 += Mr[t] * Y[t * ld + cc];
+      Y[(r0 + r) * ld + cc] = -(a0 + a1);
+    }
+    c.sync();
+  }
 }

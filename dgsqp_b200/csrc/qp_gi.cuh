@@ -77,7 +77,8 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
   double* DG_RESTRICT Rm = B.matA;
   if (!cholesky_lower<SM>(c, n, ld, B.matA, B.sp, B.part)) return 1;
   c.lap(PH_CHOL);
-  tri_inverse<SM>(c, n, ld, B.matA, Y);
+  tri_inverse<SM>(c, n, ld, B.matA, Y, B.sp, B.part);
+  c.sync();
   // x = -J J' q = -Y' (Y q):   t = Y q (warp per row), x_i = -sum_j Y[j][i] t_j
   for (int j = c.warp(); j < n; j += c.nwarps()) {
     const double* DG_RESTRICT Yj = Y + j * ld;
@@ -112,17 +113,28 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
     bool added = false;
     while (!added) {
       if (++it > max_iter) { status = 3; break; }
-      // d = J' n_p = -Y npv   (warp per row);  also npv . x
+      // d = J' n_p = -Y npv   (2D over the CTA: thread = row of Y, column groups interleave the columns);  also npv . x
       double dd_tail = 0.0, dd_all = 0.0, gx = 0.0;
-      for (int j = c.warp(); j < n; j += c.nwarps()) {
-        const double* DG_RESTRICT Yj = Y + j * ld;
-        double pp = 0.0;
-        for (int i = c.lane(); i < n; i += c.wsz) pp += Yj[i] * Q.npv[i];
-        pp = -c.warp_sum(pp);
-        if (c.lane() == 0) {
-          Q.dv[j] = pp;
-          dd_all += pp * pp;
-          if (j >= iq) dd_tail += pp * pp;
+      {
+        const Split2 sp = split2(c, n);
+        for (int j = sp.i0; j < n; j += sp.istep) {
+          const double* DG_RESTRICT Yj = Y + j * ld;
+          double a0 = 0.0, a1 = 0.0;
+          int i = sp.g;
+          for (; i + sp.G < n; i += 2 * sp.G) { a0 += Yj[i] * Q.npv[i]; a1 += Yj[i + sp.G] * Q.npv[i + sp.G]; }
+          if (i < n) a0 += Yj[i] * Q.npv[i];
+          B.part[sp.g * sp.istep + j] = a0 + a1;
+        }
+        c.sync();
+        if (sp.g == 0) {
+          for (int j = sp.i0; j < n; j += sp.istep) {
+            double acc = B.part[j];
+            for (int g = 1; g < sp.G; ++g) acc += B.part[g * sp.istep + j];
+            acc = -acc;
+            Q.dv[j] = acc;
+            dd_all += acc * acc;
+            if (j >= iq) dd_tail += acc * acc;
+          }
         }
       }
       DG_FOR(i, n) gx += Q.npv[i] * Q.xq[i];
@@ -165,9 +177,13 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
       c.sync();
       // dual step bound t1, primal step length t2
       double t1 = 1e300; int ldrop = -1;
-      for (int k = 0; k < iq; ++k) {
-        double rk = Q.rv[k];
-        if (rk > 0.0) { double tk = Q.lam_act[k] / rk; if (tk < t1) { t1 = tk; ldrop = k; } }
+      {
+        double bv = 1e300; int bk = 0x7fffffff;
+        DG_FOR(k, iq) {
+          const double rk = Q.rv[k];
+          if (rk > 0.0) { const double tk = Q.lam_act[k] / rk; if (tk < bv) { bv = tk; bk = k; } }
+        }
+        if (iq > 0) { c.argmin(bv, bk, t1, ldrop); if (!(t1 < 1e300)) ldrop = -1; }
       }
       double t2 = 1e300;
       if (zn > DG_QP_DEP_TOL * dall && zn > 0.0) t2 = (E.g[p] + gx) / zn;      // -s_p / |d2|^2

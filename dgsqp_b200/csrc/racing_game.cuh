@@ -104,7 +104,11 @@ DG_DEV int uidx(const Dims& D, int a, int k, int c) { return a * D.twoN + 2 * k 
 
 // ---- track look-ups (radius_arclength_track.py:199-225; CasADi pw_const / pw_lin / fmod) ----
 DG_DEV void track_eval(const TrackTable& T, double s, double& kappa, double& psit, double& dpsit) {
-  double sb = fmod(fmod(s, T.L) + T.L, T.L);
+  // sb = fmod(fmod(s, L) + L, L).  For 0 <= s < L both fmods are exact subtractions (fmod(s, L) = s and s + L lies in
+  // [L, 2L]), so the fast path returns bit-for-bit the same value without the two slow fmod calls.
+  double sb;
+  if (s >= 0.0 && s < T.L) { const double t = s + T.L; sb = t >= 2.0 * T.L ? t - 2.0 * T.L : t - T.L; }
+  else sb = fmod(fmod(s, T.L) + T.L, T.L);
   double kap = T.curv[0];
   double l_prev = T.cum_ang[0] + T.slope[0] * (sb - T.cum_len[0]);
   double ps = l_prev, dp = T.slope[0];
@@ -144,20 +148,50 @@ struct EvalBuf {
   DG_ASSUME_SHARED((E).tmpS); DG_ASSUME_SHARED((E).cf); DG_ASSUME_SHARED((E).AB); DG_ASSUME_SHARED((E).cst); DG_ASSUME_SHARED((E).Hc); \
   DG_ASSUME_SHARED((E).Vbuf); DG_ASSUME_SHARED((E).Wrow); DG_ASSUME_SHARED((E).T2); DG_ASSUME_SHARED((E).S); } while (0)
 
-// x_{k+1} = x_k + dt f(x_k,u_k): agents are dynamically decoupled, thread a rolls out agent a.
+// x_{k+1} = x_k + dt f(x_k,u_k)  (explicit Euler of the Frenet bicycle, dynamics_models.py:1030-1070,90-91).
+// Agents are dynamically decoupled and the stage recursion is serial, so only M threads can walk the horizon.  Everything
+// that depends on the inputs alone is therefore hoisted into a CTA-wide pre-pass over the N*M stages
+//   beta = atan(L_r tan(delta) / L),  c_rot = psidot / v = tan(delta) / (L sqrt(1 + (L_r tan(delta)/L)^2)),
+//   c_slip = c_s (tan(delta)/L)^2 / (1 + (L_r tan(delta)/L)^2)
+// (pre[(k*M + a)*3 ..]), which leaves two sincos and one division on the serial chain of a stage.
 template <bool SM>
-DG_DEVN void game_rollout(Cta& c, const GameDesc& G, const Dims& D_, const double* u, const double* x0, double* x) {
+DG_DEVN void game_rollout(Cta& c, const GameDesc& G, const Dims& D_, const double* u, const double* x0, double* x,
+                          double* pre) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
   const Dims D = D_;
-  DG_ASSUME_SHARED(x);
+  DG_ASSUME_SHARED(x); DG_ASSUME_SHARED(pre);
+  const BicycleParams P = G.veh;
+  DG_FOR(t, D.N * D.M) {
+    const int k = t / D.M, a = t - k * D.M;
+    const double t0 = tan(u[uidx(D, a, k, 1)]);
+    const double t1 = t0 / P.L;
+    const double t5 = t1 * t1;
+    const double t6 = (P.Lr * P.Lr) * t5 + 1.0;
+    pre[t * 3] = atan(P.Lr * t1);
+    pre[t * 3 + 1] = t1 / sqrt(t6);
+    pre[t * 3 + 2] = P.c_s * t5 / t6;
+  }
+  c.sync();
   DG_FOR(a, D.M) {
     double qk[DG_NQA];
     for (int i = 0; i < DG_NQA; ++i) { qk[i] = x0[a * DG_NQA + i]; x[a * DG_NQA + i] = qk[i]; }
     for (int k = 0; k < D.N; ++k) {
-      double kap, ps, dp, dq[DG_NQA];
+      double kap, ps, dp;
       track_eval(G.trk, qk[4], kap, ps, dp);
-      bicycle_fd_raw(qk, u + uidx(D, a, k, 0), G.veh, kap, ps, dp, qk[2] > 0 ? 1.0 : -1.0, dq);
-      for (int i = 0; i < DG_NQA; ++i) { qk[i] += dq[i]; x[(k + 1) * D.nq + a * DG_NQA + i] = qk[i]; }
+      const double* pk = pre + (k * D.M + a) * 3;
+      const double v = qk[2], sgnv = v > 0 ? 1.0 : -1.0;
+      const double t2 = qk[3] + pk[0], t4 = P.dt * v;
+      double s2, c2, s3, c3;
+      sincos(t2, &s2, &c2);
+      sincos(ps + t2, &s3, &c3);
+      const double t7 = c2 / (qk[5] * kap - 1.0);
+      qk[0] += t4 * c3;
+      qk[1] += t4 * s3;
+      qk[2] += P.dt * (u[uidx(D, a, k, 0)] - P.inv_m * v * (P.c_da + P.c_dr * sgnv * v + pk[2] * v));
+      qk[3] += t4 * (kap * t7 + pk[1]);
+      qk[4] += -t4 * t7;
+      qk[5] += t4 * s2;
+      for (int i = 0; i < DG_NQA; ++i) x[(k + 1) * D.nq + a * DG_NQA + i] = qk[i];
     }
   }
 }

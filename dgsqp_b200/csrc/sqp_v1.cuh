@@ -67,7 +67,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
     W.Q.xq = at(0); W.Q.dv = at(1); W.Q.zv = at(2); W.Q.rv = at(3); W.Q.npv = at(4); W.Q.lam_act = at(5);
   }
   PLACE(W.Q.sl, m);
-  PLACE(W.B.part, (n > DG_MAX_THREADS ? n : DG_MAX_THREADS));
+  PLACE(W.B.part, (n > DG_PART_SZ ? n : DG_PART_SZ));
   { double* t; PLACE(t, (n + 1) / 2 + 1); W.Q.act = (int*)t; PLACE(t, (m + 1) / 2 + 1); W.Q.is_act = (int*)t; }
   const bool pool_ok = go == 0;                 // nothing of the pool fell back to global memory
   // ---- ARENA
@@ -120,7 +120,7 @@ DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l) {
   const Dims D = X.D; const EvalBuf E = X.W.E; DG_SH_EVAL(E);
   c.sync();
   c.lap(PH_OTHER);
-  game_rollout<SM>(c, *X.G, D, u, X.x0, E.x);
+  game_rollout<SM>(c, *X.G, D, u, X.x0, E.x, E.tmpS);
   c.sync();
   game_linearize<SM>(c, *X.G, D, u, E, true);
   c.sync();
@@ -144,7 +144,7 @@ DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l, bo
   const Dims D = X.D; const EvalBuf E = X.W.E; DG_SH_EVAL(E);
   c.sync();
   c.lap(PH_OTHER);
-  game_rollout<SM>(c, *X.G, D, u, X.x0, E.x);
+  game_rollout<SM>(c, *X.G, D, u, X.x0, E.x, E.tmpS);
   c.sync();
   game_linearize<SM>(c, *X.G, D, u, E, false);
   c.sync();
@@ -422,7 +422,7 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
   }
   // outputs: x_bar = evaluate_dynamics(u), costs f_J  (DGSQP.py:476-498)
   c.sync();
-  game_rollout<SM>(c, *X.G, D, S.u, X.x0, E.x);
+  game_rollout<SM>(c, *X.G, D, S.u, X.x0, E.x, E.tmpS);
   c.sync();
   DG_FOR(j, n) O.u[j] = S.u[j];
   DG_FOR(r, m) O.l[r] = S.l[r];

@@ -13,7 +13,7 @@ struct UnitArgs {
 };
 
 template <bool SM>
-__global__ void units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArgs A) {
+__global__ void __launch_bounds__(256, 1) units_kernel(const GameDesc* Gp, const SolverParams* Pp, UnitArgs A) {
   extern __shared__ double s_dyn[];
   Cta c;
   c.flip = 0;
