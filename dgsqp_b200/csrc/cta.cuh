@@ -63,7 +63,7 @@ struct Cta {
 #endif
 // CTA-wide scratch of the reductions (2 buffers x 160 doubles) and the phase counters: file-scope shared
 // variables, so no pointer has to be fetched from the (local-memory resident) Cta object
-__shared__ double dg_s_red[320];
+__shared__ __align__(16) double dg_s_red[320];
 __shared__ long long dg_s_ph[DG_NPHASE + 1];
 
 struct Cta {
@@ -93,6 +93,12 @@ struct Cta {
   __device__ __forceinline__ void syncwarp() { __syncwarp(); }
   // sum of the nwarps (<= 16) per-warp partials at b[0..]: fixed pairwise tree, identical in every thread
   __device__ __forceinline__ double tree16(const double* b) const {
+    if (nwarps() == 8) {
+      // the default CTA width: four 128-bit loads and a fixed pairwise tree
+      const double2 p0 = reinterpret_cast<const double2*>(b)[0], p1 = reinterpret_cast<const double2*>(b)[1];
+      const double2 p2 = reinterpret_cast<const double2*>(b)[2], p3 = reinterpret_cast<const double2*>(b)[3];
+      return ((p0.x + p0.y) + (p1.x + p1.y)) + ((p2.x + p2.y) + (p3.x + p3.y));
+    }
     double t[16];
 #pragma unroll
     for (int w = 0; w < 16; ++w) t[w] = w < nwarps() ? b[w] : 0.0;

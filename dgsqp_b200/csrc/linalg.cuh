@@ -144,9 +144,15 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_) {
 // touches shared memory.  Thread (i = tid & 127, g = tid >> 7) owns column i of the rows j = g, g+2, ... in
 // a[r] (j = g + 2r); the Householder vector / the rank-2 vectors are broadcast from shared memory in a parity-split
 // layout (element j at (j&1)*XS + (j>>1)) so that a thread fetches two of its rows' coefficients per 128-bit load.
-// Per step: partial products  sum_j A[j][i] u_j  (u = v / scale, u_off = alpha - beta)  ->  barrier  ->  p, v, p.v
-// (block sum)  ->  w = p - hk v  ->  barrier  ->  A -= v w' + w v' in registers, the next row (= next column, by
-// symmetry) and the next diagonal entry are peeled off on the fly  ->  block sum of the next column norm.
+// Per step k (off = k+1):
+//   row off is peeled out of the registers (uniform select)                       [needed twice below]
+//   partial products  sum_{j>=off} A[j][i] x_j  with the raw column x; the j = off term is corrected to
+//   u_off = alpha - beta  (u = v / scale)                                           -> barrier
+//   p = tau*scale*(sum), v, p.v (block sum), w = p - hk v                           -> barrier
+//   A -= v w' + w v' in registers; the next column = updated row off = row - (w + w_off v) needs no second peel
+//   block sum of the next column norm.
+// Rows that are already eliminated and padding rows (j >= n) need no masks: their entries of x are kept at zero, so
+// they add nothing to the products, and whatever the update writes into their registers is never used.
 // Same outputs as sym_tridiag: dg, od, od2, tau and the reflectors in W[k+2.., k].
 template <int RMAX, bool SM>
 DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
@@ -154,18 +160,21 @@ DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
   double* DG_RESTRICT W = B.matA;
   const int ld = B.ld;
   const int i = c.tid() & 127, g = c.tid() >> 7;
-  const int XS = (((n + 1) >> 1) + 1) & ~1;                       // even stride of the parity-split layout
+  const int XS = (((n + 1) >> 1) + 3) & ~3;                       // stride of the parity-split layout: a whole number of 4-row chunks
+  const int VS = 2 * XS;                                          // doubles per parity-split vector incl. zero padding (<= 2*RMAX)
   double* DG_RESTRICT part = B.part;                              // [2][128] partial products
-  double* DG_RESTRICT xs = B.part + 256;                          // u  (parity-split, 2*XS <= 256)
-  double* DG_RESTRICT pv = B.pv;                                  // v  (parity-split)
-  double* DG_RESTRICT wv = B.pv + (((3 * n) >> 1) + 1 & ~1);      // w  (parity-split; pv..pv+3n is one region)
+  double* DG_RESTRICT xs = B.part + 256;                          // x  (parity-split)
+  double* DG_RESTRICT pv = B.pv;                                  // v  (parity-split; pv .. pv+3n is one region)
+  double* DG_RESTRICT wv = B.pv + VS;                             // w  (parity-split)
 #define DG_PS(j) ((((j) & 1) * XS) + ((j) >> 1))
   const int r_end = (n - g + 1) >> 1;                             // rows owned: j = g + 2r < n
   const bool col_ok = i < n;
   double a[RMAX];
 #pragma unroll
   for (int r = 0; r < RMAX; ++r) { const int j = g + 2 * r; a[r] = (r < r_end && col_ok) ? W[j * ld + i] : 0.0; }
-  // row 0 -> u, |x[1:]|^2, first diagonal entry
+  DG_FOR(t, VS) { xs[t] = 0.0; pv[t] = 0.0; wv[t] = 0.0; }
+  c.sync();
+  // row 0 -> x, |x[1:]|^2, first diagonal entry
   double nrm = 0.0;
   if (g == 0 && col_ok) {
     if (i >= 1) xs[DG_PS(i)] = a[0];
@@ -184,77 +193,73 @@ DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
     }
     if (c.tid() == 0) { B.od[k] = beta; B.od2[k] = beta * beta; B.tau[k] = tauk; }
     const int r_first = (off - g + 1) >> 1;                       // first owned row with j >= off
-    const bool colact = col_ok && i >= off;
-    double vi = 0.0, wi = 0.0;
-    if (tauk != 0.0) {
-      const double amb = alpha - beta;
-      const double* DG_RESTRICT xg = xs + g * XS;
-      double acc0 = 0.0, acc1 = 0.0;
+    const int cb_first = r_first & ~3;
+    const bool own_off = g == (off & 1);                          // this thread's group holds row off, at r_first
+    // peel row off (pre-update) out of the registers
+    double rowv = 0.0;
+    if (own_off) {
 #pragma unroll
       for (int cb = 0; cb < RMAX; cb += 4) {
-        if (cb + 4 > r_first && cb < r_end) {
-          const double2 x01 = *reinterpret_cast<const double2*>(xg + cb);
-          const double2 x23 = *reinterpret_cast<const double2*>(xg + cb + 2);
-          const double xq[4] = {x01.x, x01.y, x23.x, x23.y};
+        if (cb == cb_first) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int r = cb + q;
-            {
-              const int j = g + 2 * r;
-              const double uv = j == off ? amb : xq[q];
-              if (r >= r_first && r < r_end) { if (q & 1) acc1 += a[r] * uv; else acc0 += a[r] * uv; }
-            }
-          }
+          for (int q = 0; q < 4; ++q) if (cb + q < RMAX && cb + q == r_first) rowv = a[cb + q];
         }
       }
-      part[g * 128 + i] = acc0 + acc1;
+    }
+    double vi = 0.0, wi = 0.0, woff = 0.0;
+    if (tauk != 0.0) {
+      const double* DG_RESTRICT xg = xs + g * XS;
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+      for (int cb = 0; cb < RMAX; cb += 4) {
+        if (cb >= cb_first && cb < r_end) {
+          const double2 x01 = *reinterpret_cast<const double2*>(xg + cb);
+          const double2 x23 = *reinterpret_cast<const double2*>(xg + cb + 2);
+          acc0 += a[cb + 0] * x01.x; acc1 += a[cb + 1] * x01.y; acc2 += a[cb + 2] * x23.x; acc3 += a[cb + 3] * x23.y;
+        }
+      }
+      double acc = (acc0 + acc1) + (acc2 + acc3);
+      if (own_off) acc -= rowv * beta;                             // u_off = alpha - beta instead of alpha
+      part[g * 128 + i] = acc;
       c.sync();
       double pdot = 0.0, pi = 0.0;
-      if (g == 0 && colact) {
+      if (c.tid() == 0) xs[DG_PS(off)] = 0.0;                       // alpha has been consumed: dead entries of x must read as 0
+      if (g == 0 && col_ok && i >= off) {
         pi = (part[i] + part[128 + i]) * (tauk * scale);
         vi = i == off ? 1.0 : xs[DG_PS(i)] * scale;
         pv[DG_PS(i)] = vi;
         pdot = pi * vi;
       }
       const double hk = 0.5 * tauk * c.sum(pdot);
-      if (g == 0 && colact) {
+      if (g == 0 && col_ok && i >= off) {
         wv[DG_PS(i)] = pi - hk * vi;
         if (i > off) W[i * ld + k] = vi;                           // keep the reflector
       }
       c.sync();
-      if (colact) { vi = pv[DG_PS(i)]; wi = wv[DG_PS(i)]; }
-    }
-    // rank-2 update of the owned rows j >= off; row off (= the next column) and the next diagonal entry peel off
-    nrm = 0.0;
-    {
+      if (col_ok) { vi = pv[DG_PS(i)]; wi = wv[DG_PS(i)]; }
+      woff = wv[DG_PS(off)];
+      // rank-2 update of the owned rows j >= off
       const double* DG_RESTRICT pg = pv + g * XS;
       const double* DG_RESTRICT wg = wv + g * XS;
 #pragma unroll
       for (int cb = 0; cb < RMAX; cb += 4) {
-        if (cb + 4 > r_first && cb < r_end) {
-          double vq[4] = {0.0, 0.0, 0.0, 0.0}, wq[4] = {0.0, 0.0, 0.0, 0.0};
-          if (tauk != 0.0) {
-            const double2 v01 = *reinterpret_cast<const double2*>(pg + cb), v23 = *reinterpret_cast<const double2*>(pg + cb + 2);
-            const double2 w01 = *reinterpret_cast<const double2*>(wg + cb), w23 = *reinterpret_cast<const double2*>(wg + cb + 2);
-            vq[0] = v01.x; vq[1] = v01.y; vq[2] = v23.x; vq[3] = v23.y;
-            wq[0] = w01.x; wq[1] = w01.y; wq[2] = w23.x; wq[3] = w23.y;
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int r = cb + q;
-            {
-              const int j = g + 2 * r;
-              if (r >= r_first && r < r_end && colact) {
-                if (tauk != 0.0) a[r] -= vq[q] * wi + wq[q] * vi;
-                if (j == off) {
-                  if (i >= off + 1) xs[DG_PS(i)] = a[r];
-                  if (i >= off + 2) nrm += a[r] * a[r];
-                  if (i == off) B.dg[off] = a[r];
-                }
-              }
-            }
-          }
+        if (cb >= cb_first && cb < r_end) {
+          const double2 v01 = *reinterpret_cast<const double2*>(pg + cb), v23 = *reinterpret_cast<const double2*>(pg + cb + 2);
+          const double2 w01 = *reinterpret_cast<const double2*>(wg + cb), w23 = *reinterpret_cast<const double2*>(wg + cb + 2);
+          a[cb + 0] -= v01.x * wi + w01.x * vi; a[cb + 1] -= v01.y * wi + w01.y * vi;
+          a[cb + 2] -= v23.x * wi + w23.x * vi; a[cb + 3] -= v23.y * wi + w23.y * vi;
         }
+      }
+    } else c.sync();                                               // (rare) nothing to annihilate: order the x reads before the writes below
+    // next column = updated row off  (v_off = 1)
+    nrm = 0.0;
+    if (tauk == 0.0 && c.tid() == 0) xs[DG_PS(off)] = 0.0;
+    if (own_off && col_ok && i >= off) {
+      const double xnew = tauk != 0.0 ? rowv - (wi + woff * vi) : rowv;
+      if (i == off) B.dg[off] = xnew;
+      else {
+        xs[DG_PS(i)] = xnew;
+        if (i >= off + 2) nrm = xnew * xnew;
       }
     }
     xn2 = c.sum(nrm);
@@ -584,10 +589,10 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, doubl
         double* DG_RESTRICT col = Hm + j;
         for (int i = j + gi; i < n; i += groups) {
           const double* DG_RESTRICT r0 = sp + (i - k0) * NB;
-          double c0 = col[i * ld];
+          double s0 = 0.0, s1 = 0.0;                   // two chains instead of one 8-deep dependent one
 #pragma unroll
-          for (int t = 0; t < NB; ++t) c0 -= r0[t] * lj[t];
-          col[i * ld] = c0;
+          for (int t = 0; t < NB; t += 2) { s0 += r0[t] * lj[t]; s1 += r0[t + 1] * lj[t + 1]; }
+          col[i * ld] -= s0 + s1;
         }
       }
     }

@@ -163,10 +163,13 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
           }
         }
         if (c.warp() == c.nwarps() - 1) {
-          for (int i = c.lane(); i < iq; i += c.wsz) Q.rv[i] = Q.dv[i];
+          // reciprocal pivots first (independent divisions), so that the serial chain below only multiplies;
+          // they are parked in the tail of zv's partial-sum scratch (part[256..], beyond the G*cw <= 256 partial sums)
+          double* DG_RESTRICT rinv = B.part + 256;
+          for (int i = c.lane(); i < iq; i += c.wsz) { Q.rv[i] = Q.dv[i]; rinv[i] = 1.0 / Rm[i * ld + i]; }
           c.syncwarp();
           for (int i = iq - 1; i >= 0; --i) {
-            const double ri = Q.rv[i] / Rm[i * ld + i];
+            const double ri = Q.rv[i] * rinv[i];
             c.syncwarp();
             if (c.lane() == 0) Q.rv[i] = ri;
             for (int j = c.lane(); j < i; j += c.wsz) Q.rv[j] -= Rm[j * ld + i] * ri;

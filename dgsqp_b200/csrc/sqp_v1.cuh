@@ -72,7 +72,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   const bool pool_ok = go == 0;                 // nothing of the pool fell back to global memory
   // ---- ARENA
   const size_t ev_a = rnd(N * M * 48) + rnd((M + 1) * (N + 1) * nq) + rnd((M + 1) * N * M * 15) + rnd(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq) +
-                      rnd((M + 1) * nq * n) + rnd(N * M * 90);
+                      rnd((M + 1) * nq * n) + rnd(N * M * 90) + rnd(m);
   const size_t mats = 2 * rnd(n * ld);
   const size_t arena = ev_a > mats ? ev_a : mats;
   double* ar = nullptr;
@@ -81,7 +81,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
     size_t o = 0;
     auto sub = [&](size_t cnt) { double* r = ar ? ar + o : nullptr; o += rnd(cnt); return r; };
     W.E.AB = sub(N * M * 48); W.E.cst = sub((M + 1) * (N + 1) * nq); W.E.Hc = sub((M + 1) * N * M * 15);
-    W.E.Vbuf = sub(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq); W.E.Wrow = sub((M + 1) * nq * n); W.E.T2 = sub(N * M * 90);
+    W.E.Vbuf = sub(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq); W.E.Wrow = sub((M + 1) * nq * n); W.E.T2 = sub(N * M * 90); W.E.lbuf = sub(m);
     W.B.ld = (int)ld; W.B.matA = ar; W.B.matB = ar ? ar + rnd(n * ld) : nullptr;
   }
   // ---- SENS
@@ -116,10 +116,14 @@ struct SolveCtx {
 
 // _evaluate(u, l, hessian=True)
 template <bool SM>
-DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l) {
+DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l_in) {
   const Dims D = X.D; const EvalBuf E = X.W.E; DG_SH_EVAL(E);
   c.sync();
   c.lap(PH_OTHER);
+  // the multipliers are walked by serial chains (costates, Hessian DP): stage them in the arena (the candidate /
+  // watchdog iterates live in global memory)
+  { double* lb = E.lbuf; DG_FOR(r, D.m) lb[r] = l_in[r]; }
+  const double* l = E.lbuf;
   game_rollout<SM>(c, *X.G, D, u, X.x0, E.x, E.tmpS);
   c.sync();
   game_linearize<SM>(c, *X.G, D, u, E, true);
@@ -140,10 +144,12 @@ DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l) {
 
 // _evaluate(u, l, hessian=False): x, g, q, G'l only (sensitivities optional)
 template <bool SM>
-DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l, bool with_sens) {
+DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l_in, bool with_sens) {
   const Dims D = X.D; const EvalBuf E = X.W.E; DG_SH_EVAL(E);
   c.sync();
   c.lap(PH_OTHER);
+  { double* lb = E.lbuf; DG_FOR(r, D.m) lb[r] = l_in[r]; }
+  const double* l = E.lbuf;
   game_rollout<SM>(c, *X.G, D, u, X.x0, E.x, E.tmpS);
   c.sync();
   game_linearize<SM>(c, *X.G, D, u, E, false);
