@@ -140,38 +140,85 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_) {
 }
 
 #ifndef DG_HOSTSIM
-// Register-resident variant of sym_tridiag for 256-thread CTAs and n <= 2*RMAX <= 128: the trailing matrix never
-// touches shared memory.  Thread (i = tid & 127, g = tid >> 7) owns column i of the rows j = g, g+2, ... in
-// a[r] (j = g + 2r); the Householder vector / the rank-2 vectors are broadcast from shared memory in a parity-split
-// layout (element j at (j&1)*XS + (j>>1)) so that a thread fetches two of its rows' coefficients per 128-bit load.
+// ---- register-resident tridiagonalisation (256-thread CTAs, n <= 2*RMAX <= 128) --------------------------------
+// Thread (i = tid & 127, g = tid >> 7) owns column i of the rows j = g, g+2, ... in a[r] (j = g + 2r): the trailing
+// matrix never touches shared memory.  The Householder vector / the rank-2 vectors are broadcast from shared
+// memory in a parity-split layout (element j at (j&1)*RMAX + (j>>1)) so that a thread fetches two of its rows'
+// coefficients per 128-bit load.  The live part of a thread's rows starts at r_first = ceil((off - g) / 2), which
+// moves by one 4-row chunk every 8 steps: the three register sweeps of a step (peel, products, update) are
+// compiled once per chunk offset CB and selected by ONE CTA-uniform switch on (k+1)>>3, so the sweeps themselves
+// are branch-free straight-line code (per-chunk guards cost more than the arithmetic they skipped).
+// Rows that are already eliminated and padding rows (j >= n) need no masks: their entries of x are kept at zero, so
+// they add nothing to the products, and whatever the update writes into their registers is never used.
+template <int RMAX, int CB>
+DG_DEV void tri_sweep_products(const double (&a)[RMAX], const double* DG_RESTRICT xg, double& acc) {
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+  for (int cb = CB; cb < RMAX; cb += 4) {
+    const double2 x01 = *reinterpret_cast<const double2*>(xg + cb);
+    const double2 x23 = *reinterpret_cast<const double2*>(xg + cb + 2);
+    acc0 += a[cb + 0] * x01.x; acc1 += a[cb + 1] * x01.y; acc2 += a[cb + 2] * x23.x; acc3 += a[cb + 3] * x23.y;
+  }
+  acc = (acc0 + acc1) + (acc2 + acc3);
+}
+template <int RMAX, int CB>
+DG_DEV void tri_sweep_update(double (&a)[RMAX], const double* DG_RESTRICT pg, const double* DG_RESTRICT wg, double vi, double wi) {
+  const double nvi = -vi, nwi = -wi;
+#pragma unroll
+  for (int cb = CB; cb < RMAX; cb += 4) {
+    const double2 v01 = *reinterpret_cast<const double2*>(pg + cb), v23 = *reinterpret_cast<const double2*>(pg + cb + 2);
+    const double2 w01 = *reinterpret_cast<const double2*>(wg + cb), w23 = *reinterpret_cast<const double2*>(wg + cb + 2);
+    // two fused multiply-adds per entry (nvi = -v_i, nwi = -w_i)
+    a[cb + 0] = fma(v01.x, nwi, fma(w01.x, nvi, a[cb + 0])); a[cb + 1] = fma(v01.y, nwi, fma(w01.y, nvi, a[cb + 1]));
+    a[cb + 2] = fma(v23.x, nwi, fma(w23.x, nvi, a[cb + 2])); a[cb + 3] = fma(v23.y, nwi, fma(w23.y, nvi, a[cb + 3]));
+  }
+}
+// a[CB + d], d in 0..4 (the row `off` of this thread's parity sits at r_first, within 4 rows of the chunk offset)
+template <int RMAX, int CB>
+DG_DEV double tri_peel(const double (&a)[RMAX], int d) {
+  double v = a[CB];
+#pragma unroll
+  for (int q = 1; q <= 4; ++q) if (CB + q < RMAX) v = d == q ? a[CB + q < RMAX ? CB + q : 0] : v;
+  return v;
+}
+#define DG_TRI_CASE(m, ...) case m: if constexpr (4 * m < RMAX) { constexpr int CB = 4 * m; __VA_ARGS__; } break;
+#define DG_TRI_SWITCH(seg, ...) switch (seg) { \
+  DG_TRI_CASE(0, __VA_ARGS__) DG_TRI_CASE(1, __VA_ARGS__) DG_TRI_CASE(2, __VA_ARGS__) DG_TRI_CASE(3, __VA_ARGS__) DG_TRI_CASE(4, __VA_ARGS__) DG_TRI_CASE(5, __VA_ARGS__) \
+  DG_TRI_CASE(6, __VA_ARGS__) DG_TRI_CASE(7, __VA_ARGS__) DG_TRI_CASE(8, __VA_ARGS__) DG_TRI_CASE(9, __VA_ARGS__) DG_TRI_CASE(10, __VA_ARGS__) DG_TRI_CASE(11, __VA_ARGS__) \
+  DG_TRI_CASE(12, __VA_ARGS__) DG_TRI_CASE(13, __VA_ARGS__) DG_TRI_CASE(14, __VA_ARGS__) DG_TRI_CASE(15, __VA_ARGS__) default: break; }
+
 // Per step k (off = k+1):
-//   row off is peeled out of the registers (uniform select)                       [needed twice below]
-//   partial products  sum_{j>=off} A[j][i] x_j  with the raw column x; the j = off term is corrected to
+//   row off is peeled out of the registers                                          [needed twice below]
+//   partial products  sum_j A[j][i] x_j  with the raw column x; the j = off term is corrected to
 //   u_off = alpha - beta  (u = v / scale)                                           -> barrier
 //   p = tau*scale*(sum), v, p.v (block sum), w = p - hk v                           -> barrier
 //   A -= v w' + w v' in registers; the next column = updated row off = row - (w + w_off v) needs no second peel
 //   block sum of the next column norm.
-// Rows that are already eliminated and padding rows (j >= n) need no masks: their entries of x are kept at zero, so
-// they add nothing to the products, and whatever the update writes into their registers is never used.
 // Same outputs as sym_tridiag: dg, od, od2, tau and the reflectors in W[k+2.., k].
+// Needs 4*RMAX <= 3n doubles behind B.pv (pv .. pv+3n is one region) and 256 + 2*RMAX <= DG_PART_SZ.
 template <int RMAX, bool SM>
 DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
+  static_assert(RMAX % 4 == 0 && RMAX <= 64, "RMAX: multiple of the 4-row chunk, at most 64 rows per thread");
   const LinBuf B = B_; DG_SH_LIN_T(B);
   double* DG_RESTRICT W = B.matA;
   const int ld = B.ld;
   const int i = c.tid() & 127, g = c.tid() >> 7;
-  const int XS = (((n + 1) >> 1) + 3) & ~3;                       // stride of the parity-split layout: a whole number of 4-row chunks
-  const int VS = 2 * XS;                                          // doubles per parity-split vector incl. zero padding (<= 2*RMAX)
+  constexpr int XS = RMAX;                                        // stride of the parity-split layout
+  constexpr int VS = 2 * XS;                                      // doubles per parity-split vector incl. zero padding
   double* DG_RESTRICT part = B.part;                              // [2][128] partial products
   double* DG_RESTRICT xs = B.part + 256;                          // x  (parity-split)
-  double* DG_RESTRICT pv = B.pv;                                  // v  (parity-split; pv .. pv+3n is one region)
+  double* DG_RESTRICT pv = B.pv;                                  // v  (parity-split)
   double* DG_RESTRICT wv = B.pv + VS;                             // w  (parity-split)
 #define DG_PS(j) ((((j) & 1) * XS) + ((j) >> 1))
   const int r_end = (n - g + 1) >> 1;                             // rows owned: j = g + 2r < n
   const bool col_ok = i < n;
   double a[RMAX];
 #pragma unroll
-  for (int r = 0; r < RMAX; ++r) { const int j = g + 2 * r; a[r] = (r < r_end && col_ok) ? W[j * ld + i] : 0.0; }
+  for (int r = 0; r < RMAX; ++r) a[r] = 0.0;
+  if (col_ok) {
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) if (r < r_end) a[r] = W[(g + 2 * r) * ld + i];
+  }
   DG_FOR(t, VS) { xs[t] = 0.0; pv[t] = 0.0; wv[t] = 0.0; }
   c.sync();
   // row 0 -> x, |x[1:]|^2, first diagonal entry
@@ -182,8 +229,12 @@ DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
     if (i == 0) B.dg[0] = a[0];
   }
   double xn2 = c.sum(nrm);
+  const double* DG_RESTRICT xg = xs + g * XS;
+  const double* DG_RESTRICT pg = pv + g * XS;
+  const double* DG_RESTRICT wg = wv + g * XS;
   for (int k = 0; k + 1 < n; ++k) {
     const int off = k + 1;
+    const int seg = off >> 3;                                     // CTA-uniform chunk offset CB = 4*seg <= r_first
     const double alpha = xs[DG_PS(off)];
     double tauk = 0.0, beta = alpha, scale = 0.0;
     if (xn2 > 0.0) {
@@ -193,32 +244,14 @@ DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
     }
     if (c.tid() == 0) { B.od[k] = beta; B.od2[k] = beta * beta; B.tau[k] = tauk; }
     const int r_first = (off - g + 1) >> 1;                       // first owned row with j >= off
-    const int cb_first = r_first & ~3;
     const bool own_off = g == (off & 1);                          // this thread's group holds row off, at r_first
     // peel row off (pre-update) out of the registers
     double rowv = 0.0;
-    if (own_off) {
-#pragma unroll
-      for (int cb = 0; cb < RMAX; cb += 4) {
-        if (cb == cb_first) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) if (cb + q < RMAX && cb + q == r_first) rowv = a[cb + q];
-        }
-      }
-    }
+    DG_TRI_SWITCH(seg, rowv = tri_peel<RMAX, CB>(a, r_first - CB))
     double vi = 0.0, wi = 0.0, woff = 0.0;
     if (tauk != 0.0) {
-      const double* DG_RESTRICT xg = xs + g * XS;
-      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll
-      for (int cb = 0; cb < RMAX; cb += 4) {
-        if (cb >= cb_first && cb < r_end) {
-          const double2 x01 = *reinterpret_cast<const double2*>(xg + cb);
-          const double2 x23 = *reinterpret_cast<const double2*>(xg + cb + 2);
-          acc0 += a[cb + 0] * x01.x; acc1 += a[cb + 1] * x01.y; acc2 += a[cb + 2] * x23.x; acc3 += a[cb + 3] * x23.y;
-        }
-      }
-      double acc = (acc0 + acc1) + (acc2 + acc3);
+      double acc = 0.0;
+      DG_TRI_SWITCH(seg, (tri_sweep_products<RMAX, CB>(a, xg, acc)))
       if (own_off) acc -= rowv * beta;                             // u_off = alpha - beta instead of alpha
       part[g * 128 + i] = acc;
       c.sync();
@@ -238,18 +271,7 @@ DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
       c.sync();
       if (col_ok) { vi = pv[DG_PS(i)]; wi = wv[DG_PS(i)]; }
       woff = wv[DG_PS(off)];
-      // rank-2 update of the owned rows j >= off
-      const double* DG_RESTRICT pg = pv + g * XS;
-      const double* DG_RESTRICT wg = wv + g * XS;
-#pragma unroll
-      for (int cb = 0; cb < RMAX; cb += 4) {
-        if (cb >= cb_first && cb < r_end) {
-          const double2 v01 = *reinterpret_cast<const double2*>(pg + cb), v23 = *reinterpret_cast<const double2*>(pg + cb + 2);
-          const double2 w01 = *reinterpret_cast<const double2*>(wg + cb), w23 = *reinterpret_cast<const double2*>(wg + cb + 2);
-          a[cb + 0] -= v01.x * wi + w01.x * vi; a[cb + 1] -= v01.y * wi + w01.y * vi;
-          a[cb + 2] -= v23.x * wi + w23.x * vi; a[cb + 3] -= v23.y * wi + w23.y * vi;
-        }
-      }
+      DG_TRI_SWITCH(seg, (tri_sweep_update<RMAX, CB>(a, pg, wg, vi, wi)))
     } else c.sync();                                               // (rare) nothing to annihilate: order the x reads before the writes below
     // next column = updated row off  (v_off = 1)
     nrm = 0.0;
@@ -267,6 +289,17 @@ DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
   if (c.tid() == 0) { B.od[n - 1] = 0.0; B.od2[n - 1] = 0.0; }
   c.sync();
 #undef DG_PS
+}
+
+// picks the instantiation whose scratch fits: 4*RMAX <= 3n and n <= 2*RMAX
+template <bool SM>
+DG_DEV bool sym_tridiag_regs_dispatch(Cta& c, int n, const LinBuf& B) {
+  if (!SM || c.nt() != 256) return false;
+  if (n >= 27 && n <= 40) { sym_tridiag_regs<20, SM>(c, n, B); return true; }
+  if (n >= 43 && n <= 64) { sym_tridiag_regs<32, SM>(c, n, B); return true; }
+  if (n >= 70 && n <= 104) { sym_tridiag_regs<52, SM>(c, n, B); return true; }
+  if (n >= 105 && n <= 128) { sym_tridiag_regs<64, SM>(c, n, B); return true; }
+  return false;
 }
 #endif
 
@@ -408,9 +441,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
     }
     c.sync();
 #ifndef DG_HOSTSIM
-    if (SM && c.nt() == 256 && n <= 104 && n >= 8) sym_tridiag_regs<52, SM>(c, n, B);
-    else if (SM && c.nt() == 256 && n <= 128 && n >= 8) sym_tridiag_regs<64, SM>(c, n, B);
-    else
+    if (!sym_tridiag_regs_dispatch<SM>(c, n, B))
 #endif
     sym_tridiag<SM>(c, n, B);
     c.lap(PH_PD_TRIDIAG);
