@@ -37,7 +37,18 @@ class ParamsStruct(C.Structure):
                 ("mu_vio_thresh", C.c_double)]
 
 
-EXPORTS = ["dgsqp_create", "dgsqp_destroy", "dgsqp_dims", "dgsqp_solve_batch", "dgsqp_solve_batch_async",
+class ParamsV2Struct(C.Structure):
+    """dgsqp_v2_params (include/dgsqp_b200.h) <- DGSQPV2Params (DGSQP/solvers/solver_types.py:130-174)."""
+    _fields_ = [("reg", C.c_double), ("reg_decay", C.c_double), ("p_tol", C.c_double), ("d_tol", C.c_double),
+                ("beta", C.c_double), ("tau", C.c_double),
+                ("line_search_iters", C.c_int32), ("sqp_iters", C.c_int32),
+                ("nms", C.c_int32), ("nms_frequency", C.c_int32), ("nms_memory_size", C.c_int32),
+                ("merit_function", C.c_int32), ("has_merit_parameter", C.c_int32), ("merit_parameter", C.c_double),
+                ("merit_decrease", C.c_double), ("merit_decrease_condition", C.c_int32), ("delta_decay", C.c_double),
+                ("mu_vio_thresh", C.c_double)]
+
+
+EXPORTS = ["dgsqp_create", "dgsqp_create_v2", "dgsqp_destroy", "dgsqp_dims", "dgsqp_solve_batch", "dgsqp_solve_batch_async",
            "dgsqp_last_diag", "dgsqp_phase_count", "dgsqp_last_phase_cycles", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_memory_plan", "dgsqp_set_smem_limit", "dgsqp_last_error", "dgsqp_version"]
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "libdgsqp_b200.so"
@@ -62,6 +73,8 @@ def load():
     dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
     lib.dgsqp_create.argtypes = [C.POINTER(RacingGameStruct), C.POINTER(ParamsStruct), C.c_int, C.POINTER(vp)]
     lib.dgsqp_create.restype = C.c_int
+    lib.dgsqp_create_v2.argtypes = [C.POINTER(RacingGameStruct), C.POINTER(ParamsV2Struct), C.c_int, C.POINTER(vp)]
+    lib.dgsqp_create_v2.restype = C.c_int
     lib.dgsqp_destroy.argtypes = [vp]
     lib.dgsqp_destroy.restype = C.c_int
     lib.dgsqp_dims.argtypes = [vp, ip]

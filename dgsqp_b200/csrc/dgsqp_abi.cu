@@ -11,7 +11,7 @@
 #include <string>
 #include <new>
 
-#include "sqp_v1.cuh"
+#include "sqp_v2.cuh"
 #include "host_setup.h"
 
 #define DGSQP_VERSION_STR "dgsqp_b200 0.1.0 (sm_100a)"
@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(DG_MAX_THREADS, 1) dgsqp_solve_kernel(const Ga
     O.diag = A.diag ? A.diag + (size_t)inst * DG_NDIAG : nullptr;
     O.l_init = nullptr;
     if (threadIdx.x == 0) { for (int i = 0; i < DG_NPHASE; ++i) dg_s_ph[i] = 0; dg_s_ph[DG_NPHASE] = clock64(); }
-    sqp_solve_v1<SM>(c, X, A.u_ws + (size_t)inst * D.n, A.l_ws ? A.l_ws + (size_t)inst * D.m : nullptr, O);
+    if (sP.policy == 2) sqp_solve_v2<SM>(c, X, A.u_ws + (size_t)inst * D.n, A.l_ws ? A.l_ws + (size_t)inst * D.m : nullptr, O);
+    else sqp_solve_v1<SM>(c, X, A.u_ws + (size_t)inst * D.n, A.l_ws ? A.l_ws + (size_t)inst * D.m : nullptr, O);
     c.lap(PH_OTHER);
     if (threadIdx.x == 0 && A.phase) for (int i = 0; i < DG_NPHASE; ++i) A.phase[(size_t)inst * DG_NPHASE + i] = dg_s_ph[i];
   }
@@ -170,13 +171,13 @@ const char* dgsqp_last_error(void) { return g_last_error.c_str(); }
 const char* dgsqp_version(void) { return DGSQP_VERSION_STR; }
 int64_t dgsqp_kernel_launches(void) { return (int64_t)g_launches.load(); }
 
-int dgsqp_create(const dgsqp_racing_game* game, const dgsqp_params* params, int device, dgsqp_handle** out) {
+static int create_common(const dgsqp_racing_game* game, const dgsqp_params* params, const dgsqp_v2_params* params2, int device, dgsqp_handle** out) {
   if (!out) return set_err(DGSQP_EINVAL, "out is NULL");
   *out = nullptr;
   dgsqp_handle* h = new (std::nothrow) dgsqp_handle();
   if (!h) return set_err(DGSQP_ENOMEM, "host allocation failed");
   if (dg_fill_game(game, &h->G) != 0) { delete h; return set_err(DGSQP_EINVAL, "invalid racing game descriptor"); }
-  if (dg_fill_params(params, &h->P) != 0) { delete h; return set_err(DGSQP_EINVAL, "invalid solver parameters"); }
+  if ((params2 ? dg_fill_params_v2(params2, &h->P) : dg_fill_params(params, &h->P)) != 0) { delete h; return set_err(DGSQP_EINVAL, "invalid solver parameters"); }
   h->D = make_dims(h->G.M, h->G.N);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -203,6 +204,15 @@ int dgsqp_create(const dgsqp_racing_game* game, const dgsqp_params* params, int 
   if (rc != 0) { dgsqp_destroy(h); return rc; }
   *out = h;
   return DGSQP_OK;
+}
+
+int dgsqp_create(const dgsqp_racing_game* game, const dgsqp_params* params, int device, dgsqp_handle** out) {
+  return create_common(game, params, nullptr, device, out);
+}
+
+int dgsqp_create_v2(const dgsqp_racing_game* game, const dgsqp_v2_params* params, int device, dgsqp_handle** out) {
+  if (!params) return set_err(DGSQP_EINVAL, "NULL parameters");
+  return create_common(game, nullptr, params, device, out);
 }
 
 int dgsqp_destroy(dgsqp_handle* h) {

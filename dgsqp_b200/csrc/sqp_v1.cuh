@@ -18,6 +18,9 @@ struct SolverParams {
   double mu_vio_thresh;    // _get_mu's `thresh` (DGSQP.py:560); see DESIGN.md deviation D2
   double dbg_l0_perturb;   // test hook (sensitivity studies): relative perturbation of the dual initialisation; 0 in production
   int line_search_iters, sqp_iters, nonmono_ls, merit_l1, conv_approx, rel_tol_req, t_hat;
+  // v2 step policy (DGSQPV2Params, DGSQP_v2.py:55-230); policy = 1: v1 (sqp_v1.cuh), 2: v2 (sqp_v2.cuh)
+  int policy, nms, nms_frequency, nms_memory, armijo, has_merit_parameter;
+  double reg_decay, sigma, gamma, merit_parameter;
 };
 
 struct SqpBuf {
@@ -27,6 +30,8 @@ struct SqpBuf {
   double *u_c, *l_c;                 // candidate point
   double *Gdu, *tn, *tn2;
   double* up;                        // nu (zeros: v1 resets u_prev every solve, DGSQP.py:305)
+  // v2 only: iterate at the start of the running iteration, record of the last appended iteration
+  double *c_u, *c_l, *r_u, *r_du, *r_l, *r_dl, *r_s, *r_ds;
 };
 
 struct Workspace { EvalBuf E; LinBuf B; QpBuf Q; LsqrBuf L; SqpBuf S; };
@@ -96,6 +101,8 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   GTAKE(W.L.u, m); GTAKE(W.L.v, m); GTAKE(W.L.w, m); GTAKE(W.L.x, m); GTAKE(W.L.tn, n); GTAKE(W.L.tm, m);
   GTAKE(W.S.u_im1, n); GTAKE(W.S.l_im1, m);
   GTAKE(W.S.u_t, n); GTAKE(W.S.l_t, m); GTAKE(W.S.du_t, n); GTAKE(W.S.dl_t, m); GTAKE(W.S.s_t, m); GTAKE(W.S.ds_t, m);
+  GTAKE(W.S.c_u, n); GTAKE(W.S.c_l, m); GTAKE(W.S.r_u, n); GTAKE(W.S.r_du, n); GTAKE(W.S.r_l, m); GTAKE(W.S.r_dl, m);
+  GTAKE(W.S.r_s, m); GTAKE(W.S.r_ds, m);
 #undef GTAKE
 #undef STAKE
 #undef PLACE

@@ -16,7 +16,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import _abi
-from .games import RacingGame, params_to_struct, NQA, NUA
+from .games import RacingGame, params_to_struct, params_v2_to_struct, NQA, NUA
 from .solver_types import DGSQPParams, DGSQPV2Params
 from .types import VehicleState, VehiclePrediction
 
@@ -43,8 +43,7 @@ class DGSQP:
     def __init__(self, game: RacingGame, params: DGSQPParams = None, print_method=print, device: int = 0):
         if params is None:
             params = DGSQPParams()
-        if isinstance(params, DGSQPV2Params):
-            raise NotImplementedError("the v2 step policy (DGSQPV2Params) is not implemented yet; use DGSQPParams")
+        self.v2 = isinstance(params, DGSQPV2Params)      # step policy of DGSQP_v2.py instead of DGSQP.py
         if params.N != game.N:
             raise ValueError("params.N = %i but the game was built for N = %i" % (params.N, game.N))
         if params.qp_solver != "osqp" or params.qp_interface != "casadi":
@@ -62,9 +61,14 @@ class DGSQP:
         self.solver_name = params.solver_name
 
         self._lib = _abi.load()
-        gs, ps = game.to_struct(), params_to_struct(params)
+        gs = game.to_struct()
         self._h = C.c_void_p()
-        _abi.check(self._lib.dgsqp_create(C.byref(gs), C.byref(ps), int(device), C.byref(self._h)))
+        if self.v2:
+            ps = params_v2_to_struct(params)
+            _abi.check(self._lib.dgsqp_create_v2(C.byref(gs), C.byref(ps), int(device), C.byref(self._h)))
+        else:
+            ps = params_to_struct(params)
+            _abi.check(self._lib.dgsqp_create(C.byref(gs), C.byref(ps), int(device), C.byref(self._h)))
         dims = (C.c_int32 * 4)()
         _abi.check(self._lib.dgsqp_dims(self._h, dims))
         assert (dims[0], dims[1], dims[2], dims[3]) == (game.n_q, game.n_u, game.n, game.m)

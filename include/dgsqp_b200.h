@@ -81,12 +81,35 @@ typedef struct {
   double mu_vio_thresh;
 } dgsqp_params;
 
+/* Mirrors DGSQPV2Params (DGSQP/solvers/solver_types.py:130-174): the v2 step policy of DGSQP/solvers/DGSQP_v2.py
+ * (decaying regularisation, relaxed d-steps inside a shrinking radius, m-steps against a merit memory with
+ * checkpoint reload, max_it counted in m-steps).  Constants the reference hard-codes (rel_tol_req = 10,
+ * initial radius factor 20, eigenvalue floor 1e-9, divergence at 1e10) are hard-coded here too. */
+typedef struct {
+  double reg, reg_decay;
+  double p_tol, d_tol;
+  double beta, tau;
+  int32_t line_search_iters;
+  int32_t sqp_iters;                /* counted in m-steps (DGSQP_v2.py:407) */
+  int32_t nms, nms_frequency, nms_memory_size;   /* memory size 1..16 */
+  int32_t merit_function;           /* 0 = 'stat_l1'; 'sum_obj_l1' is not supported (needs the gradient of the summed costs) */
+  int32_t has_merit_parameter;      /* 0: mu from _get_mu (:683-707), 1: constant merit_parameter */
+  double merit_parameter;
+  double merit_decrease;            /* sigma */
+  int32_t merit_decrease_condition; /* 0 = 'armijo', 1 = 'max' */
+  double delta_decay;               /* gamma */
+  double mu_vio_thresh;             /* see dgsqp_params */
+} dgsqp_v2_params;
+
 typedef struct dgsqp_handle dgsqp_handle;
 
 /* Builds the device-side solver for one game (the analogue of DGSQP.__init__/_build_solver,
  * DGSQP.py:26-230,587-979).  device = CUDA ordinal.  Fails with DGSQP_ECUDA when no GPU is usable:
  * there is no CPU fallback. */
 int dgsqp_create(const dgsqp_racing_game* game, const dgsqp_params* params, int device, dgsqp_handle** out);
+/* Same for the v2 solver class (DGSQP_v2.py:55-230); dgsqp_solve_batch then runs the v2 policy.  v2 keeps u_prev
+ * between calls (:328); the batched entry point uses u_prev = 0 like the Monte-Carlo drivers do. */
+int dgsqp_create_v2(const dgsqp_racing_game* game, const dgsqp_v2_params* params, int device, dgsqp_handle** out);
 int dgsqp_destroy(dgsqp_handle* h);
 
 /* dims[0..3] = n_q (joint state), n_u (joint input), n = N*n_u, m = number of constraint rows */

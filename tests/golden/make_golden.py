@@ -18,13 +18,14 @@ from oracle.track import chicane_track, curve_track          # noqa: E402
 from oracle.racing_game import RacingGame                    # noqa: E402
 from oracle.sampler import sample_head_to_head, sample_agents  # noqa: E402
 from oracle.dgsqp_v1 import OracleDGSQP                      # noqa: E402
+from oracle.dgsqp_v2 import OracleDGSQPV2                    # noqa: E402
 
 OUT = pathlib.Path(__file__).resolve().parent
 
 
-def make(name, game, sampler, solver_kw, count, seed, regression):
+def make(name, game, sampler, solver_kw, count, seed, regression, cls=OracleDGSQP):
     rng = np.random.default_rng(seed)
-    sol = OracleDGSQP(game, **solver_kw)
+    sol = cls(game, **solver_kw)
     keys = ["x0", "u_ws", "l_init", "u", "l", "x", "cost", "cond"]
     arr = {k: [] for k in keys}
     meta = dict(name=name, seed=seed, count=count, msg=[], num_iters=[], qp_solves=[], solver_kw=solver_kw,
@@ -46,7 +47,7 @@ def make(name, game, sampler, solver_kw, count, seed, regression):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["chicane", "curve", "agents3"]
+    which = sys.argv[1:] or ["chicane", "curve", "agents3", "chicane_v2"]
     if "chicane" in which:
         make("chicane_N25_seed0", RacingGame(chicane_track(), M=2, N=25), sample_head_to_head, dict(reg=1e-3), 48, 0,
              [3, 4, 7])
@@ -57,3 +58,8 @@ if __name__ == "__main__":
     if "agents3" in which:
         g = RacingGame(curve_track(curve_angle=np.pi / 2), M=3, N=15, obs_r=0.4)
         make("agents3_N15_seed0", g, sample_agents, dict(reg=1e-3), 16, 0, [0])
+    if "chicane_v2" in which:
+        # v2 step policy (DGSQPV2Params); a faster regularisation decay than the class default keeps the file small
+        make("chicane_v2_N15_seed0", RacingGame(chicane_track(), M=2, N=15), sample_head_to_head,
+             dict(reg=1e2, reg_decay=0.9, nms_frequency=3, sqp_iters=60, p_tol=1e-4, d_tol=1e-4), 16, 0, [0],
+             cls=OracleDGSQPV2)

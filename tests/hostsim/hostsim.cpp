@@ -6,16 +6,16 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
-#include "../../dgsqp_b200/csrc/sqp_v1.cuh"
+#include "../../dgsqp_b200/csrc/sqp_v2.cuh"
 #include "../../dgsqp_b200/csrc/host_setup.h"
 
 extern "C" {
 
 struct HsHandle { GameDesc G; SolverParams P; Dims D; std::vector<double> ws, sh; Workspace W; };
 
-void* hs_create(const dgsqp_racing_game* g, const dgsqp_params* p) {
+static void* hs_create_common(const dgsqp_racing_game* g, const dgsqp_params* p, const dgsqp_v2_params* p2) {
   HsHandle* h = new HsHandle();
-  if (dg_fill_game(g, &h->G) != 0 || dg_fill_params(p, &h->P) != 0) { delete h; return nullptr; }
+  if (dg_fill_game(g, &h->G) != 0 || (p2 ? dg_fill_params_v2(p2, &h->P) : dg_fill_params(p, &h->P)) != 0) { delete h; return nullptr; }
   h->D = make_dims(h->G.M, h->G.N);
   Workspace tmp;
   const char* lim = getenv("DG_HOSTSIM_SMEM_DOUBLES");      // tests cover both placements
@@ -26,6 +26,8 @@ void* hs_create(const dgsqp_racing_game* g, const dgsqp_params* p) {
   plan_memory(h->D, h->ws.data(), h->sh.data(), budget, h->W);
   return h;
 }
+void* hs_create(const dgsqp_racing_game* g, const dgsqp_params* p) { return hs_create_common(g, p, nullptr); }
+void* hs_create_v2(const dgsqp_racing_game* g, const dgsqp_v2_params* p) { return hs_create_common(g, nullptr, p); }
 void hs_set_l0_perturb(void* hp, double v) { ((HsHandle*)hp)->P.dbg_l0_perturb = v; }
 void hs_destroy(void* hp) { delete (HsHandle*)hp; }
 void hs_dims(void* hp, int* out) { HsHandle* h = (HsHandle*)hp; out[0] = h->D.nq; out[1] = h->D.nu; out[2] = h->D.n; out[3] = h->D.m; }
@@ -82,6 +84,7 @@ void hs_solve(void* hp, const double* x0, const double* u_ws, const double* l_ws
   SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0;
   SolveOut O; O.u = u; O.l = l; O.x = x; O.cost = cost; O.cond = cond; O.num_iters = num_iters; O.status = status;
   O.qp_solves = qp_solves; O.diag = diag; O.l_init = l_init;
-  sqp_solve_v1<false>(c, X, u_ws, l_ws, O);
+  if (h->P.policy == 2) sqp_solve_v2<false>(c, X, u_ws, l_ws, O);
+  else sqp_solve_v1<false>(c, X, u_ws, l_ws, O);
 }
 }

@@ -6,8 +6,9 @@ import subprocess
 
 import numpy as np
 
-from dgsqp_b200._abi import RacingGameStruct, ParamsStruct
-from dgsqp_b200.games import params_to_struct
+from dgsqp_b200._abi import RacingGameStruct, ParamsStruct, ParamsV2Struct
+from dgsqp_b200.games import params_to_struct, params_v2_to_struct
+from dgsqp_b200.solver_types import DGSQPV2Params
 
 HERE = pathlib.Path(__file__).resolve().parent / "hostsim"
 _libs = {}
@@ -30,6 +31,8 @@ def load(asan=False):
     lib = C.CDLL(str(build(asan)))
     lib.hs_create.restype = C.c_void_p
     lib.hs_create.argtypes = [C.POINTER(RacingGameStruct), C.POINTER(ParamsStruct)]
+    lib.hs_create_v2.restype = C.c_void_p
+    lib.hs_create_v2.argtypes = [C.POINTER(RacingGameStruct), C.POINTER(ParamsV2Struct)]
     for name in ["hs_destroy", "hs_dims", "hs_evaluate", "hs_G_dense", "hs_G_times", "hs_GT_times", "hs_nearest_pd",
                  "hs_qp", "hs_lsqr", "hs_solve"]:
         getattr(lib, name).argtypes = None
@@ -48,8 +51,13 @@ class HostSim:
     def __init__(self, game, params, asan=False):
         self.lib = load(asan)
         self.game = game
-        gs, ps = game.to_struct(), params_to_struct(params)
-        self.h = C.c_void_p(self.lib.hs_create(C.byref(gs), C.byref(ps)))
+        gs = game.to_struct()
+        if isinstance(params, DGSQPV2Params):
+            ps = params_v2_to_struct(params)
+            self.h = C.c_void_p(self.lib.hs_create_v2(C.byref(gs), C.byref(ps)))
+        else:
+            ps = params_to_struct(params)
+            self.h = C.c_void_p(self.lib.hs_create(C.byref(gs), C.byref(ps)))
         assert self.h.value, "hs_create failed"
         dims = np.zeros(4, dtype=np.int32)
         self.lib.hs_dims(self.h, _p(dims))

@@ -249,3 +249,45 @@ def test_multi_agent_games_run_and_satisfy_kkt(M):
     Q, q, G, g, x = og.evaluate(res.u[i], res.l[i], x0[i], np.zeros(2 * M), True)
     assert np.abs(q + G.T @ res.l[i]).max() < 1e-3 and g.max() < 1e-3 and np.abs(g * res.l[i]).max() < 1e-3
     assert np.abs(x.ravel() - res.x[i]).max() < 1e-10
+
+
+# ------------------------------------------------------------------ v2 step policy (DGSQPV2Params)
+def test_v2_solve_vs_golden():
+    """The v2 policy on device against the v2 oracle's golden results: identical status / iteration count / QP count
+    and equilibria within 1e-6 relative."""
+    data, meta = _golden("chicane_v2_N15_seed0")
+    game = dg.chicane_game(N=15)
+    solver = dg.DGSQP(game, dg.DGSQPV2Params(N=15, **meta["solver_kw"]), print_method=None)
+    B = data["x0"].shape[0]
+    for l0 in (data["l_init"], None):
+        res = solver.solve_batch(data["x0"], data["u_ws"], l0)
+        same = np.array([res.msg[i] == meta["msg"][i] and int(res.num_iters[i]) == meta["num_iters"][i] for i in range(B)])
+        assert same.mean() >= 0.9, f"identical (status, iters): {same.sum()}/{B}"
+        for i in np.where(same)[0]:
+            assert _rel(res.u[i], data["u"][i]) < 1e-6 and _rel(res.x[i], data["x"][i]) < 1e-6
+            assert _rel(res.l[i], data["l"][i]) < 1e-5
+            assert int(res.qp_solves[i]) == meta["qp_solves"][i]
+    again = solver.solve_batch(data["x0"], data["u_ws"])
+    bits = lambda a: np.ascontiguousarray(a).view(np.int64)
+    assert np.array_equal(bits(again.u), bits(res.u)) and np.array_equal(again.num_iters, res.num_iters)
+
+
+def test_v2_batch_kkt_and_limits():
+    """A 512-instance v2 batch with a Newton-like setting: KKT tolerances at converged points; 'max_it' means the
+    m-step budget was spent; unsupported options are rejected."""
+    N = 25
+    game = dg.chicane_game(N=N)
+    params = dg.DGSQPV2Params(N=N, reg=1e-3, p_tol=1e-3, d_tol=1e-3, sqp_iters=40)
+    x0, u_ws = sample_head_to_head(game, 512, seed=2)
+    solver = dg.DGSQP(game, params, print_method=None)
+    res = solver.solve_batch(x0, u_ws)
+    conv = res.status == 0
+    assert conv.mean() > 0.3 and set(np.unique(res.status)) <= {0, 1, 2, 3, 4}
+    assert np.all(res.cond[conv, 0] < params.p_tol) and np.all(res.cond[conv, 1] < params.d_tol)
+    assert np.all(res.cond[conv, 2] < params.d_tol)
+    d = solver.last_diag(512)
+    assert np.all(d[res.status == 2, 6] == params.sqp_iters) and np.all(d[:, 6] <= params.sqp_iters)
+    with pytest.raises(NotImplementedError):
+        dg.DGSQP(game, dg.DGSQPV2Params(N=N, merit_function="sum_obj_l1"), print_method=None)
+    with pytest.raises(ValueError):
+        dg.DGSQP(game, dg.DGSQPV2Params(N=N, merit_decrease_condition="wolfe"), print_method=None)

@@ -147,6 +147,32 @@ def test_solve_other_games_match_golden(name, mk, tol):
     assert same >= 0.9 * B, f"identical (status, iters) on {same}/{B}"
 
 
+def test_v2_policy_matches_oracle_and_golden():
+    """Kernel source of the v2 step policy (sqp_v2.cuh) against the v2 oracle: live on a Newton-like and a 'max'
+    decrease setting, and on the committed golden instances."""
+    from oracle.dgsqp_v2 import OracleDGSQPV2
+    from oracle.sampler import sample_head_to_head
+    N = 15
+    game, og = dg.chicane_game(N=N), RacingGame(chicane_track(), M=2, N=N)
+    for kw in (dict(reg=1e-3, p_tol=1e-3, d_tol=1e-3, sqp_iters=50),
+               dict(reg=1.0, reg_decay=0.8, sqp_iters=60, merit_decrease_condition="max")):
+        hs, sol = HostSim(game, dg.DGSQPV2Params(N=N, **kw)), OracleDGSQPV2(og, **kw)
+        rng = np.random.default_rng(0)
+        for i in range(3):
+            x0, u_ws = sample_head_to_head(og, rng)
+            r, h = sol.solve(x0, u_ws), hs.solve(x0, u_ws)
+            assert MSG[h["status"]] == r["msg"] and h["num_iters"] == r["num_iters"] and h["qp_solves"] == r["qp_solves"]
+            assert h["diag"][6] == r["m_steps"]
+            assert np.abs(h["u"] - r["u"]).max() < 1e-9 and np.abs(h["l"] - r["l"]).max() < 1e-8
+    data = np.load(GOLDEN / "chicane_v2_N15_seed0.npz")
+    meta = json.loads((GOLDEN / "chicane_v2_N15_seed0.json").read_text())
+    hs = HostSim(game, dg.DGSQPV2Params(N=N, **meta["solver_kw"]))
+    for i in range(4):
+        h = hs.solve(data["x0"][i], data["u_ws"][i], data["l_init"][i])
+        assert MSG[h["status"]] == meta["msg"][i] and h["num_iters"] == meta["num_iters"][i]
+        assert np.abs(h["u"] - data["u"][i]).max() < 1e-8
+
+
 def test_kernel_source_under_asan_ubsan():
     """One evaluate + nearestPD + QP + short solve of the kernel source under AddressSanitizer / UBSan
     (separate process: the sanitizer runtime has to be preloaded)."""

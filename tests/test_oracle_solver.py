@@ -9,6 +9,8 @@ import scipy.optimize as so
 
 from oracle.qp import solve_qp_gi, kkt_residuals, QPFailure
 from oracle.dgsqp_v1 import OracleDGSQP, nearest_pd
+from oracle.racing_game import RacingGame
+from oracle.track import chicane_track
 
 GOLDEN = pathlib.Path(__file__).parent / "golden"
 
@@ -103,3 +105,47 @@ def test_solve_regression_golden(chicane_full):
         assert r["msg"] == meta["msg"][i] and r["num_iters"] == meta["num_iters"][i]
         if r["msg"] == "conv_abs_tol":
             assert np.abs(r["u"] - data["u"][i]).max() < 1e-7
+
+
+# ------------------------------------------------------------------ v2 step policy (DGSQP_v2.py)
+def test_v2_merit_directional_derivative(chicane_small):
+    """v2 'stat_l1' (DGSQP_v2.py:1143-1161): dphi's stationarity part is the derivative of 1/2|q+G'l|^2 along
+    (du, dl), with the row-stacked game Hessian Q as the Jacobian of stat w.r.t. u."""
+    from oracle.dgsqp_v2 import OracleDGSQPV2
+    og, _, _ = chicane_small
+    rng = np.random.default_rng(2)
+    x0 = np.array([0.5, 0.3, 2.5, 0.0, 0.5, 0.3, 1.3, -0.3, 2.2, 0.0, 1.3, -0.3])
+    u = rng.normal(size=og.n) * 0.1
+    l = np.abs(rng.normal(size=og.m)) * 0.1
+    up = np.zeros(og.n_u)
+    Q, q, G, g, _ = og.evaluate(u, l, x0, up, True)
+    du, dl = rng.normal(size=og.n) * 0.1, rng.normal(size=og.m) * 0.1
+    d0 = OracleDGSQPV2._dstat2(du, l, dl, Q, q, G)
+
+    def phi(a):
+        q2, G2, _, _ = og.evaluate(u + a * du, l + a * dl, x0, up, False)
+        return OracleDGSQPV2._phi2(l + a * dl, np.zeros(og.m), q2, G2, 0.0)
+    h = 1e-6
+    assert abs((phi(h) - phi(-h)) / (2 * h) - d0) < 1e-5 * max(1.0, abs(d0))
+
+
+def test_v2_solve_properties_and_golden():
+    """v2 solves: KKT tolerances at 'conv_abs_tol', max_it counted in m-steps, and the committed golden values."""
+    from oracle.dgsqp_v2 import OracleDGSQPV2
+    og = RacingGame(chicane_track(), M=2, N=15)
+    data = np.load(GOLDEN / "chicane_v2_N15_seed0.npz")
+    meta = json.loads((GOLDEN / "chicane_v2_N15_seed0.json").read_text())
+    sol = OracleDGSQPV2(og, **meta["solver_kw"])
+    for i in meta["regression_instances"]:
+        r = sol.solve(data["x0"][i], data["u_ws"][i])
+        assert r["msg"] == meta["msg"][i] and r["num_iters"] == meta["num_iters"][i]
+        assert np.abs(r["u"] - data["u"][i]).max() < 1e-9 and np.abs(r["l"] - data["l"][i]).max() < 1e-8
+        assert r["cond"]["p_feas"] < 1e-4 and r["cond"]["comp"] < 1e-4 and r["cond"]["stat"] < 1e-4
+        assert r["m_steps"] + r["d_steps"] == r["num_iters"]
+    # a budget of 2 m-steps cannot converge from the PID warm start: 'max_it' after exactly 2 m-steps
+    r = OracleDGSQPV2(og, **dict(meta["solver_kw"], sqp_iters=2)).solve(data["x0"][0], data["u_ws"][0])
+    assert r["msg"] == "max_it" and r["m_steps"] == 2 and not r["status"]
+    # Newton-like setting (tiny regularisation): a handful of relaxed steps, same equilibrium as v1
+    r2 = OracleDGSQPV2(og, reg=1e-3, p_tol=1e-3, d_tol=1e-3, sqp_iters=50).solve(data["x0"][0], data["u_ws"][0])
+    r1 = OracleDGSQP(og).solve(data["x0"][0], data["u_ws"][0])
+    assert r2["status"] and r1["status"] and np.abs(r2["u"] - r1["u"]).max() < 1e-3
