@@ -41,7 +41,7 @@ def _oracle_worker(args):
     except NameError:
         _ORACLE = OracleDGSQP(RacingGame(chicane_track(), M=2, N=25))
     r = _ORACLE.solve(x0, u_ws)
-    return bool(r["status"]), int(r["num_iters"])
+    return bool(r["status"]), int(r["num_iters"]), r["msg"], r["u"]
 
 
 def cpu_oracle_throughput(x0, u_ws, cores):
@@ -57,6 +57,8 @@ def cpu_oracle_throughput(x0, u_ws, cores):
         dt = time.perf_counter() - t0
     conv = sum(o[0] for o in out)
     iters = sum(o[1] for o in out)
+    global _LAST_ORACLE_RESULTS
+    _LAST_ORACLE_RESULTS = out          # (status, iters, msg, u) per instance: parity of the GPU path on the same sample
     return conv / dt, iters / dt, dt, conv
 
 
@@ -293,6 +295,17 @@ def main():
             line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=cores, kind="port",
                                         sample=f"first {n_s} instances of the same batch, one oracle process per core, "
                                                f"{dt:.1f} s wall", sqp_iters_per_sec=ips)
+            # parity of the GPU results with the oracle on that sample (status, iteration count; u on converged ones)
+            msgs = _abi.STATUS_MSG
+            u_gpu = res.u[:n_s].cpu().numpy()
+            same, worst = 0, 0.0
+            for i, (st_o, it_o, msg_o, u_o) in enumerate(_LAST_ORACLE_RESULTS):
+                if msgs[int(status[i])] == msg_o and int(iters[i]) == it_o:
+                    same += 1
+                    if st_o:
+                        worst = max(worst, float(np.abs(u_gpu[i] - u_o).max() / max(1.0, np.abs(u_o).max())))
+            line["parity"] = dict(sample=n_s, identical_status_and_iters=same, max_rel_err_u_converged=worst,
+                                  against="oracle port (own LSQR dual initialisation on both sides)")
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

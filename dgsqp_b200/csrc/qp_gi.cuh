@@ -93,6 +93,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
   c.lap(PH_TRINV);
   int iq = 0, it = 0;
   const int max_iter = 10 * (n + m);
+  const Split2 sp = split2(c, n);                 // one decomposition for every n-wide sweep of the loop (integer divisions)
   int status = 0;
   while (true) {
     // slacks of all constraints, most violated one
@@ -116,7 +117,6 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
       // d = J' n_p = -Y npv   (2D over the CTA: thread = row of Y, column groups interleave the columns);  also npv . x
       double dd_tail = 0.0, dd_all = 0.0, gx = 0.0;
       {
-        const Split2 sp = split2(c, n);
         for (int j = sp.i0; j < n; j += sp.istep) {
           const double* DG_RESTRICT Yj = Y + j * ld;
           double a0 = 0.0, a1 = 0.0;
@@ -143,7 +143,6 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
       // z = J[:, iq:] d[iq:]  (2D over the CTA);  r = R^-1 d[:iq]  (column-oriented back substitution on the last warp,
       // while the first column group combines the partial sums of z)
       {
-        const Split2 sp = split2(c, n);
         for (int i = sp.i0; i < n; i += sp.istep) {
           double a0 = 0.0, a1 = 0.0;
           int j = iq + sp.g;
@@ -209,7 +208,6 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
           // w = (J2 v) * 2/(v'v) into npv (the entering row is not needed any more)
           DG_FOR(i, n) Q.npv[i] = (Q.zv[i] - alpha * Y[iq * ld + i]) * sc;
           c.sync();
-          const Split2 sp = split2(c, n);
           for (int i = sp.i0; i < n; i += sp.istep) {
             const double wi = Q.npv[i];
             double* DG_RESTRICT col = Y + iq * ld + i;

@@ -100,6 +100,15 @@ DG_DEV void decode_row(const Dims& D, int r, int& k, int& kind, int& a, int& b) 
   }
 }
 
+// The row layout only depends on (M, N): the decode (three integer divisions) is tabulated once per instance
+// (EvalBuf::rowtab, packed k | kind << 6 | a << 9 | b << 11) for the loops that walk all m rows.
+DG_DEV int pack_row(const Dims& D, int r) {
+  int k, kind, a, b;
+  decode_row(D, r, k, kind, a, b);
+  return k | (kind << 6) | (a << 9) | (b << 11);
+}
+DG_DEV void unpack_row(int p, int& k, int& kind, int& a, int& b) { k = p & 63; kind = (p >> 6) & 7; a = (p >> 9) & 3; b = (p >> 11) & 7; }
+
 DG_DEV int uidx(const Dims& D, int a, int k, int c) { return a * D.twoN + 2 * k + c; }
 
 // ---- track look-ups (radius_arclength_track.py:199-225; CasADi pw_const / pw_lin / fmod) ----
@@ -141,6 +150,7 @@ struct EvalBuf {
   double* tmpS;  // M*N*3   state-row products for G v
   double* cf;    // M*N*3   per (a,k) coefficients for G' w
   double* lbuf;  // m       staged copy of the multipliers the evaluation runs with
+  int* rowtab;   // m       packed row decode (global memory, read-only after game_row_table)
 };
 
 
@@ -212,16 +222,23 @@ DG_DEVN void game_linearize(Cta& c, const GameDesc& G, const Dims& D_, const dou
   }
 }
 
+template <bool SM>
+DG_DEVN void game_row_table(Cta& c, const Dims& D_, int* rowtab) {
+  const Dims D = D_;
+  DG_FOR(r, D.m) rowtab[r] = pack_row(D, r);
+  c.sync();
+}
+
 // f_Cxu: one thread per row
 template <bool SM>
 DG_DEVN void game_constraints(Cta& c, const GameDesc& G, const Dims& D_, const double* u, const double* up,
-                              const double* x, double* g) {
+                              const double* x, double* g, const int* DG_RESTRICT rowtab) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
   const Dims D = D_;
   DG_ASSUME_SHARED(x); DG_ASSUME_SHARED(g); DG_ASSUME_SHARED(up);
   DG_FOR(r, D.m) {
     int k, kind, a, b;
-    decode_row(D, r, k, kind, a, b);
+    unpack_row(rowtab[r], k, kind, a, b);
     double val;
     if (kind == K_COLL) {
       double dx = x[k * D.nq + a * DG_NQA] - x[k * D.nq + b * DG_NQA];
@@ -294,7 +311,7 @@ DG_DEVN void game_G_times(Cta& c, const Dims& D_, const EvalBuf& E_, const doubl
   c.sync();
   DG_FOR(r, D.m) {
     int k, kind, a, b;
-    decode_row(D, r, k, kind, a, b);
+    unpack_row(E.rowtab[r], k, kind, a, b);
     double val;
     if (kind == K_COLL) {
       double dx = E.x[k * D.nq + a * DG_NQA] - E.x[k * D.nq + b * DG_NQA];

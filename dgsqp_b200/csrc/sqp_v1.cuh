@@ -97,6 +97,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   PLACE(W.S.tn, n); PLACE(W.S.tn2, n);
   // ---- global only
   GTAKE(W.E.Q, n * n); GTAKE(W.B.Zg, n * n);
+  { double* t; GTAKE(t, (m + 1) / 2 + 1); W.E.rowtab = (int*)t; }
   GTAKE(W.L.Ub, DG_LSQR_BASIS * m); GTAKE(W.L.Vb, DG_LSQR_BASIS * m); GTAKE(W.L.cf, DG_LSQR_BASIS);
   GTAKE(W.L.u, m); GTAKE(W.L.v, m); GTAKE(W.L.w, m); GTAKE(W.L.x, m); GTAKE(W.L.tn, n); GTAKE(W.L.tm, m);
   GTAKE(W.S.u_im1, n); GTAKE(W.S.l_im1, m);
@@ -136,7 +137,7 @@ DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l_in)
   game_linearize<SM>(c, *X.G, D, u, E, true);
   c.sync();
   c.lap(PH_LIN_FULL);
-  game_constraints<SM>(c, *X.G, D, u, X.W.S.up, E.x, E.g);
+  game_constraints<SM>(c, *X.G, D, u, X.W.S.up, E.x, E.g, E.rowtab);
   game_costates<SM>(c, *X.G, D, E, l);
   game_sens<SM>(c, D, E);
   c.sync();
@@ -162,7 +163,7 @@ DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l_in,
   game_linearize<SM>(c, *X.G, D, u, E, false);
   c.sync();
   c.lap(PH_LIN_GRAD);
-  game_constraints<SM>(c, *X.G, D, u, X.W.S.up, E.x, E.g);
+  game_constraints<SM>(c, *X.G, D, u, X.W.S.up, E.x, E.g, E.rowtab);
   game_costates<SM>(c, *X.G, D, E, l);
   if (with_sens) game_sens<SM>(c, D, E);
   c.sync();
@@ -371,6 +372,7 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
   const Dims D = X.D; const SqpBuf S = X.W.S; const EvalBuf E = X.W.E; DG_SH_EVAL(E); const SolverParams P = *X.P;
   const int n = D.n, m = D.m;
   if (c.tid() == 0) X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0;
+  game_row_table<SM>(c, D, E.rowtab);
   DG_FOR(j, n) S.u[j] = u_ws[j];
   DG_FOR(r, m) S.l[r] = 0.0;
   DG_FOR(j, D.nu) S.up[j] = 0.0;

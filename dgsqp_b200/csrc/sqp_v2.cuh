@@ -117,6 +117,7 @@ DG_DEVN void sqp_solve_v2(Cta& c, SolveCtx& X, const double* u_ws, const double*
   const Dims D = X.D; const SqpBuf S = X.W.S; const EvalBuf E = X.W.E; DG_SH_EVAL(E); const SolverParams P = *X.P;
   const int n = D.n, m = D.m;
   if (c.tid() == 0) X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0;
+  game_row_table<SM>(c, D, E.rowtab);
   DG_FOR(j, n) S.u[j] = u_ws[j];
   DG_FOR(r, m) S.l[r] = 0.0;
   DG_FOR(j, D.nu) S.up[j] = 0.0;

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256, 1) units_kernel(const GameDesc* Gp, const
   __syncthreads();
   SolveCtx& X = sX;
   const Dims& D = X.D; const int n = D.n, m = D.m;
+  game_row_table<SM>(c, D, X.W.E.rowtab);
   for (int inst = blockIdx.x; inst < A.B; inst += gridDim.x) {
     c.sync();
     if (threadIdx.x == 0) X.x0 = A.x0 + (size_t)inst * D.nq;

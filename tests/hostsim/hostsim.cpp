@@ -24,6 +24,7 @@ static void* hs_create_common(const dgsqp_racing_game* g, const dgsqp_params* p,
   h->ws.assign(pl.gmem + 2, 0.0);
   h->sh.assign(pl.smem + 2, 0.0);
   plan_memory(h->D, h->ws.data(), h->sh.data(), budget, h->W);
+  { Cta c; game_row_table<false>(c, h->D, h->W.E.rowtab); }
   return h;
 }
 void* hs_create(const dgsqp_racing_game* g, const dgsqp_params* p) { return hs_create_common(g, p, nullptr); }
