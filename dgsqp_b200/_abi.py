@@ -29,6 +29,20 @@ class RacingGameStruct(C.Structure):
                 ("track_seg_len", C.c_double * MAX_TRACK_SEGS), ("track_seg_curv", C.c_double * MAX_TRACK_SEGS)]
 
 
+class LaneRowStruct(C.Structure):
+    _fields_ = [("brk", C.c_double), ("n_lo", C.c_double * 2), ("n_hi", C.c_double * 2), ("pt", C.c_double * 2)]
+
+
+class MergeGameStruct(C.Structure):
+    """dgsqp_merge_game (include/dgsqp_b200.h)."""
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("dt", C.c_double), ("mass", C.c_double),
+                ("input_weight", C.c_double * 2), ("state_weight", C.c_double * 4), ("term_scale", C.c_double),
+                ("goal", (C.c_double * 4) * MAX_AGENTS),
+                ("u_ub", C.c_double * 2), ("u_lb", C.c_double * 2), ("v_ub", C.c_double), ("v_lb", C.c_double),
+                ("obs_r", C.c_double * MAX_AGENTS), ("lane_r", C.c_double),
+                ("lane", (LaneRowStruct * 2) * MAX_AGENTS)]
+
+
 class ParamsStruct(C.Structure):
     _fields_ = [("reg", C.c_double), ("p_tol", C.c_double), ("d_tol", C.c_double),
                 ("beta", C.c_double), ("tau", C.c_double),
@@ -48,7 +62,7 @@ class ParamsV2Struct(C.Structure):
                 ("mu_vio_thresh", C.c_double)]
 
 
-EXPORTS = ["dgsqp_create", "dgsqp_create_v2", "dgsqp_destroy", "dgsqp_dims", "dgsqp_solve_batch", "dgsqp_solve_batch_async",
+EXPORTS = ["dgsqp_create", "dgsqp_create_v2", "dgsqp_create_merge", "dgsqp_create_merge_v2", "dgsqp_destroy", "dgsqp_dims", "dgsqp_solve_batch", "dgsqp_solve_batch_async",
            "dgsqp_last_diag", "dgsqp_phase_count", "dgsqp_last_phase_cycles", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_memory_plan", "dgsqp_set_smem_limit", "dgsqp_last_error", "dgsqp_version"]
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "libdgsqp_b200.so"
@@ -75,6 +89,10 @@ def load():
     lib.dgsqp_create.restype = C.c_int
     lib.dgsqp_create_v2.argtypes = [C.POINTER(RacingGameStruct), C.POINTER(ParamsV2Struct), C.c_int, C.POINTER(vp)]
     lib.dgsqp_create_v2.restype = C.c_int
+    lib.dgsqp_create_merge.argtypes = [C.POINTER(MergeGameStruct), C.POINTER(ParamsStruct), C.c_int, C.POINTER(vp)]
+    lib.dgsqp_create_merge.restype = C.c_int
+    lib.dgsqp_create_merge_v2.argtypes = [C.POINTER(MergeGameStruct), C.POINTER(ParamsV2Struct), C.c_int, C.POINTER(vp)]
+    lib.dgsqp_create_merge_v2.restype = C.c_int
     lib.dgsqp_destroy.argtypes = [vp]
     lib.dgsqp_destroy.restype = C.c_int
     lib.dgsqp_dims.argtypes = [vp, ip]

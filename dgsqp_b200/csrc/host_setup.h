@@ -3,11 +3,35 @@
 // get_tangent_angle_casadi_fn (DGSQP/tracks/radius_arclength_track.py:361-408,199-225).
 #pragma once
 #include "../../include/dgsqp_b200.h"
-#include "racing_game.cuh"
+#include "game.cuh"
 #include "sqp_v2.cuh"
 
+#ifdef DG_GAME_MERGE
+typedef dgsqp_merge_game dg_game_struct;
+static inline int dg_fill_game(const dgsqp_merge_game* g, GameDesc* G) {
+  if (!g || g->M < 2 || g->M > DG_MAX_AGENTS || g->N < 2 || g->N > 63) return -1;
+  if (!(g->mass > 0.0) || !(g->dt > 0.0)) return -1;
+  G->M = g->M; G->N = g->N;
+  G->veh.inv_m = 1.0 / g->mass; G->veh.dt = g->dt;
+  for (int i = 0; i < 2; ++i) { G->w_u[i] = g->input_weight[i]; G->u_ub[i] = g->u_ub[i]; G->u_lb[i] = g->u_lb[i]; }
+  for (int i = 0; i < 4; ++i) G->w_q[i] = g->state_weight[i];
+  G->term_scale = g->term_scale; G->v_ub = g->v_ub; G->v_lb = g->v_lb; G->lane_r = g->lane_r;
+  for (int a = 0; a < DG_MAX_AGENTS; ++a) {
+    G->obs_r[a] = g->obs_r[a];
+    for (int i = 0; i < 4; ++i) G->goal[a][i] = g->goal[a][i];
+    for (int j = 0; j < 2; ++j) {
+      const dgsqp_lane_row& s = g->lane[a][j];
+      LaneRow& L = G->lane[a][j];
+      L.brk = s.brk;
+      for (int i = 0; i < 2; ++i) { L.na[i] = s.n_lo[i]; L.nb[i] = s.n_hi[i]; L.pt[i] = s.pt[i]; }
+    }
+  }
+  return 0;
+}
+#else
+typedef dgsqp_racing_game dg_game_struct;
 static inline int dg_fill_game(const dgsqp_racing_game* g, GameDesc* G) {
-  if (!g || g->M < 2 || g->M > DG_MAX_AGENTS || g->N < 2 || g->N > 64) return -1;
+  if (!g || g->M < 2 || g->M > DG_MAX_AGENTS || g->N < 2 || g->N > 63) return -1;   // the packed row table keeps the stage in 6 bits
   if (g->track_nseg < 1 || g->track_nseg > DG_MAX_SEGS) return -1;
   G->M = g->M; G->N = g->N;
   G->veh.Lr = g->L_r; G->veh.L = g->L_f + g->L_r; G->veh.c_da = g->c_da; G->veh.c_dr = g->c_dr; G->veh.c_s = g->c_s;
@@ -36,6 +60,7 @@ static inline int dg_fill_game(const dgsqp_racing_game* g, GameDesc* G) {
   }
   return 0;
 }
+#endif
 
 static inline int dg_fill_params(const dgsqp_params* p, SolverParams* P) {
   if (!p || p->line_search_iters < 1 || p->sqp_iters < 1 || !(p->mu_vio_thresh >= 0.0)) return -1;

@@ -12,7 +12,7 @@
 // ones (classical Gram-Schmidt, two passes; basis capped at DG_LSQR_BASIS vectors).  In exact arithmetic
 // this is the same algorithm; in FP64 the iterates then track the exact-arithmetic ones to ~1e-12.
 #pragma once
-#include "racing_game.cuh"
+#include "game.cuh"
 
 #define DG_LSQR_BASIS 64
 

@@ -14,7 +14,7 @@
 // threads = consecutive columns of Y, column groups interleave the rows) with partial sums combined through
 // B.part; the triangular solve with R runs on one warp while the others combine the partial sums.
 #pragma once
-#include "racing_game.cuh"
+#include "game.cuh"
 #include "linalg.cuh"
 
 #define DG_QP_FEAS_TOL 1e-10

@@ -5,7 +5,7 @@
 // _watchdog_line_search_4 (:1174-1288).  Everything -- rollout, KKT assembly, eigen-projection,
 // QP, merit, step acceptance, convergence tests -- runs on device; the host only launches.
 #pragma once
-#include "racing_game.cuh"
+#include "game.cuh"
 #include "linalg.cuh"
 #include "qp_gi.cuh"
 #include "lsqr.cuh"
@@ -76,8 +76,8 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   { double* t; PLACE(t, (n + 1) / 2 + 1); W.Q.act = (int*)t; PLACE(t, (m + 1) / 2 + 1); W.Q.is_act = (int*)t; }
   const bool pool_ok = go == 0;                 // nothing of the pool fell back to global memory
   // ---- ARENA
-  const size_t ev_a = rnd(N * M * 48) + rnd((M + 1) * (N + 1) * nq) + rnd((M + 1) * N * M * 15) + rnd(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq) +
-                      rnd((M + 1) * nq * n) + rnd(N * M * 90) + rnd(m);
+  const size_t ev_a = rnd(N * M * DG_AB_SZ) + rnd((M + 1) * (N + 1) * nq) + rnd((M + 1) * N * M * DG_HC_SZ) + rnd(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq) +
+                      rnd((M + 1) * nq * n) + rnd(N * M * DG_T2_SZ) + rnd(m);
   const size_t mats = 2 * rnd(n * ld);
   const size_t arena = ev_a > mats ? ev_a : mats;
   double* ar = nullptr;
@@ -85,8 +85,8 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   {
     size_t o = 0;
     auto sub = [&](size_t cnt) { double* r = ar ? ar + o : nullptr; o += rnd(cnt); return r; };
-    W.E.AB = sub(N * M * 48); W.E.cst = sub((M + 1) * (N + 1) * nq); W.E.Hc = sub((M + 1) * N * M * 15);
-    W.E.Vbuf = sub(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq); W.E.Wrow = sub((M + 1) * nq * n); W.E.T2 = sub(N * M * 90); W.E.lbuf = sub(m);
+    W.E.AB = sub(N * M * DG_AB_SZ); W.E.cst = sub((M + 1) * (N + 1) * nq); W.E.Hc = sub((M + 1) * N * M * DG_HC_SZ);
+    W.E.Vbuf = sub(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq); W.E.Wrow = sub((M + 1) * nq * n); W.E.T2 = sub(N * M * DG_T2_SZ); W.E.lbuf = sub(m);
     W.B.ld = (int)ld; W.B.matA = ar; W.B.matB = ar ? ar + rnd(n * ld) : nullptr;
   }
   // ---- SENS
@@ -442,19 +442,7 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
   DG_FOR(j, n) O.u[j] = S.u[j];
   DG_FOR(r, m) O.l[r] = S.l[r];
   DG_FOR(j, (D.N + 1) * D.nq) O.x[j] = E.x[j];
-  DG_FOR(a, D.M) {
-    double J = 0.0;
-    for (int k = 0; k < D.N; ++k)
-      for (int cc = 0; cc < 2; ++cc) {
-        double uk = S.u[uidx(D, a, k, cc)];
-        double um = k == 0 ? S.up[a * 2 + cc] : S.u[uidx(D, a, k - 1, cc)];
-        J += 0.5 * X.G->w_u[cc] * uk * uk + 0.5 * X.G->w_du[cc] * (uk - um) * (uk - um);
-      }
-    const double* xN = E.x + D.N * D.nq;
-    J += -X.G->c_prog * xN[a * DG_NQA + 4];
-    for (int b = 0; b < D.M; ++b) if (b != a) J += X.G->c_comp * atan(xN[b * DG_NQA + 4] - xN[a * DG_NQA + 4]);
-    O.cost[a] = J;
-  }
+  game_costs<SM>(c, *X.G, D, S.u, S.up, E.x, O.cost);
   if (c.tid() == 0) {
     O.cond[0] = p_feas; O.cond[1] = comp; O.cond[2] = stat;
     *O.num_iters = sqp_it; *O.status = status; *O.qp_solves = total_qp;

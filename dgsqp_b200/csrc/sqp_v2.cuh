@@ -273,19 +273,7 @@ DG_DEVN void sqp_solve_v2(Cta& c, SolveCtx& X, const double* u_ws, const double*
   DG_FOR(j, n) O.u[j] = S.u[j];
   DG_FOR(r, m) O.l[r] = S.l[r];
   DG_FOR(j, (D.N + 1) * D.nq) O.x[j] = E.x[j];
-  DG_FOR(a, D.M) {
-    double J = 0.0;
-    for (int k = 0; k < D.N; ++k)
-      for (int cc = 0; cc < 2; ++cc) {
-        double uk = S.u[uidx(D, a, k, cc)];
-        double um = k == 0 ? S.up[a * 2 + cc] : S.u[uidx(D, a, k - 1, cc)];
-        J += 0.5 * X.G->w_u[cc] * uk * uk + 0.5 * X.G->w_du[cc] * (uk - um) * (uk - um);
-      }
-    const double* xN = E.x + D.N * D.nq;
-    J += -X.G->c_prog * xN[a * DG_NQA + 4];
-    for (int b = 0; b < D.M; ++b) if (b != a) J += X.G->c_comp * atan(xN[b * DG_NQA + 4] - xN[a * DG_NQA + 4]);
-    O.cost[a] = J;
-  }
+  game_costs<SM>(c, *X.G, D, S.u, S.up, E.x, O.cost);
   if (c.tid() == 0) {
     O.cond[0] = p_feas; O.cond[1] = comp; O.cond[2] = stat;
     *O.num_iters = sqp_it; *O.status = status; *O.qp_solves = total_qp;

@@ -6,6 +6,7 @@ Factories reproduce the literals of the BASELINE configurations:
 ``chicane_game``  scripts/DGSQP_ALGAMES_monte_carlo_chicane.py:49-174
 ``curve_game``    scripts/DGSQP_ALGAMES_monte_carlo_curve.py (theta, N sweep; reg = 0, steer rate 4.5, r = 0.2)
 ``agents_game``   scripts/DGSQP_monte_carlo_agents.py:47-153 (M agents, 90 degree curve, r = 0.4)
+``merge_game``    scripts/DGSQP_merge_monte_carlo.py:40-192 (three unicycles, one on the ramp; ``dgsqp_merge_game``)
 """
 from dataclasses import dataclass, field
 import math
@@ -13,7 +14,7 @@ from typing import List, Tuple
 
 import numpy as np
 
-from ._abi import RacingGameStruct, MAX_AGENTS, MAX_TRACK_SEGS
+from ._abi import RacingGameStruct, MergeGameStruct, MAX_AGENTS, MAX_TRACK_SEGS
 from .solver_types import DGSQPParams
 from .tracks import RadiusArclengthTrack, ChicaneTrack, CurveTrack
 from .types import VehicleState
@@ -131,6 +132,107 @@ def agents_game(M=3, theta_deg=90.0, N=25):
 def agents_params(N=25):
     return DGSQPParams(solver_name="DGSQP", dt=0.1, N=N, reg=1e-3, nonmono_ls=True, line_search_iters=50,
                        sqp_iters=50, p_tol=1e-3, d_tol=1e-3, beta=0.01, tau=0.5)
+
+
+def merge_lanes(lw=0.3, mw=0.3, mp=1.5, th=math.pi / 12):
+    """Lane half-planes of the merge scenario per car (scripts/DGSQP_merge_monte_carlo.py:40-74,316-318): rows
+    ``n(x)'(p - (pt - r n(x))) <= 0`` as tuples (brk, n_lo, n_hi, pt); cars 1, 2 drive the straight lane, car 3 the ramp
+    whose normals switch to the straight lane's at x6 / x7 (``ca.pw_const``)."""
+    ns = (0.0, 1.0)
+    nm = (-math.sin(th), math.cos(th))
+    neg = lambda v: (-v[0], -v[1])
+    x1, x3 = (0.0, lw), (0.0, 0.0)
+    x6 = (mp + lw / math.tan(th), lw)
+    x7 = (mp + mw / math.sin(th), 0.0)
+    inf = float("inf")
+    straight = [(inf, ns, ns, x1), (inf, neg(ns), neg(ns), x3)]
+    ramp = [(x6[0], nm, ns, x6), (x7[0], neg(nm), neg(ns), x7)]
+    return [straight, straight, ramp]
+
+
+@dataclass
+class MergeGame:
+    """Merge scenario (scripts/DGSQP_merge_monte_carlo.py): M kinematic unicycles ``q = [x, y, v, psi]``,
+    ``u = [F_x, w_z]`` (``CasadiKinematicUnicycle``, dynamics_models.py:306-345) under RK3 (:202-212).  The script's
+    DynamicsConfig carries no mass; the DynamicsConfig default 2.366 applies (model_types.py:99)."""
+    M: int = 3
+    N: int = 20
+    dt: float = 0.1
+    mass: float = 2.366
+    input_weight: Tuple[float, float] = (0.1, 0.1)
+    state_weight: Tuple[float, float, float, float] = (1.0, 10.0, 1.0, 1.0)
+    term_scale: float = 10.0
+    goals: List[Tuple[float, float, float, float]] = field(
+        default_factory=lambda: [(4.0, 0.15, 0.3, 0.0), (4.5, 0.15, 0.3, 0.0), (4.25, 0.15, 0.3, 0.0)])
+    u_ub: Tuple[float, float] = (2.0, 4.5)
+    u_lb: Tuple[float, float] = (-2.0, -4.5)
+    v_ub: float = 2.0
+    v_lb: float = -2.0
+    obs_r: List[float] = field(default_factory=lambda: [0.1, 0.1, 0.1])
+    lane_r: float = 0.1
+    lanes: list = field(default_factory=merge_lanes)
+    name: str = "merge"
+
+    def __post_init__(self):
+        if not 2 <= self.M <= MAX_AGENTS:
+            raise ValueError(f"merge game supports 2..{MAX_AGENTS} agents, got {self.M}")
+        if len(self.obs_r) != self.M or len(self.goals) != self.M or len(self.lanes) != self.M:
+            raise ValueError("Number of agents: %i, but %i radii / %i goals / %i lane sets were provided"
+                             % (self.M, len(self.obs_r), len(self.goals), len(self.lanes)))
+
+    @property
+    def n_q(self):
+        return 4 * self.M
+
+    @property
+    def n_u(self):
+        return 2 * self.M
+
+    @property
+    def n(self):
+        return self.N * self.n_u
+
+    @property
+    def n_c(self):
+        P = self.M * (self.M - 1) // 2
+        return [6 * self.M] + [P + 8 * self.M] * (self.N - 1) + [P + 4 * self.M]
+
+    @property
+    def m(self):
+        return int(sum(self.n_c))
+
+    def state2q(self, states: List[VehicleState]) -> np.ndarray:
+        """CasadiKinematicUnicycle.state2q (dynamics_models.py:343-345 / state2qu :340-342)."""
+        return np.array([[s.x.x, s.x.y, s.v.v_long, s.e.psi] for s in states], dtype=np.float64).ravel()
+
+    def to_struct(self) -> MergeGameStruct:
+        g = MergeGameStruct()
+        g.M, g.N, g.dt, g.mass = self.M, self.N, self.dt, self.mass
+        for i in range(2):
+            g.input_weight[i], g.u_ub[i], g.u_lb[i] = self.input_weight[i], self.u_ub[i], self.u_lb[i]
+        for i in range(4):
+            g.state_weight[i] = self.state_weight[i]
+        g.term_scale, g.v_ub, g.v_lb, g.lane_r = self.term_scale, self.v_ub, self.v_lb, self.lane_r
+        for a in range(self.M):
+            g.obs_r[a] = self.obs_r[a]
+            for i in range(4):
+                g.goal[a][i] = self.goals[a][i]
+            for j in range(2):
+                brk, n_lo, n_hi, pt = self.lanes[a][j]
+                g.lane[a][j].brk = brk
+                for i in range(2):
+                    g.lane[a][j].n_lo[i], g.lane[a][j].n_hi[i], g.lane[a][j].pt[i] = n_lo[i], n_hi[i], pt[i]
+        return g
+
+
+def merge_game(N=20):
+    return MergeGame(N=N, name=f"merge_N{N}")
+
+
+def merge_params(N=20):
+    """scripts/DGSQP_merge_monte_carlo.py:178-192."""
+    return DGSQPParams(solver_name="DGSQP", dt=0.1, N=N, reg=0.0, merit_function="stat_l1", nonmono_ls=True,
+                       line_search_iters=50, sqp_iters=50, p_tol=1e-3, d_tol=1e-3, beta=0.01, tau=0.5)
 
 
 MU_VIO_THRESH = 1e-10     # see include/dgsqp_b200.h (dgsqp_params.mu_vio_thresh) and DESIGN.md D2

@@ -64,6 +64,36 @@ typedef struct {
   double track_seg_curv[DGSQP_MAX_TRACK_SEGS];  /* signed curvature 1/r (0 = straight) */
 } dgsqp_racing_game;
 
+/* Highway-merge game of M kinematic unicycles (BASELINE config 5).  Replaces the CasADi objects
+ * scripts/DGSQP_merge_monte_carlo.py builds and hands to DGSQP.__init__:
+ *   vehicle  CasadiKinematicUnicycle, q = [x, y, v, psi], u = [F_x, w_z]   DGSQP/dynamics/dynamics_models.py:306-345
+ *            discretised by rk3 with one sub-step                         DGSQP/dynamics/dynamics_models.py:202-212
+ *   costs    stage 1/2 w_u.u^2 + 1/2 (q-goal)'diag(w_q)(q-goal), terminal term_scale * state term   merge.py:253-304
+ *   lanes    two rows per agent and stage k = 0..N:  n(x)'(p - (pt - lane_r n(x))) <= 0 with the normal switched by
+ *            ca.pw_const at x = brk (n_lo for x < brk, n_hi otherwise; brk = +inf for a straight lane)  merge.py:40-74,316-318
+ *   bounds   input box (k < N), v bounds (k >= 1), pairwise collision rows (k >= 1)                    merge.py:130-169,306-314 */
+typedef struct {
+  double brk;
+  double n_lo[2], n_hi[2];
+  double pt[2];
+} dgsqp_lane_row;
+
+typedef struct {
+  int32_t M;                 /* agents, 2..4 */
+  int32_t N;                 /* horizon */
+  double dt;
+  double mass;
+  double input_weight[2];
+  double state_weight[4];
+  double term_scale;
+  double goal[DGSQP_MAX_AGENTS][4];
+  double u_ub[2], u_lb[2];
+  double v_ub, v_lb;
+  double obs_r[DGSQP_MAX_AGENTS];
+  double lane_r;
+  dgsqp_lane_row lane[DGSQP_MAX_AGENTS][2];
+} dgsqp_merge_game;
+
 /* Mirrors DGSQPParams (DGSQP/solvers/solver_types.py:92-127); fields that only steer Python-side
  * behaviour (verbose, code_gen, debug_plot, ...) stay in the Python dataclass. */
 typedef struct {
@@ -110,6 +140,10 @@ int dgsqp_create(const dgsqp_racing_game* game, const dgsqp_params* params, int 
 /* Same for the v2 solver class (DGSQP_v2.py:55-230); dgsqp_solve_batch then runs the v2 policy.  v2 keeps u_prev
  * between calls (:328); the batched entry point uses u_prev = 0 like the Monte-Carlo drivers do. */
 int dgsqp_create_v2(const dgsqp_racing_game* game, const dgsqp_v2_params* params, int device, dgsqp_handle** out);
+/* Same two constructors for the merge game; every other entry point takes the handle of either game.
+ * dims for this game: n_q = 4M, n_u = 2M, n = N*n_u, m = 6M + (N-1)(P+8M) + (P+4M), P = M(M-1)/2. */
+int dgsqp_create_merge(const dgsqp_merge_game* game, const dgsqp_params* params, int device, dgsqp_handle** out);
+int dgsqp_create_merge_v2(const dgsqp_merge_game* game, const dgsqp_v2_params* params, int device, dgsqp_handle** out);
 int dgsqp_destroy(dgsqp_handle* h);
 
 /* dims[0..3] = n_q (joint state), n_u (joint input), n = N*n_u, m = number of constraint rows */

@@ -1,7 +1,7 @@
 // Single-thread host build of the device solver source (DG_HOSTSIM).  TEST HARNESS ONLY: lets the
 // CPU test-suite exercise the exact kernel source (arithmetic, control flow, memory bounds under
 // ASan) on machines without a GPU.  It is not part of the product library and nothing in
-// dgsqp_b200/ loads it.
+// dgsqp_b200/ loads it.  Compiled once per game (-DDG_GAME_MERGE selects the merge game, see csrc/game.cuh).
 #define DG_HOSTSIM 1
 #include <cstdlib>
 #include <cstring>
@@ -13,7 +13,7 @@ extern "C" {
 
 struct HsHandle { GameDesc G; SolverParams P; Dims D; std::vector<double> ws, sh; Workspace W; };
 
-static void* hs_create_common(const dgsqp_racing_game* g, const dgsqp_params* p, const dgsqp_v2_params* p2) {
+static void* hs_create_common(const dg_game_struct* g, const dgsqp_params* p, const dgsqp_v2_params* p2) {
   HsHandle* h = new HsHandle();
   if (dg_fill_game(g, &h->G) != 0 || (p2 ? dg_fill_params_v2(p2, &h->P) : dg_fill_params(p, &h->P)) != 0) { delete h; return nullptr; }
   h->D = make_dims(h->G.M, h->G.N);
@@ -24,11 +24,12 @@ static void* hs_create_common(const dgsqp_racing_game* g, const dgsqp_params* p,
   h->ws.assign(pl.gmem + 2, 0.0);
   h->sh.assign(pl.smem + 2, 0.0);
   plan_memory(h->D, h->ws.data(), h->sh.data(), budget, h->W);
+  game_bind(h->W.E, &h->G);
   { Cta c; game_row_table<false>(c, h->D, h->W.E.rowtab); }
   return h;
 }
-void* hs_create(const dgsqp_racing_game* g, const dgsqp_params* p) { return hs_create_common(g, p, nullptr); }
-void* hs_create_v2(const dgsqp_racing_game* g, const dgsqp_v2_params* p) { return hs_create_common(g, nullptr, p); }
+void* hs_create(const dg_game_struct* g, const dgsqp_params* p) { return hs_create_common(g, p, nullptr); }
+void* hs_create_v2(const dg_game_struct* g, const dgsqp_v2_params* p) { return hs_create_common(g, nullptr, p); }
 void hs_set_l0_perturb(void* hp, double v) { ((HsHandle*)hp)->P.dbg_l0_perturb = v; }
 void hs_destroy(void* hp) { delete (HsHandle*)hp; }
 void hs_dims(void* hp, int* out) { HsHandle* h = (HsHandle*)hp; out[0] = h->D.nq; out[1] = h->D.nu; out[2] = h->D.n; out[3] = h->D.m; }

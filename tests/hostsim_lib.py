@@ -6,40 +6,43 @@ import subprocess
 
 import numpy as np
 
-from dgsqp_b200._abi import RacingGameStruct, ParamsStruct, ParamsV2Struct
-from dgsqp_b200.games import params_to_struct, params_v2_to_struct
+from dgsqp_b200._abi import RacingGameStruct, MergeGameStruct, ParamsStruct, ParamsV2Struct
+from dgsqp_b200.games import params_to_struct, params_v2_to_struct, MergeGame
 from dgsqp_b200.solver_types import DGSQPV2Params
 
 HERE = pathlib.Path(__file__).resolve().parent / "hostsim"
 _libs = {}
 
 
-def build(asan=False):
-    out = HERE / ("libhostsim_asan.so" if asan else "libhostsim.so")
+def build(asan=False, merge=False):
+    out = HERE / ("libhostsim" + ("_merge" if merge else "") + ("_asan" if asan else "") + ".so")
     srcs = [HERE / "hostsim.cpp"] + sorted((HERE.parents[1] / "dgsqp_b200" / "csrc").glob("*.cuh")) \
         + sorted((HERE.parents[1] / "dgsqp_b200" / "csrc").glob("*.h"))
     if out.exists() and all(out.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return out
     flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if asan else ["-O2"]
+    if merge:
+        flags = flags + ["-DDG_GAME_MERGE=1"]
     subprocess.check_call(["g++", *flags, "-shared", "-fPIC", "-std=c++17", "-o", str(out), str(HERE / "hostsim.cpp")])
     return out
 
 
-def load(asan=False):
-    if asan in _libs:
-        return _libs[asan]
-    lib = C.CDLL(str(build(asan)))
+def load(asan=False, merge=False):
+    if (asan, merge) in _libs:
+        return _libs[(asan, merge)]
+    lib = C.CDLL(str(build(asan, merge)))
+    gs = MergeGameStruct if merge else RacingGameStruct
     lib.hs_create.restype = C.c_void_p
-    lib.hs_create.argtypes = [C.POINTER(RacingGameStruct), C.POINTER(ParamsStruct)]
+    lib.hs_create.argtypes = [C.POINTER(gs), C.POINTER(ParamsStruct)]
     lib.hs_create_v2.restype = C.c_void_p
-    lib.hs_create_v2.argtypes = [C.POINTER(RacingGameStruct), C.POINTER(ParamsV2Struct)]
+    lib.hs_create_v2.argtypes = [C.POINTER(gs), C.POINTER(ParamsV2Struct)]
     for name in ["hs_destroy", "hs_dims", "hs_evaluate", "hs_G_dense", "hs_G_times", "hs_GT_times", "hs_nearest_pd",
                  "hs_qp", "hs_lsqr", "hs_solve"]:
         getattr(lib, name).argtypes = None
     lib.hs_nearest_pd.restype = C.c_int
     lib.hs_qp.restype = C.c_int
     lib.hs_lsqr.restype = C.c_int
-    _libs[asan] = lib
+    _libs[(asan, merge)] = lib
     return lib
 
 
@@ -49,7 +52,7 @@ def _p(a):
 
 class HostSim:
     def __init__(self, game, params, asan=False):
-        self.lib = load(asan)
+        self.lib = load(asan, merge=isinstance(game, MergeGame))
         self.game = game
         gs = game.to_struct()
         if isinstance(params, DGSQPV2Params):
