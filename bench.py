@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Headline benchmark: converged 2-agent chicane game solves / s (BASELINE.json configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--workload chicane|merge]
 
 A step = one solve_batch over B = 10 000 synthetic chicane instances per GPU (randomised initial conditions,
 PID warm start; dgsqp_b200.montecarlo).  `value` is measured with the inputs resident in HBM (CUDA events on
@@ -10,6 +10,8 @@ region.  N > 1: one process per GPU under torchrun, instances sharded with no co
 (weak scaling: B per GPU), statistics gathered at the end, time = max over ranks.
 `--impl reference` times the CPU oracle (NumPy restatement of the reference solver; the reference itself
 needs CasADi + OSQP which are not installable offline) on all host cores.
+`--workload merge` runs the same measurement on the merge scenario (BASELINE.json configs[4]: three unicycles,
+N = 20, seed-1 sampler of scripts/DGSQP_merge_monte_carlo.py); the default is the headline chicane workload.
 """
 import argparse
 import json
@@ -33,13 +35,17 @@ def _oracle_worker(args):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     import numpy as np  # noqa: F401
     from oracle.dgsqp_v1 import OracleDGSQP
-    from oracle.racing_game import RacingGame
-    from oracle.track import chicane_track
     global _ORACLE
     try:
         _ORACLE
     except NameError:
-        _ORACLE = OracleDGSQP(RacingGame(chicane_track(), M=2, N=25))
+        if len(x0) == 12 and len(u_ws) == 120:          # merge scenario (3 unicycles, N = 20)
+            from oracle.merge_game import MergeGame
+            _ORACLE = OracleDGSQP(MergeGame(N=20), reg=0.0)
+        else:
+            from oracle.racing_game import RacingGame
+            from oracle.track import chicane_track
+            _ORACLE = OracleDGSQP(RacingGame(chicane_track(), M=2, N=25))
     r = _ORACLE.solve(x0, u_ws)
     return bool(r["status"]), int(r["num_iters"]), r["msg"], r["u"]
 
@@ -134,6 +140,7 @@ def main():
     ap.add_argument("--batch", type=int, default=10000, help="instances per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances for the CPU baseline (0 = 1 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="chicane", choices=["chicane", "merge"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -142,19 +149,27 @@ def main():
 
     import numpy as np
     import dgsqp_b200 as dg
-    from dgsqp_b200.montecarlo import sample_head_to_head
+    from dgsqp_b200.montecarlo import sample_head_to_head, sample_merge
 
-    game, params = dg.chicane_game(), dg.chicane_params()
-    config = dict(workload=WORKLOAD, instances_per_gpu=args.batch, agents=2, horizon=25, n=game.n, m=game.m,
-                  solver="DGSQP v1 (DGSQPParams: reg=1e-3, nonmono_ls, 50 SQP iters, tol 1e-3)",
-                  l2_policy="256 MiB buffer written between timed steps (L2 flush)", sampler_seed=0)
+    if args.workload == "merge":
+        game, params = dg.merge_game(), dg.merge_params()
+        sample = lambda g, B, seed: sample_merge(g, B, seed=1 + seed)     # the script's seed is 1
+        config = dict(workload="merge_3agent_N20_mc", instances_per_gpu=args.batch, agents=3, horizon=20, n=game.n,
+                      m=game.m, solver="DGSQP v1 (DGSQPParams: reg=0, nonmono_ls, 50 SQP iters, tol 1e-3)",
+                      l2_policy="256 MiB buffer written between timed steps (L2 flush)", sampler_seed=1)
+    else:
+        game, params = dg.chicane_game(), dg.chicane_params()
+        sample = sample_head_to_head
+        config = dict(workload=WORKLOAD, instances_per_gpu=args.batch, agents=2, horizon=25, n=game.n, m=game.m,
+                      solver="DGSQP v1 (DGSQPParams: reg=1e-3, nonmono_ls, 50 SQP iters, tol 1e-3)",
+                      l2_policy="256 MiB buffer written between timed steps (L2 flush)", sampler_seed=0)
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
         n_s = args.cpu_sample or cores
-        x0, u_ws = sample_head_to_head(game, n_s * (args.steps + args.warmup), seed=0)
+        x0, u_ws = sample(game, n_s * (args.steps + args.warmup), 0)
         vals, its, secs = [], [], []
         for s in range(args.warmup + args.steps):
             sl = slice(s * n_s, (s + 1) * n_s)
@@ -167,7 +182,7 @@ def main():
                     dtype="f64", data="synthetic", config=dict(config, instances_per_step=n_s), impl="reference",
                     sqp_iters_per_sec=float(np.mean(its)),
                     cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
-                                      sample=f"{n_s} chicane instances per step, one oracle process per core"),
+                                      sample=f"{n_s} {args.workload} instances per step, one oracle process per core"),
                     e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
         print(json.dumps(line))
         return
@@ -185,7 +200,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    x0, u_ws = sample_head_to_head(game, B, seed=rank)           # each rank owns its shard of the global batch
+    x0, u_ws = sample(game, B, rank)                             # each rank owns its shard of the global batch
     solver = dg.DGSQP(game, params, print_method=None, device=local_rank)
     lib = _abi.load()
     x0_d, u_d = torch.from_numpy(x0).to(dev), torch.from_numpy(u_ws).to(dev)

@@ -7,12 +7,14 @@ from .solver_types import DGSQPParams, DGSQPV2Params, PIDParams
 from .types import (VehicleState, VehicleActuation, VehiclePrediction, Position, ParametricPose, OrientationEuler,
                     BodyLinearVelocity, BodyAngularVelocity)
 from .tracks import RadiusArclengthTrack, ChicaneTrack, CurveTrack, StraightTrack
-from .games import RacingGame, chicane_game, curve_game, agents_game, chicane_params, curve_params, agents_params
+from .games import (RacingGame, MergeGame, chicane_game, curve_game, agents_game, merge_game, chicane_params,
+                    curve_params, agents_params, merge_params)
 
 __all__ = ["DGSQPParams", "DGSQPV2Params", "PIDParams", "VehicleState", "VehicleActuation", "VehiclePrediction",
            "Position", "ParametricPose", "OrientationEuler", "BodyLinearVelocity", "BodyAngularVelocity",
            "RadiusArclengthTrack", "ChicaneTrack", "CurveTrack", "StraightTrack", "RacingGame", "chicane_game",
-           "curve_game", "agents_game", "chicane_params", "curve_params", "agents_params", "DGSQP"]
+           "curve_game", "agents_game", "chicane_params", "curve_params", "agents_params", "MergeGame", "merge_game",
+           "merge_params", "DGSQP"]
 
 
 def __getattr__(name):

@@ -78,7 +78,10 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   // ---- ARENA
   const size_t ev_a = rnd(N * M * DG_AB_SZ) + rnd((M + 1) * (N + 1) * nq) + rnd((M + 1) * N * M * DG_HC_SZ) + rnd(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq) +
                       rnd((M + 1) * nq * n) + rnd(N * M * DG_T2_SZ) + rnd(m);
-  const size_t mats = 2 * rnd(n * ld);
+  // matB doubles as the scratch of the eigenvector stage of nearest_pd (Sturm counters, DG_EIG_CHUNK interleaved
+  // inverse-iteration work vectors and iterates: (n+1)/2+1 + 6 n DG_EIG_CHUNK doubles), which exceeds n*ld below n ~ 97
+  const size_t eig_scr = rnd((n + 1) / 2 + 1 + 6 * n * DG_EIG_CHUNK);
+  const size_t mats = rnd(n * ld) + (rnd(n * ld) > eig_scr ? rnd(n * ld) : eig_scr);
   const size_t arena = ev_a > mats ? ev_a : mats;
   double* ar = nullptr;
   if (so + arena <= sbudget) { STAKE(ar, arena); P.mats_in_smem = 1; } else GTAKE(ar, arena);

@@ -9,10 +9,13 @@ Instance distributions and the PID warm start follow the reference drivers
   SciPy's adaptive RK45 (``dynamics_models.py:161-186``) so that it vectorises;
 * rejection sampling is done on whole batches, so the random stream is consumed in a different
   order than the sequential script (the reference scripts for these games are unseeded anyway).
+
+``sample_merge`` follows ``scripts/DGSQP_merge_monte_carlo.py:424-495`` (seeded, ``default_rng(1)``) and consumes
+the random stream in exactly the script's order (12 draws per trial, rejected trials included).
 """
 import numpy as np
 
-from .games import RacingGame, NQA, NUA
+from .games import RacingGame, MergeGame, NQA, NUA
 
 
 def _track_lookup(track, s):
@@ -154,3 +157,45 @@ def sample_agents(game: RacingGame, B, seed=0):
         uws.append(np.hstack(us)[ok])
         have += int(ok.sum())
     return np.ascontiguousarray(np.vstack(x0s)[:B]), np.ascontiguousarray(np.vstack(uws)[:B])
+
+
+def sample_merge(game: MergeGame, B, seed=1):
+    """B accepted merge instances: x0 [B, 4M] (q = [x, y, v, psi] per car), u_ws [B, n] = 0 (the script never calls
+    set_warm_start, DGSQP.py:179).  Trial t of the script uses draws 12t..12t+11 of ``default_rng(seed)``; a trial is
+    rejected when the zero-input RK3 roll-outs collide -- with car 3 rolled out from the ZERO state, because the script
+    never initialises ``car3_q_ws[0]`` (:486-488; SURVEY App. C #6)."""
+    assert game.M == 3
+    rng = np.random.default_rng(seed)
+    th = np.pi / 12
+    x5_0, x7_0 = 1.5, game.lanes[2][1][0]
+    h, N = game.dt, game.N
+    out, have = [], 0
+    while have < B:
+        K = max(64, int(1.5 * (B - have)))
+        r = rng.random((K, 12))
+        cars = []
+        for c, x_nom in enumerate((0.0, 0.5)):
+            x = x_nom + 0.5 * r[:, 4 * c] - 0.25
+            y = 0.15 + 0.1 * r[:, 4 * c + 1] - 0.05
+            v = 0.3 * (1 + 0.06 * r[:, 4 * c + 2] - 0.03)
+            p = 0.0 + (5 * r[:, 4 * c + 3] - 2.5) * np.pi / 180
+            cars.append(np.stack([x, y, v, p], axis=1))
+        x_nom, y_nom = 0.25, -((x7_0 + x5_0) / 2 - 0.25) * np.tan(th)
+        s_, ey = 0.5 * r[:, 8] - 0.25, 0.1 * r[:, 9] - 0.05
+        x = x_nom + s_ * np.cos(th) - ey * np.sin(th)
+        y = y_nom + s_ * np.sin(th) + ey * np.cos(th)
+        v = 0.3 * (1 + 0.06 * r[:, 10] - 0.03)
+        p = np.pi / 12 + (5 * r[:, 11] - 2.5) * np.pi / 180
+        cars.append(np.stack([x, y, v, p], axis=1))
+        # zero-input roll-outs: v and psi stay constant, rk3 advances the position by (a1 + 4 a2 + a3)/6 per step
+        xys = []
+        for q0 in (cars[0], cars[1], np.zeros_like(cars[2])):
+            a = np.stack([h * q0[:, 2] * np.cos(q0[:, 3]), h * q0[:, 2] * np.sin(q0[:, 3])], axis=1)
+            inc = (a + 4 * a + a) / 6
+            xys.append(q0[:, None, :2] + np.arange(N + 1)[None, :, None] * inc[:, None, :])
+        ok = _collision_free(xys, list(game.obs_r))
+        acc = np.hstack(cars)[ok]
+        out.append(acc)
+        have += len(acc)
+    x0 = np.ascontiguousarray(np.vstack(out)[:B])
+    return x0, np.zeros((B, game.n))

@@ -16,7 +16,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import _abi
-from .games import RacingGame, params_to_struct, params_v2_to_struct, NQA, NUA
+from .games import RacingGame, MergeGame, params_to_struct, params_v2_to_struct, NUA
 from .solver_types import DGSQPParams, DGSQPV2Params
 from .types import VehicleState, VehiclePrediction
 
@@ -55,7 +55,9 @@ class DGSQP:
         self.M, self.N = game.M, game.N
         self.n_u, self.n_q = game.n_u, game.n_q
         self.n_c = game.n_c
-        self.num_qa_d = [NQA] * self.M
+        self.merge = isinstance(game, MergeGame)         # merge scenario (unicycles) instead of a racing game (bicycles)
+        self.nqa = game.n_q // game.M
+        self.num_qa_d = [self.nqa] * self.M
         self.num_ua_d = [NUA] * self.M
         self.num_ua_el = [self.N * NUA] * self.M
         self.solver_name = params.solver_name
@@ -65,10 +67,11 @@ class DGSQP:
         self._h = C.c_void_p()
         if self.v2:
             ps = params_v2_to_struct(params)
-            _abi.check(self._lib.dgsqp_create_v2(C.byref(gs), C.byref(ps), int(device), C.byref(self._h)))
+            create = self._lib.dgsqp_create_merge_v2 if self.merge else self._lib.dgsqp_create_v2
         else:
             ps = params_to_struct(params)
-            _abi.check(self._lib.dgsqp_create(C.byref(gs), C.byref(ps), int(device), C.byref(self._h)))
+            create = self._lib.dgsqp_create_merge if self.merge else self._lib.dgsqp_create
+        _abi.check(create(C.byref(gs), C.byref(ps), int(device), C.byref(self._h)))
         dims = (C.c_int32 * 4)()
         _abi.check(self._lib.dgsqp_dims(self._h, dims))
         assert (dims[0], dims[1], dims[2], dims[3]) == (game.n_q, game.n_u, game.n, game.m)
@@ -144,6 +147,18 @@ class DGSQP:
         return self.state_input_predictions
 
     def _fill_predictions(self, t):
+        if self.merge:
+            # CasadiKinematicUnicycle.qu2prediction (dynamics_models.py:347-359)
+            for a, pred in enumerate(self.state_input_predictions):
+                q = self.q_pred[:, 4 * a:4 * (a + 1)]
+                u = self.u_pred[:, NUA * a:NUA * (a + 1)]
+                for name, col in (("x", 0), ("y", 1), ("v_long", 2), ("psi", 3)):
+                    setattr(pred, name, array.array('d', q[:, col]))
+                pred.u_a = array.array('d', u[:, 0])
+                pred.u_steer = array.array('d', u[:, 1])
+                pred.t = t
+            return
+        NQA = self.nqa
         L_f, L_r = self.game.L_f, self.game.L_r
         for a, pred in enumerate(self.state_input_predictions):
             q = self.q_pred[:, NQA * a:NQA * (a + 1)]

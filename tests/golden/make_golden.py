@@ -3,7 +3,7 @@
 CasADi / OSQP are not importable -- see oracle/__init__.py).  Instances come from the oracle's
 faithful sampler (SciPy RK45 PID roll-outs, seed recorded).
 
-    python tests/golden/make_golden.py [chicane] [curve] [agents3]
+    python tests/golden/make_golden.py [chicane] [curve] [agents3] [chicane_v2] [merge]
 """
 import json
 import pathlib
@@ -19,6 +19,7 @@ from oracle.racing_game import RacingGame                    # noqa: E402
 from oracle.sampler import sample_head_to_head, sample_agents  # noqa: E402
 from oracle.dgsqp_v1 import OracleDGSQP                      # noqa: E402
 from oracle.dgsqp_v2 import OracleDGSQPV2                    # noqa: E402
+from oracle.merge_game import MergeGame, sample_merge        # noqa: E402
 
 OUT = pathlib.Path(__file__).resolve().parent
 
@@ -47,7 +48,12 @@ def make(name, game, sampler, solver_kw, count, seed, regression, cls=OracleDGSQ
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["chicane", "curve", "agents3", "chicane_v2"]
+    which = sys.argv[1:] or ["chicane", "curve", "agents3", "chicane_v2", "merge"]
+    if "merge" in which:
+        # scripts/DGSQP_merge_monte_carlo.py: seed 1, zero warm start, reg = 0; the sampler is sequential in the script's order
+        g = MergeGame(N=20)
+        X0 = iter(sample_merge(32, seed=1, game=g))
+        make("merge_N20_seed1", g, lambda game, rng: (next(X0), np.zeros(game.n)), dict(reg=0.0), 32, 1, [0])
     if "chicane" in which:
         make("chicane_N25_seed0", RacingGame(chicane_track(), M=2, N=25), sample_head_to_head, dict(reg=1e-3), 48, 0,
              [3, 4, 7])

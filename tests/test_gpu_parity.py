@@ -291,3 +291,87 @@ def test_v2_batch_kkt_and_limits():
         dg.DGSQP(game, dg.DGSQPV2Params(N=N, merit_function="sum_obj_l1"), print_method=None)
     with pytest.raises(ValueError):
         dg.DGSQP(game, dg.DGSQPV2Params(N=N, merit_decrease_condition="wolfe"), print_method=None)
+
+
+# ------------------------------------------------------------------ merge scenario (BASELINE config 5)
+def test_merge_vs_golden():
+    """Merge game (three unicycles, RK3, lane half-planes) on device against the oracle's golden results
+    (scripts/DGSQP_merge_monte_carlo.py: seed 1, zero warm start, reg = 0): identical status / iterations / QP counts
+    on every instance, trajectories and costs within 1e-6.  reg = 0 leaves eigenvalues of the QP Hessian at the 1e-10
+    floor (condition ~1e11), so inputs agree to cond * eps ~ 1e-5 and multipliers to 1e-4 (tests/test_merge.py)."""
+    from dgsqp_b200.montecarlo import sample_merge
+    data, meta = _golden("merge_N20_seed1")
+    game, params = dg.merge_game(), dg.merge_params()
+    x0, u_ws = sample_merge(game, 32, seed=1)
+    assert np.array_equal(x0, data["x0"]) and not u_ws.any()
+    solver = dg.DGSQP(game, params, print_method=None)
+    assert solver.memory_plan()["hot_in_smem"]
+    B = x0.shape[0]
+    for l0 in (data["l_init"], None):
+        res = solver.solve_batch(x0, u_ws, l0)
+        same = np.array([res.msg[i] == meta["msg"][i] and int(res.num_iters[i]) == meta["num_iters"][i] for i in range(B)])
+        assert same.mean() >= 0.99, f"identical (status, iters): {same.sum()}/{B}"
+        for i in np.where(same)[0]:
+            assert int(res.qp_solves[i]) == meta["qp_solves"][i]
+            assert _rel(res.x[i], data["x"][i]) < 1e-6 and _rel(res.cost[i], data["cost"][i]) < 1e-6
+            assert _rel(res.u[i], data["u"][i]) < 1e-5 and _rel(res.l[i], data["l"][i]) < 1e-4
+    # both memory placements give the same answer
+    solver.set_smem_limit(16 * 1024)
+    assert not solver.memory_plan()["hot_in_smem"]
+    low = solver.solve_batch(x0, u_ws)
+    assert np.array_equal(low.status, res.status) and np.array_equal(low.num_iters, res.num_iters)
+    assert _rel(low.x, res.x) < 1e-6
+
+
+def test_merge_batch_properties():
+    """4096 merge instances: KKT tolerances at converged points (checked independently with the oracle's derivatives on
+    a sample), x_out is the RK3 rollout of u_out, bitwise run-to-run determinism, batch-position independence, solver
+    class surface for the unicycle states."""
+    from dgsqp_b200.montecarlo import sample_merge
+    from oracle.merge_game import MergeGame
+    game, params = dg.merge_game(), dg.merge_params()
+    B = 4096
+    x0, u_ws = sample_merge(game, B, seed=1)
+    solver = dg.DGSQP(game, params, print_method=None)
+    res = solver.solve_batch(x0, u_ws)
+    assert set(np.unique(res.status)) <= {0, 1, 2, 3, 4}
+    conv = res.status == 0
+    assert conv.mean() > 0.9
+    assert np.all(res.cond[conv] < 1e-3) and np.all(res.l[conv] >= 0)
+    og = MergeGame(N=20)
+    for i in np.where(conv)[0][:4]:
+        Q, q, G, g, x = og.evaluate(res.u[i], res.l[i], x0[i], np.zeros(6), True)
+        assert np.abs(x.ravel() - res.x[i]).max() < 1e-11
+        assert np.abs(q + G.T @ res.l[i]).max() < 1e-3 and g.max() < 1e-3 and np.abs(g * res.l[i]).max() < 1e-3
+        assert np.allclose(og.costs(x, res.u[i], np.zeros(6)), res.cost[i], rtol=1e-12)
+    again = solver.solve_batch(x0, u_ws)
+    bits = lambda a: np.ascontiguousarray(a).view(np.int64)
+    assert np.array_equal(again.status, res.status) and np.array_equal(bits(again.u), bits(res.u))
+    idx = np.array([5, 4000, 77, 2048])
+    sub = solver.solve_batch(x0[idx], u_ws[idx])
+    assert np.array_equal(bits(sub.u), bits(res.u[idx])) and np.array_equal(sub.num_iters, res.num_iters[idx])
+    # reference surface: solve(states) with the unicycle state2q order
+    states = [dg.VehicleState(t=0.0, x=dg.Position(x=x0[0, 4 * a], y=x0[0, 4 * a + 1]),
+                              v=dg.BodyLinearVelocity(v_long=x0[0, 4 * a + 2]),
+                              e=dg.OrientationEuler(psi=x0[0, 4 * a + 3])) for a in range(3)]
+    info = solver.solve(states)
+    assert info["msg"] == res.msg[0] and info["num_iters"] == int(res.num_iters[0])
+    assert solver.q_pred.shape == (21, 12) and solver.u_pred.shape == (20, 6)
+    assert np.array_equal(solver.u_pred, solver.agent_to_stage_major(res.u[:1])[0])
+
+
+def test_small_horizon_games_eigen_scratch():
+    """Games with n < 97 (the eigenvector scratch of nearest_pd is larger than one n x n matrix there): full solves of
+    short-horizon chicane and merge games against the oracle run live."""
+    from dgsqp_b200.montecarlo import sample_merge
+    from oracle.dgsqp_v1 import OracleDGSQP
+    from oracle.merge_game import MergeGame
+    N = 10
+    game, params = dg.merge_game(N=N), dg.merge_params(N)
+    x0, u_ws = sample_merge(game, 6, seed=1)
+    res = dg.DGSQP(game, params, print_method=None).solve_batch(x0, u_ws)
+    orc = OracleDGSQP(MergeGame(N=N), reg=0.0)
+    for i in range(6):
+        r = orc.solve(x0[i], u_ws[i])
+        assert res.msg[i] == r["msg"] and int(res.num_iters[i]) == r["num_iters"]
+        assert _rel(res.x[i], r["x"].ravel()) < 1e-6
