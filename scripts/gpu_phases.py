@@ -11,8 +11,14 @@ from dgsqp_b200.montecarlo import sample_head_to_head
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 threads = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 ctas = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-game, params = dg.chicane_game(), dg.chicane_params()
-x0, u_ws = sample_head_to_head(game, B, seed=0)
+import os
+if os.environ.get("DG_WORKLOAD") == "merge":
+    from dgsqp_b200.montecarlo import sample_merge
+    game, params = dg.merge_game(), dg.merge_params()
+    x0, u_ws = sample_merge(game, B, seed=1)
+else:
+    game, params = dg.chicane_game(), dg.chicane_params()
+    x0, u_ws = sample_head_to_head(game, B, seed=0)
 solver = dg.DGSQP(game, params, print_method=None)
 if threads or ctas:
     solver.configure(ctas, threads)
