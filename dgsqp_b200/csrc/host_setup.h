@@ -74,6 +74,7 @@ static inline int dg_fill_params(const dgsqp_params* p, SolverParams* P) {
   P->t_hat = 5;                    // DGSQP.py:1179
   P->dbg_l0_perturb = 0.0;
   P->mu_vio_thresh = p->mu_vio_thresh;
+  P->merit_obj = 0;
   P->policy = 1; P->nms = 0; P->nms_frequency = 0; P->nms_memory = 1; P->armijo = 1; P->has_merit_parameter = 0;
   P->reg_decay = 1.0; P->sigma = 0.0; P->gamma = 1.0; P->merit_parameter = 0.0;
   return 0;
@@ -82,7 +83,7 @@ static inline int dg_fill_params(const dgsqp_params* p, SolverParams* P) {
 static inline int dg_fill_params_v2(const dgsqp_v2_params* p, SolverParams* P) {
   if (!p || p->line_search_iters < 1 || p->sqp_iters < 1 || !(p->mu_vio_thresh >= 0.0)) return -1;
   if (p->nms_memory_size < 1 || p->nms_memory_size > DG_V2_MEM_MAX || p->nms_frequency < 0) return -1;
-  if (p->merit_function != 0) return -1;                       // 'sum_obj_l1' is not supported (include/dgsqp_b200.h)
+  if (p->merit_function != 0 && p->merit_function != 1) return -1;
   if (p->merit_decrease_condition != 0 && p->merit_decrease_condition != 1) return -1;
   P->reg = p->reg; P->p_tol = p->p_tol; P->d_tol = p->d_tol; P->beta = p->beta; P->tau = p->tau;
   P->eig_floor = 1e-9;             // DGSQP_v2.py:1273
@@ -94,6 +95,7 @@ static inline int dg_fill_params_v2(const dgsqp_v2_params* p, SolverParams* P) {
   P->t_hat = 0;
   P->dbg_l0_perturb = 0.0;
   P->mu_vio_thresh = p->mu_vio_thresh;
+  P->merit_obj = p->merit_function == 1;
   P->policy = 2; P->nms = p->nms != 0; P->nms_frequency = p->nms_frequency; P->nms_memory = p->nms_memory_size;
   P->armijo = p->merit_decrease_condition == 0; P->has_merit_parameter = p->has_merit_parameter != 0;
   P->reg_decay = p->reg_decay; P->sigma = p->merit_decrease; P->gamma = p->delta_decay; P->merit_parameter = p->merit_parameter;

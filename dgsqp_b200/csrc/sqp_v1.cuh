@@ -20,6 +20,7 @@ struct SolverParams {
   int line_search_iters, sqp_iters, nonmono_ls, merit_l1, conv_approx, rel_tol_req, t_hat;
   // v2 step policy (DGSQPV2Params, DGSQP_v2.py:55-230); policy = 1: v1 (sqp_v1.cuh), 2: v2 (sqp_v2.cuh)
   int policy, nms, nms_frequency, nms_memory, armijo, has_merit_parameter;
+  int merit_obj;           // v2 merit 'sum_obj_l1' (sum of the agents' costs) instead of 'stat_l1'
   double reg_decay, sigma, gamma, merit_parameter;
 };
 
@@ -97,7 +98,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   // ---- SQP iterate vectors, hottest first
   PLACE(W.S.u, n); PLACE(W.S.du, n); PLACE(W.S.l, m); PLACE(W.S.dl, m); PLACE(W.Q.lam, m);
   PLACE(W.S.u_c, n); PLACE(W.S.l_c, m); PLACE(W.S.s, m); PLACE(W.S.ds, m); PLACE(W.S.Gdu, m);
-  PLACE(W.S.tn, n); PLACE(W.S.tn2, n);
+  PLACE(W.S.tn, n); PLACE(W.S.tn2, n); PLACE(W.E.qs, n);
   // ---- global only
   GTAKE(W.E.Q, n * n); GTAKE(W.B.Zg, n * n);
   { double* t; GTAKE(t, (m + 1) / 2 + 1); W.E.rowtab = (int*)t; }
@@ -145,7 +146,7 @@ DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l_in)
   game_sens<SM>(c, D, E);
   c.sync();
   game_contract<SM>(c, D, E);
-  game_gradients<SM>(c, *X.G, D, E, u, X.W.S.up, l);
+  game_gradients<SM>(c, *X.G, D, E, u, X.W.S.up, l, X.P->merit_obj != 0);
   c.sync();
   c.lap(PH_ADJ_FULL);
   game_hessian<SM>(c, *X.G, D, E, l);
@@ -170,7 +171,7 @@ DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l_in,
   game_costates<SM>(c, *X.G, D, E, l);
   if (with_sens) game_sens<SM>(c, D, E);
   c.sync();
-  game_gradients<SM>(c, *X.G, D, E, u, X.W.S.up, l);
+  game_gradients<SM>(c, *X.G, D, E, u, X.W.S.up, l, X.P->merit_obj != 0);
   c.sync();
   c.lap(PH_ADJ_GRAD);
   if (c.tid() == 0) ++X.n_evals_grad;

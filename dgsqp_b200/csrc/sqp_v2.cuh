@@ -14,15 +14,23 @@
 
 #define DG_V2_MEM_MAX 16
 
-// merit pieces at the currently evaluated point: |q + G'l|^2 and sum(max(0, g))
+// merit pieces at the currently evaluated point (inputs u): the smooth part -- 1/2 |q + G'l|^2 for 'stat_l1', the sum
+// of the agents' costs for 'sum_obj_l1' (:1143-1151) -- and sum(max(0, g))
 template <bool SM>
-DG_DEVN void v2_point_terms(Cta& c, SolveCtx& X, double& dd, double& vio) {
+DG_DEVN void v2_point_terms(Cta& c, SolveCtx& X, const double* u, double& base, double& vio) {
   const Dims D = X.D; const EvalBuf E = X.W.E; DG_SH_EVAL(E);
   double p1 = 0.0, p2 = 0.0;
-  DG_FOR(i, D.n) { double d = E.q[i] + E.gtl[i]; p1 += d * d; }
+  if (X.P->merit_obj) {
+    c.sync();
+    game_costs<SM>(c, *X.G, D, u, X.W.S.up, E.x, E.cf);         // cf: scratch of the G' products, dead here
+    c.sync();
+    if (c.tid() == 0) for (int a = 0; a < D.M; ++a) p1 += E.cf[a];
+  } else {
+    DG_FOR(i, D.n) { double d = E.q[i] + E.gtl[i]; p1 += 0.5 * d * d; }
+  }
   DG_FOR(r, D.m) { double gv = E.g[r]; p2 += gv > 0.0 ? gv : 0.0; }
   c.sum2(p1, p2);
-  dd = p1; vio = p2;
+  base = p1; vio = p2;
   c.lap(PH_MERIT);
 }
 
@@ -31,6 +39,14 @@ template <bool SM>
 DG_DEVN double v2_dstat(Cta& c, SolveCtx& X, const double* du, const double* dl) {
   const Dims D = X.D; const EvalBuf E = X.W.E; DG_SH_EVAL(E); const SqpBuf S = X.W.S;
   const int n = D.n;
+  if (X.P->merit_obj) {
+    // d(sum of costs) along du (:1150-1151); the multipliers do not enter
+    double p = 0.0;
+    DG_FOR(i, n) p += E.qs[i] * du[i];
+    p = c.sum(p);
+    c.lap(PH_MERIT);
+    return p;
+  }
   game_GT_times<SM>(c, D, E, dl, S.tn2);
   for (int i = c.warp(); i < n; i += c.nwarps()) {
     const double* DG_RESTRICT Qi = E.Q + (size_t)i * n;
@@ -78,12 +94,12 @@ DG_DEVN double v2_line_search(Cta& c, SolveCtx& X, double mu, double mem_max) {
   double phi0 = 0.0, dphi0 = 0.0;
   if (P.armijo) {
     eval_full<SM>(c, X, S.u, S.l);
-    double dd, vio0;
-    v2_point_terms<SM>(c, X, dd, vio0);
+    double base0, vio0;
+    v2_point_terms<SM>(c, X, S.u, base0, vio0);
     double ssum = 0.0;
     DG_FOR(r, D.m) ssum += S.s[r];
     ssum = c.sum(ssum);
-    phi0 = 0.5 * dd + mu * ssum;
+    phi0 = base0 + mu * ssum;
     dphi0 = v2_dstat<SM>(c, X, S.du, S.dl) - mu * vio0;
   }
   double a = 1.0, phi1 = 0.0;
@@ -93,11 +109,11 @@ DG_DEVN double v2_line_search(Cta& c, SolveCtx& X, double mu, double mem_max) {
     DG_FOR(r, D.m) S.l_c[r] = S.l[r] + a * S.dl[r];
     eval_grad<SM>(c, X, S.u_c, S.l_c, false);
     if (c.tid() == 0) ++X.n_ls_trials;
-    double dd, vio;
-    v2_point_terms<SM>(c, X, dd, vio);
-    phi1 = 0.5 * dd + vio;
+    double base, vio;
+    v2_point_terms<SM>(c, X, S.u_c, base, vio);
+    phi1 = base + vio;
     const double ref = P.armijo ? phi0 + P.sigma * a * dphi0 : (1.0 - P.sigma * a) * mem_max;
-    if (0.5 * dd + mu * vio <= ref) break;
+    if (base + mu * vio <= ref) break;
     a *= P.tau;
   }
   return phi1;
@@ -133,9 +149,9 @@ DG_DEVN void sqp_solve_v2(Cta& c, SolveCtx& X, const double* u_ws, const double*
   {
     // phi(u, l0) needs G'l0: gradient-only evaluation at (u, l0)
     eval_grad<SM>(c, X, S.u, S.l, false);
-    double dd, vio;
-    v2_point_terms<SM>(c, X, dd, vio);
-    mem[0] = 0.5 * dd + vio; mem_len = 1; mem_pos = 1 % mem_cap;
+    double base, vio;
+    v2_point_terms<SM>(c, X, S.u, base, vio);
+    mem[0] = base + vio; mem_len = 1; mem_pos = 1 % mem_cap;
   }
   c.sync();
   vcopy<SM>(c, n, S.u_im1, S.u); vcopy<SM>(c, m, S.l_im1, S.l);
@@ -217,9 +233,9 @@ DG_DEVN void sqp_solve_v2(Cta& c, SolveCtx& X, const double* u_ws, const double*
       DG_FOR(j, n) S.u_c[j] = S.u[j] + S.du[j];
       DG_FOR(r, m) S.l_c[r] = S.l[r] + S.dl[r];
       eval_grad<SM>(c, X, S.u_c, S.l_c, false);
-      double dd, vio;
-      v2_point_terms<SM>(c, X, dd, vio);
-      phi = 0.5 * dd + vio;
+      double base, vio;
+      v2_point_terms<SM>(c, X, S.u_c, base, vio);
+      phi = base + vio;
       double mem_max = mem[0];
       for (int t = 1; t < mem_len; ++t) mem_max = fmax(mem_max, mem[t]);
       if (!(phi <= (1.0 - P.sigma) * mem_max)) {

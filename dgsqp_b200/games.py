@@ -255,10 +255,7 @@ def params_to_struct(params, mu_vio_thresh=MU_VIO_THRESH):
 def params_v2_to_struct(params, mu_vio_thresh=MU_VIO_THRESH):
     """DGSQPV2Params -> dgsqp_v2_params.  Unknown option strings raise like the reference (DGSQP_v2.py:1162-1163)."""
     from ._abi import ParamsV2Struct
-    if params.merit_function == "sum_obj_l1":
-        raise NotImplementedError("merit function 'sum_obj_l1' needs the gradient of the summed costs, which the "
-                                  "condensed game evaluation does not produce; use 'stat_l1'")
-    if params.merit_function != "stat_l1":
+    if params.merit_function not in ("stat_l1", "sum_obj_l1"):
         raise ValueError(f"Merit function option {params.merit_function} not recognized")
     if params.merit_decrease_condition not in ("armijo", "max"):
         raise ValueError(f"Merit decrease condition {params.merit_decrease_condition} not recognized")
@@ -269,7 +266,7 @@ def params_v2_to_struct(params, mu_vio_thresh=MU_VIO_THRESH):
                                                           params.beta, params.tau)
     p.line_search_iters, p.sqp_iters = params.line_search_iters, params.sqp_iters
     p.nms, p.nms_frequency, p.nms_memory_size = int(bool(params.nms)), params.nms_frequency, params.nms_memory_size
-    p.merit_function = 0
+    p.merit_function = 0 if params.merit_function == "stat_l1" else 1
     p.has_merit_parameter = int(params.merit_parameter is not None)
     p.merit_parameter = 0.0 if params.merit_parameter is None else float(params.merit_parameter)
     p.merit_decrease = params.merit_decrease

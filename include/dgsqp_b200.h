@@ -122,7 +122,7 @@ typedef struct {
   int32_t line_search_iters;
   int32_t sqp_iters;                /* counted in m-steps (DGSQP_v2.py:407) */
   int32_t nms, nms_frequency, nms_memory_size;   /* memory size 1..16 */
-  int32_t merit_function;           /* 0 = 'stat_l1'; 'sum_obj_l1' is not supported (needs the gradient of the summed costs) */
+  int32_t merit_function;           /* 0 = 'stat_l1', 1 = 'sum_obj_l1' (DGSQP_v2.py:1157-1164) */
   int32_t has_merit_parameter;      /* 0: mu from _get_mu (:683-707), 1: constant merit_parameter */
   double merit_parameter;
   double merit_decrease;            /* sigma */

@@ -14,8 +14,10 @@ slack ``s = max(0, g)`` handed in by the caller; ``dphi = stat' (Q du + G' dl) -
 w.r.t. ``u`` is exactly the row-stacked game Hessian ``Q`` and w.r.t. ``l`` it is ``G'``).
 
 Deviations (same as the v1 oracle): exact QP instead of OSQP (D1), ``mu_vio_thresh`` (D2),
-re-orthogonalised LSQR dual initialisation (D3), no wall-clock ``time_limit``.  The 'sum_obj_l1' merit needs the
-gradient of the SUM of all agents' costs, which the condensed game evaluation does not produce: not supported.
+re-orthogonalised LSQR dual initialisation (D3), no wall-clock ``time_limit``.
+
+Merit 'sum_obj_l1' (:1149-1151,1161-1164): ``phi = sum_a J^a(u) + mu * sum(s)``, ``dphi = grad_u(sum_a J^a)' du -
+mu * sum(s)``; the games keep both quantities of the last evaluated point (``last_obj``, ``last_qs``).
 """
 from collections import deque
 
@@ -30,13 +32,14 @@ class OracleDGSQPV2(OracleDGSQP):
                  nms_memory_size=3, sqp_iters=500, p_tol=1e-4, d_tol=1e-4, beta=0.25, tau=0.5,
                  merit_function="stat_l1", merit_parameter=None, merit_decrease=0.01,
                  merit_decrease_condition="armijo", delta_decay=0.95, mu_vio_thresh=1e-10, dual_init_method="reorth"):
-        if merit_function != "stat_l1":
-            raise ValueError(f"Merit function option {merit_function} not supported by the oracle")
+        if merit_function not in ("stat_l1", "sum_obj_l1"):
+            raise ValueError(f"Merit function option {merit_function} not recognized")
         if merit_decrease_condition not in ("armijo", "max"):
             raise ValueError(f"Merit decrease condition {merit_decrease_condition} not recognized")
         super().__init__(game, reg=reg, line_search_iters=line_search_iters, sqp_iters=sqp_iters, p_tol=p_tol, d_tol=d_tol,
-                         beta=beta, tau=tau, merit_function=merit_function, mu_vio_thresh=mu_vio_thresh,
+                         beta=beta, tau=tau, merit_function="stat_l1", mu_vio_thresh=mu_vio_thresh,
                          dual_init_method=dual_init_method)
+        self.merit_obj = merit_function == "sum_obj_l1"
         self.reg_init, self.reg_decay = reg, reg_decay
         self.nms, self.nms_mstep_frequency, self.nms_memory_size = nms, nms_frequency, nms_memory_size
         self.merit_parameter, self.sigma, self.gamma = merit_parameter, merit_decrease, delta_decay
@@ -57,13 +60,17 @@ class OracleDGSQPV2(OracleDGSQP):
             return None, None
         return du, l_hat - l
 
-    @staticmethod
-    def _phi2(l, s, q, G, mu):
+    def _phi2(self, l, s, q, G, mu):
+        """f_phi at the point the game was evaluated at last (every call site follows that evaluation)."""
+        if self.merit_obj:
+            return self.game.last_obj + mu * np.sum(s)
         stat = q + G.T @ l
         return 0.5 * (stat @ stat) + mu * np.sum(s)
 
-    @staticmethod
-    def _dstat2(du, l, dl, Q, q, G):
+    def _dstat2(self, du, l, dl, Q, q, G):
+        """f_dphi_c: directional derivative of the merit's smooth part along (du, dl)."""
+        if self.merit_obj:
+            return float(self.game.last_qs @ du)
         return (q + G.T @ l) @ (Q @ du + G.T @ dl)
 
     def _get_mu2(self, du, l, dl, s, Q, q, G):

@@ -259,6 +259,15 @@ class MergeGame:
             q[sl] = ga
         return q
 
+    def sum_cost_gradient(self, x, u, up, S):
+        """grad_u sum_a J^a (the `dobj` of the v2 merit 'sum_obj_l1', DGSQP_v2.py:1150-1151)."""
+        N = self.N
+        lx = sum(self._cost_lx_lxx(x, f)[0] for f in range(self.M))
+        qs = np.tile(self.w_u, N * self.M) * u
+        for k in range(1, N + 1):
+            qs = qs + lx[k] @ S[k]
+        return qs
+
     # ------------------------------------------------------------- Hessian Q
     def _dp_hessian(self, A, B, T, lx, lxx, luu):
         """Hessian wrt the stage-major joint input sequence of Phi(u) = sum_k [l_k(x_k) + 1/2 u_k' luu u_k]
@@ -302,6 +311,8 @@ class MergeGame:
         g = self.constraints(x, u, up)
         G = self.constraint_jacobian(x, S)
         q = self.cost_gradient(x, u, up, S)
+        # kept for the v2 merit 'sum_obj_l1' (sum of the costs and its gradient at the evaluated point)
+        self.last_obj, self.last_qs = float(np.sum(self.costs(x, u, up))), self.sum_cost_gradient(x, u, up, S)
         if hessian:
             return self.hessian(x, u, l, A, B, T), q, G, g, x
         return q, G, g, x

@@ -297,6 +297,19 @@ class RacingGame:
             q[sl] = ga.ravel() + gx @ S[N][:, sl]
         return q
 
+    def sum_cost_gradient(self, x, u, up, S):
+        """grad_u sum_a J^a (the `dobj` of the v2 merit 'sum_obj_l1', DGSQP_v2.py:1150-1151): agent a's inputs enter
+        its own stage costs directly and every agent's terminal cost through the states."""
+        N, M = self.N, self.M
+        qs = self.cost_gradient(x, u, up, S)
+        for a in range(M):
+            sl = slice(a * N * NUA, (a + 1) * N * NUA)
+            for f in range(M):
+                if f != a:
+                    gx, _ = self._term_grad_hess(x[N], f)
+                    qs[sl] += gx @ S[N][:, sl]
+        return qs
+
     # ------------------------------------------------------------- Hessian Q
     def _dp_hessian(self, Aa, Ba, H, lx, lxx, luu, luu2):
         """Backward dynamic-programming Hessian of  Phi(u) = sum_k l_k(x_k,u_k,u_{k-1}) + l_N(x_N)
@@ -368,6 +381,8 @@ class RacingGame:
         g = self.constraints(x, u, up)
         G = self.constraint_jacobian(x, S)
         q = self.cost_gradient(x, u, up, S)
+        # kept for the v2 merit 'sum_obj_l1' (sum of the costs and its gradient at the evaluated point)
+        self.last_obj, self.last_qs = float(np.sum(self.costs(x, u, up))), self.sum_cost_gradient(x, u, up, S)
         if hessian:
             Q = self.hessian(x, u, l, Aa, Ba, H)
             return Q, q, G, g, x

@@ -287,8 +287,8 @@ def test_v2_batch_kkt_and_limits():
     assert np.all(res.cond[conv, 2] < params.d_tol)
     d = solver.last_diag(512)
     assert np.all(d[res.status == 2, 6] == params.sqp_iters) and np.all(d[:, 6] <= params.sqp_iters)
-    with pytest.raises(NotImplementedError):
-        dg.DGSQP(game, dg.DGSQPV2Params(N=N, merit_function="sum_obj_l1"), print_method=None)
+    with pytest.raises(ValueError):
+        dg.DGSQP(game, dg.DGSQPV2Params(N=N, merit_function="sum_obj"), print_method=None)
     with pytest.raises(ValueError):
         dg.DGSQP(game, dg.DGSQPV2Params(N=N, merit_decrease_condition="wolfe"), print_method=None)
 
