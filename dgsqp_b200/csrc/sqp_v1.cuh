@@ -37,7 +37,7 @@ struct SqpBuf {
 
 struct Workspace { EvalBuf E; LinBuf B; QpBuf Q; LsqrBuf L; SqpBuf S; };
 
-struct MemPlan { size_t smem, gmem; int mats_in_smem, sens_in_smem, hot_in_smem; };   // doubles used in each space
+struct MemPlan { size_t smem, gmem; int mats_in_smem, matA_in_smem, sens_in_smem, hot_in_smem; };   // doubles used in each space
 
 // Memory plan of one CTA (= one game instance in flight).  Everything a latency-bound phase walks through
 // lives in shared memory when it fits (budget `sbudget` doubles), the rest in the CTA's slice of global
@@ -76,23 +76,45 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   PLACE(W.B.part, (n > DG_PART_SZ ? n : DG_PART_SZ));
   { double* t; PLACE(t, (n + 1) / 2 + 1); W.Q.act = (int*)t; PLACE(t, (m + 1) / 2 + 1); W.Q.is_act = (int*)t; }
   const bool pool_ok = go == 0;                 // nothing of the pool fell back to global memory
-  // ---- ARENA
-  const size_t ev_a = rnd(N * M * DG_AB_SZ) + rnd((M + 1) * (N + 1) * nq) + rnd((M + 1) * N * M * DG_HC_SZ) + rnd(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq) +
-                      rnd((M + 1) * nq * n) + rnd(N * M * DG_T2_SZ) + rnd(m);
+  // ---- ARENA: matA | matB.  Three placements: both matrices in shared memory; matA alone (split: matA carries the
+  // latency-critical work -- reflectors, Cholesky factor, the triangular factor R of the active-set loop -- while matB
+  // (eigenvector scratch, J' of the QP) is streamed with coalesced CTA-wide sweeps from the L2-resident workspace);
+  // or both in the global workspace.
+  const size_t ev_sz[7] = {rnd(N * M * DG_AB_SZ), rnd((M + 1) * (N + 1) * nq), rnd((M + 1) * N * M * DG_HC_SZ),
+                           rnd(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq), rnd((M + 1) * nq * n), rnd(N * M * DG_T2_SZ), rnd(m)};
+  size_t ev_a = 0;
+  for (int i = 0; i < 7; ++i) ev_a += ev_sz[i];
   // matB doubles as the scratch of the eigenvector stage of nearest_pd (Sturm counters, DG_EIG_CHUNK interleaved
   // inverse-iteration work vectors and iterates: (n+1)/2+1 + 6 n DG_EIG_CHUNK doubles), which exceeds n*ld below n ~ 97
   const size_t eig_scr = rnd((n + 1) / 2 + 1 + 6 * n * DG_EIG_CHUNK);
-  const size_t mats = rnd(n * ld) + (rnd(n * ld) > eig_scr ? rnd(n * ld) : eig_scr);
-  const size_t arena = ev_a > mats ? ev_a : mats;
-  double* ar = nullptr;
-  if (so + arena <= sbudget) { STAKE(ar, arena); P.mats_in_smem = 1; } else GTAKE(ar, arena);
-  {
+  const size_t szA = rnd(n * ld);
+  size_t szB = rnd(n * ld) > eig_scr ? rnd(n * ld) : eig_scr;
+  if (szA + szB < ev_a) szB = ev_a - szA;
+  double *arA = nullptr, *arB = nullptr;
+  double** ev_ptr[7] = {&W.E.AB, &W.E.cst, &W.E.Hc, &W.E.Vbuf, &W.E.Wrow, &W.E.T2, &W.E.lbuf};
+  P.matA_in_smem = 0;
+  // (the split is only taken when the sensitivity rows still fit beside matA: every active-set iteration walks them)
+  if (so + szA + szB <= sbudget || so + szA + rnd(M * D.sens_sz) > sbudget) {
+    // one block: the evaluation data is carved from its start (no matrix is alive while the game is evaluated)
+    if (so + szA + szB <= sbudget) { STAKE(arA, szA + szB); P.mats_in_smem = 1; P.matA_in_smem = 1; } else GTAKE(arA, szA + szB);
+    arB = arA ? arA + szA : nullptr;
     size_t o = 0;
-    auto sub = [&](size_t cnt) { double* r = ar ? ar + o : nullptr; o += rnd(cnt); return r; };
-    W.E.AB = sub(N * M * DG_AB_SZ); W.E.cst = sub((M + 1) * (N + 1) * nq); W.E.Hc = sub((M + 1) * N * M * DG_HC_SZ);
-    W.E.Vbuf = sub(2 * (M + 1) * nq * nq + (M + 1) * D.nu * nq); W.E.Wrow = sub((M + 1) * nq * n); W.E.T2 = sub(N * M * DG_T2_SZ); W.E.lbuf = sub(m);
-    W.B.ld = (int)ld; W.B.matA = ar; W.B.matB = ar ? ar + rnd(n * ld) : nullptr;
+    for (int i = 0; i < 7; ++i) { *ev_ptr[i] = arA ? arA + o : nullptr; o += ev_sz[i]; }
+  } else {
+    // split: the evaluation buffers may not straddle the two spaces; small serial-chain data first into matA's block
+    const int order[7] = {0, 1, 2, 3, 6, 5, 4};
+    size_t oa = 0, ob = 0;
+    for (int t = 0; t < 7; ++t) { const int i = order[t]; if (oa + ev_sz[i] <= szA) oa += ev_sz[i]; else ob += ev_sz[i]; }
+    if (ob > szB) szB = ob;
+    STAKE(arA, szA); GTAKE(arB, szB); P.matA_in_smem = 1;
+    oa = ob = 0;
+    for (int t = 0; t < 7; ++t) {
+      const int i = order[t];
+      if (oa + ev_sz[i] <= szA) { *ev_ptr[i] = arA ? arA + oa : nullptr; oa += ev_sz[i]; }
+      else { *ev_ptr[i] = arB ? arB + ob : nullptr; ob += ev_sz[i]; }
+    }
   }
+  W.B.ld = (int)ld; W.B.matA = arA; W.B.matB = arB;
   // ---- SENS
   if (so + rnd(M * D.sens_sz) <= sbudget) { STAKE(W.E.S, M * D.sens_sz); P.sens_in_smem = 1; } else GTAKE(W.E.S, M * D.sens_sz);
   // ---- SQP iterate vectors, hottest first

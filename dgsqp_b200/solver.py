@@ -260,7 +260,8 @@ class DGSQP:
         """dict(smem_bytes, gmem_bytes, mats_in_smem, sens_in_smem) of one CTA."""
         o = (C.c_int64 * 4)()
         _abi.check(self._lib.dgsqp_memory_plan(self._h, o))
-        return dict(smem_bytes=int(o[0]), gmem_bytes=int(o[1]), mats_in_smem=bool(o[2]), sens_in_smem=bool(o[3] & 1), hot_in_smem=bool(o[3] & 2))
+        return dict(smem_bytes=int(o[0]), gmem_bytes=int(o[1]), mats_in_smem=bool(o[2]), sens_in_smem=bool(o[3] & 1), hot_in_smem=bool(o[3] & 2),
+                    matA_in_smem=bool(o[3] & 4))
 
     def set_smem_limit(self, nbytes):
         _abi.check(self._lib.dgsqp_set_smem_limit(self._h, int(nbytes)))

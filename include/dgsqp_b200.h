@@ -195,8 +195,8 @@ int dgsqp_measure_fp64_peak(int device, double* tflops);
 int64_t dgsqp_kernel_launches(void);
 
 /* Memory placement of one CTA (one game instance in flight): out[0] = dynamic shared memory bytes, out[1] = global
- * workspace bytes, out[2] = 1 when the two n x n work matrices are shared-memory resident, out[3] = 1 when the packed
- * sensitivity rows are.  dgsqp_set_smem_limit caps the shared memory the planner may use (0 = device maximum);
+ * workspace bytes, out[2] = 1 when the two n x n work matrices are shared-memory resident, out[3] = bit 0: the packed
+ * sensitivity rows are, bit 1: every hot buffer is, bit 2: the first work matrix (factors) is.  dgsqp_set_smem_limit caps the shared memory the planner may use (0 = device maximum);
  * with a small cap everything falls back to the global workspace (used by the tests to cover both placements). */
 int dgsqp_memory_plan(const dgsqp_handle* h, int64_t out[4]);
 int dgsqp_set_smem_limit(dgsqp_handle* h, int64_t bytes);

@@ -377,3 +377,27 @@ def test_small_horizon_games_eigen_scratch():
         r = orc.solve(x0[i], u_ws[i])
         assert res.msg[i] == r["msg"] and int(res.num_iters[i]) == r["num_iters"]
         assert _rel(res.x[i], r["x"].ravel()) < 1e-6
+
+
+def test_v2_sum_obj_merit_live_oracle():
+    """v2 merit 'sum_obj_l1' on device against the oracle run live (nms = False: every iteration line-searches the
+    summed costs; and the default non-monotone policy), short-horizon chicane and merge games."""
+    from dgsqp_b200.montecarlo import sample_merge
+    from oracle.dgsqp_v2 import OracleDGSQPV2
+    from oracle.merge_game import MergeGame
+    from oracle.racing_game import RacingGame
+    from oracle.track import chicane_track
+    N = 10
+    cases = [(dg.chicane_game(N=N), RacingGame(chicane_track(), M=2, N=N), sample_head_to_head(dg.chicane_game(N=N), 4, seed=2)),
+             (dg.merge_game(N=N), MergeGame(N=N), sample_merge(dg.merge_game(N=N), 4, seed=1))]
+    for kw in (dict(reg=1e-3, reg_decay=0.9, nms=False, sqp_iters=30, merit_decrease=0.3, merit_function="sum_obj_l1"),
+               dict(reg=1e-1, reg_decay=0.8, nms_frequency=2, sqp_iters=40, merit_function="sum_obj_l1")):
+        for game, og, (x0, u_ws) in cases:
+            res = dg.DGSQP(game, dg.DGSQPV2Params(N=N, **kw), print_method=None).solve_batch(x0, u_ws)
+            sol = OracleDGSQPV2(og, **kw)
+            for i in range(x0.shape[0]):
+                r = sol.solve(x0[i], u_ws[i])
+                assert res.msg[i] == r["msg"] and int(res.num_iters[i]) == r["num_iters"]
+                assert int(res.qp_solves[i]) == r["qp_solves"]
+                if r["status"]:
+                    assert _rel(res.u[i], r["u"]) < 1e-6 and _rel(res.x[i], r["x"].ravel()) < 1e-6

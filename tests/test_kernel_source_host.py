@@ -173,6 +173,30 @@ def test_v2_policy_matches_oracle_and_golden():
         assert np.abs(h["u"] - data["u"][i]).max() < 1e-8
 
 
+def test_v2_sum_obj_merit_matches_oracle():
+    """v2 merit 'sum_obj_l1' (DGSQP_v2.py:1149-1151,1161-1164) in the kernel source against the oracle: with the
+    non-monotone policy (m-steps against the merit memory) and with nms = False, where every iteration runs the
+    Armijo line search on phi = sum_a J^a + mu sum(s)."""
+    from oracle.dgsqp_v2 import OracleDGSQPV2
+    from oracle.sampler import sample_head_to_head
+    N = 10
+    game, og = dg.chicane_game(N=N), RacingGame(chicane_track(), M=2, N=N)
+    ls_total = 0
+    for kw in (dict(reg=1e-3, reg_decay=0.9, nms=False, sqp_iters=30, merit_decrease=0.3, merit_function="sum_obj_l1"),
+               dict(reg=1e-1, reg_decay=0.8, nms_frequency=2, sqp_iters=40, merit_function="sum_obj_l1",
+                    merit_decrease_condition="max")):
+        hs, sol = HostSim(game, dg.DGSQPV2Params(N=N, **kw)), OracleDGSQPV2(og, **kw)
+        rng = np.random.default_rng(1)
+        for i in range(3):
+            x0, u_ws = sample_head_to_head(og, rng)
+            r, h = sol.solve(x0, u_ws), hs.solve(x0, u_ws)
+            assert MSG[h["status"]] == r["msg"] and h["num_iters"] == r["num_iters"] and h["qp_solves"] == r["qp_solves"]
+            assert h["diag"][7] == sol.n_ls_evals
+            ls_total += sol.n_ls_evals
+            assert np.abs(h["u"] - r["u"]).max() < 1e-9 and np.abs(h["l"] - r["l"]).max() < 1e-8
+    assert ls_total > 0            # the line search on the summed costs was exercised
+
+
 def test_kernel_source_under_asan_ubsan():
     """One evaluate + nearestPD + QP + short solve of the kernel source under AddressSanitizer / UBSan
     (separate process: the sanitizer runtime has to be preloaded)."""

@@ -120,13 +120,21 @@ def test_v2_merit_directional_derivative(chicane_small):
     up = np.zeros(og.n_u)
     Q, q, G, g, _ = og.evaluate(u, l, x0, up, True)
     du, dl = rng.normal(size=og.n) * 0.1, rng.normal(size=og.m) * 0.1
-    d0 = OracleDGSQPV2._dstat2(du, l, dl, Q, q, G)
+    sol = OracleDGSQPV2(og)
+    d0 = sol._dstat2(du, l, dl, Q, q, G)
 
-    def phi(a):
+    def phi(a, s=sol):
         q2, G2, _, _ = og.evaluate(u + a * du, l + a * dl, x0, up, False)
-        return OracleDGSQPV2._phi2(l + a * dl, np.zeros(og.m), q2, G2, 0.0)
+        return s._phi2(l + a * dl, np.zeros(og.m), q2, G2, 0.0)
     h = 1e-6
     assert abs((phi(h) - phi(-h)) / (2 * h) - d0) < 1e-5 * max(1.0, abs(d0))
+    # 'sum_obj_l1' (:1149-1151): the smooth part is the sum of the agents' costs, its derivative grad_u(sum J)'du
+    so = OracleDGSQPV2(og, merit_function="sum_obj_l1")
+    og.evaluate(u, l, x0, up, True)
+    d1 = so._dstat2(du, l, dl, Q, q, G)
+    assert abs((phi(h, so) - phi(-h, so)) / (2 * h) - d1) < 1e-6 * max(1.0, abs(d1))
+    x = og.rollout(u, x0)
+    assert np.isclose(phi(0.0, so), np.sum(og.costs(x, u, up)), rtol=1e-14)
 
 
 def test_v2_solve_properties_and_golden():
