@@ -116,7 +116,26 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
       if (++it > max_iter) { status = 3; break; }
       // d = J' n_p = -Y npv   (2D over the CTA: thread = row of Y, column groups interleave the columns);  also npv . x
       double dd_tail = 0.0, dd_all = 0.0, gx = 0.0;
-      {
+      if constexpr (!SM) {
+        // Y in the L2-resident workspace: warp per row, lanes along the row (coalesced), four independent loads per lane
+        for (int j = c.warp(); j < n; j += c.nwarps()) {
+          const double* DG_RESTRICT Yj = Y + j * ld;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          int i = c.lane();
+          for (; i + 3 * c.wsz < n; i += 4 * c.wsz) {
+            const double y0 = Yj[i], y1 = Yj[i + c.wsz], y2 = Yj[i + 2 * c.wsz], y3 = Yj[i + 3 * c.wsz];
+            a0 += y0 * Q.npv[i]; a1 += y1 * Q.npv[i + c.wsz]; a2 += y2 * Q.npv[i + 2 * c.wsz]; a3 += y3 * Q.npv[i + 3 * c.wsz];
+          }
+          for (; i < n; i += c.wsz) a0 += Yj[i] * Q.npv[i];
+          double acc = c.warp_sum((a0 + a1) + (a2 + a3));
+          if (c.lane() == 0) {
+            acc = -acc;
+            Q.dv[j] = acc;
+            dd_all += acc * acc;
+            if (j >= iq) dd_tail += acc * acc;
+          }
+        }
+      } else {
         for (int j = sp.i0; j < n; j += sp.istep) {
           const double* DG_RESTRICT Yj = Y + j * ld;
           double a0 = 0.0, a1 = 0.0;
@@ -146,6 +165,15 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
         for (int i = sp.i0; i < n; i += sp.istep) {
           double a0 = 0.0, a1 = 0.0;
           int j = iq + sp.g;
+          if constexpr (!SM) {
+            // L2-resident Y: four loads in flight per thread
+            double a2 = 0.0, a3 = 0.0;
+            for (; j + 3 * sp.G < n; j += 4 * sp.G) {
+              const double y0 = Y[j * ld + i], y1 = Y[(j + sp.G) * ld + i], y2 = Y[(j + 2 * sp.G) * ld + i], y3 = Y[(j + 3 * sp.G) * ld + i];
+              a0 += y0 * Q.dv[j]; a1 += y1 * Q.dv[j + sp.G]; a2 += y2 * Q.dv[j + 2 * sp.G]; a3 += y3 * Q.dv[j + 3 * sp.G];
+            }
+            a0 += a2; a1 += a3;
+          }
           for (; j + sp.G < n; j += 2 * sp.G) { a0 += Y[j * ld + i] * Q.dv[j]; a1 += Y[(j + sp.G) * ld + i] * Q.dv[j + sp.G]; }
           if (j < n) a0 += Y[j * ld + i] * Q.dv[j];
           if (sp.G == 1) Q.zv[i] = a0 + a1;
@@ -211,7 +239,18 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
           for (int i = sp.i0; i < n; i += sp.istep) {
             const double wi = Q.npv[i];
             double* DG_RESTRICT col = Y + iq * ld + i;
-            for (int j = sp.g; j < len; j += sp.G) col[j * ld] -= (j == 0 ? d0 - alpha : Q.dv[iq + j]) * wi;
+            int j = sp.g;
+            if constexpr (!SM) {
+              // L2-resident Y: four independent read-modify-writes per step
+              for (; j + 3 * sp.G < len; j += 4 * sp.G) {
+                const double y0 = col[j * ld], y1 = col[(j + sp.G) * ld], y2 = col[(j + 2 * sp.G) * ld], y3 = col[(j + 3 * sp.G) * ld];
+                const double c0 = j == 0 ? d0 - alpha : Q.dv[iq + j];
+                const double c1 = Q.dv[iq + j + sp.G], c2 = Q.dv[iq + j + 2 * sp.G], c3 = Q.dv[iq + j + 3 * sp.G];
+                col[j * ld] = y0 - c0 * wi; col[(j + sp.G) * ld] = y1 - c1 * wi;
+                col[(j + 2 * sp.G) * ld] = y2 - c2 * wi; col[(j + 3 * sp.G) * ld] = y3 - c3 * wi;
+              }
+            }
+            for (; j < len; j += sp.G) col[j * ld] -= (j == 0 ? d0 - alpha : Q.dv[iq + j]) * wi;
           }
         }
         DG_FOR(i, iq) Rm[i * ld + iq] = Q.dv[i];
