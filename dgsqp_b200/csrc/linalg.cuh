@@ -38,7 +38,7 @@ struct LinBuf {
   double* pv;     // n
   double* wv;     // n
   double* sp;     // n*DG_CHOL_NB  Cholesky panel (aliases the seven vectors above)
-  double* part;   // max(DG_PART_SZ, n)  partial sums of the 2D-decomposed products, scratch vectors
+  double* part;   // max(DG_PART_SZ, 2n)  partial sums of the 2D-decomposed products, scratch vectors
 };
 
 #ifdef DG_NO_SH_LIN

@@ -117,22 +117,34 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
       // d = J' n_p = -Y npv   (2D over the CTA: thread = row of Y, column groups interleave the columns);  also npv . x
       double dd_tail = 0.0, dd_all = 0.0, gx = 0.0;
       if constexpr (!SM) {
-        // Y in the L2-resident workspace: warp per row, lanes along the row (coalesced), four independent loads per lane
-        for (int j = c.warp(); j < n; j += c.nwarps()) {
-          const double* DG_RESTRICT Yj = Y + j * ld;
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-          int i = c.lane();
-          for (; i + 3 * c.wsz < n; i += 4 * c.wsz) {
-            const double y0 = Yj[i], y1 = Yj[i + c.wsz], y2 = Yj[i + 2 * c.wsz], y3 = Yj[i + 3 * c.wsz];
-            a0 += y0 * Q.npv[i]; a1 += y1 * Q.npv[i + c.wsz]; a2 += y2 * Q.npv[i + 2 * c.wsz]; a3 += y3 * Q.npv[i + 3 * c.wsz];
+        // Y in the L2-resident workspace: the sweep is bound by L2 latency, so every lane keeps 16 loads in flight --
+        // a warp takes four rows at a time, lanes along the rows (coalesced), 128 columns per pass, all loads issued
+        // before the first use
+        for (int j0 = 4 * c.warp(); j0 < n; j0 += 4 * c.nwarps()) {
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int i0 = 0; i0 < n; i0 += 4 * c.wsz) {
+            double y[4][4], v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = i0 + c.lane() + u * c.wsz;
+                y[r][u] = (i < n && j0 + r < n) ? Y[(j0 + r) * ld + i] : 0.0;
+              }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + c.lane() + u * c.wsz; v[u] = i < n ? Q.npv[i] : 0.0; }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] += (y[r][0] * v[0] + y[r][1] * v[1]) + (y[r][2] * v[2] + y[r][3] * v[3]);
           }
-          for (; i < n; i += c.wsz) a0 += Yj[i] * Q.npv[i];
-          double acc = c.warp_sum((a0 + a1) + (a2 + a3));
-          if (c.lane() == 0) {
-            acc = -acc;
-            Q.dv[j] = acc;
-            dd_all += acc * acc;
-            if (j >= iq) dd_tail += acc * acc;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            double a = c.warp_sum(acc[r]);
+            if (c.lane() == 0 && j0 + r < n) {
+              a = -a;
+              Q.dv[j0 + r] = a;
+              dd_all += a * a;
+              if (j0 + r >= iq) dd_tail += a * a;
+            }
           }
         }
       } else {
@@ -166,8 +178,15 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
           double a0 = 0.0, a1 = 0.0;
           int j = iq + sp.g;
           if constexpr (!SM) {
-            // L2-resident Y: four loads in flight per thread
+            // L2-resident Y: eight loads in flight per thread
             double a2 = 0.0, a3 = 0.0;
+            for (; j + 7 * sp.G < n; j += 8 * sp.G) {
+              double y[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) y[u] = Y[(j + u * sp.G) * ld + i];
+              a0 += y[0] * Q.dv[j] + y[4] * Q.dv[j + 4 * sp.G]; a1 += y[1] * Q.dv[j + sp.G] + y[5] * Q.dv[j + 5 * sp.G];
+              a2 += y[2] * Q.dv[j + 2 * sp.G] + y[6] * Q.dv[j + 6 * sp.G]; a3 += y[3] * Q.dv[j + 3 * sp.G] + y[7] * Q.dv[j + 7 * sp.G];
+            }
             for (; j + 3 * sp.G < n; j += 4 * sp.G) {
               const double y0 = Y[j * ld + i], y1 = Y[(j + sp.G) * ld + i], y2 = Y[(j + 2 * sp.G) * ld + i], y3 = Y[(j + 3 * sp.G) * ld + i];
               a0 += y0 * Q.dv[j]; a1 += y1 * Q.dv[j + sp.G]; a2 += y2 * Q.dv[j + 2 * sp.G]; a3 += y3 * Q.dv[j + 3 * sp.G];
@@ -241,13 +260,16 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
             double* DG_RESTRICT col = Y + iq * ld + i;
             int j = sp.g;
             if constexpr (!SM) {
-              // L2-resident Y: four independent read-modify-writes per step
-              for (; j + 3 * sp.G < len; j += 4 * sp.G) {
-                const double y0 = col[j * ld], y1 = col[(j + sp.G) * ld], y2 = col[(j + 2 * sp.G) * ld], y3 = col[(j + 3 * sp.G) * ld];
-                const double c0 = j == 0 ? d0 - alpha : Q.dv[iq + j];
-                const double c1 = Q.dv[iq + j + sp.G], c2 = Q.dv[iq + j + 2 * sp.G], c3 = Q.dv[iq + j + 3 * sp.G];
-                col[j * ld] = y0 - c0 * wi; col[(j + sp.G) * ld] = y1 - c1 * wi;
-                col[(j + 2 * sp.G) * ld] = y2 - c2 * wi; col[(j + 3 * sp.G) * ld] = y3 - c3 * wi;
+              // L2-resident Y: eight independent read-modify-writes per step
+              for (; j + 7 * sp.G < len; j += 8 * sp.G) {
+                double y[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) y[u] = col[(j + u * sp.G) * ld];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const int jj = j + u * sp.G;
+                  col[jj * ld] = y[u] - (jj == 0 ? d0 - alpha : Q.dv[iq + jj]) * wi;
+                }
               }
             }
             for (; j < len; j += sp.G) col[j * ld] -= (j == 0 ? d0 - alpha : Q.dv[iq + j]) * wi;
@@ -273,22 +295,40 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
           Rm[i * ld + iq - 1] = 0.0;
         }
         c.sync();
-        for (int j = ldrop; j < iq - 1; ++j) {
-          double a = Rm[j * ld + j], b = Rm[(j + 1) * ld + j];
-          double h = hypot(a, b);
-          c.sync();                               // rotation parameters read before rows change
-          if (h != 0.0) {
-            double cs = a / h, sn = b / h;
-            for (int col = j + c.tid(); col < iq - 1; col += c.nt()) {
-              double r0 = Rm[j * ld + col], r1 = Rm[(j + 1) * ld + col];
-              Rm[j * ld + col] = cs * r0 + sn * r1;
-              Rm[(j + 1) * ld + col] = -sn * r0 + cs * r1;
+        if (ldrop < iq - 1) {
+          // Givens re-triangularisation.  The rotations form a serial chain only through R: one warp computes them and
+          // rotates R (lanes along the columns), parking (cs, sn) in the partial-sum scratch; then every thread applies
+          // the whole sequence to its own column of J (= column of the rows ldrop..iq-1 of Y) in registers -- two
+          // barriers per drop instead of two per rotation.  Same arithmetic, same order as rotating row pairs one by one.
+          double* DG_RESTRICT rot = B.part;
+          if (c.warp() == 0) {
+            for (int j = ldrop; j < iq - 1; ++j) {
+              const double a = Rm[j * ld + j], b = Rm[(j + 1) * ld + j];
+              const double h = hypot(a, b);
+              double cs = 1.0, sn = 0.0;
+              if (h != 0.0) { cs = a / h; sn = b / h; }
+              c.syncwarp();                         // a, b read by every lane before the rows change
+              if (h != 0.0) {
+                for (int col = j + c.lane(); col < iq - 1; col += c.wsz) {
+                  double r0 = Rm[j * ld + col], r1 = Rm[(j + 1) * ld + col];
+                  Rm[j * ld + col] = cs * r0 + sn * r1;
+                  Rm[(j + 1) * ld + col] = -sn * r0 + cs * r1;
+                }
+              }
+              if (c.lane() == 0) { rot[2 * (j - ldrop)] = cs; rot[2 * (j - ldrop) + 1] = sn; }
+              c.syncwarp();
             }
-            DG_FOR_OFF(i, n, 128) {               // columns j, j+1 of J = rows j, j+1 of Y
-              double j0 = Y[j * ld + i], j1 = Y[(j + 1) * ld + i];
-              Y[j * ld + i] = cs * j0 + sn * j1;
-              Y[(j + 1) * ld + i] = -sn * j0 + cs * j1;
+          }
+          c.sync();
+          DG_FOR(i, n) {
+            double t = Y[ldrop * ld + i];
+            for (int j = ldrop; j < iq - 1; ++j) {
+              const double cs = rot[2 * (j - ldrop)], sn = rot[2 * (j - ldrop) + 1];
+              const double u1 = Y[(j + 1) * ld + i];
+              if (cs == 1.0 && sn == 0.0) { Y[j * ld + i] = t; t = u1; }      // h == 0: no rotation
+              else { Y[j * ld + i] = cs * t + sn * u1; t = -sn * t + cs * u1; }
             }
+            Y[(iq - 1) * ld + i] = t;
           }
           c.sync();
         }

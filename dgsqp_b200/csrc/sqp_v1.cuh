@@ -73,7 +73,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
     W.Q.xq = at(0); W.Q.dv = at(1); W.Q.zv = at(2); W.Q.rv = at(3); W.Q.npv = at(4); W.Q.lam_act = at(5);
   }
   PLACE(W.Q.sl, m);
-  PLACE(W.B.part, (n > DG_PART_SZ ? n : DG_PART_SZ));
+  PLACE(W.B.part, (2 * n > DG_PART_SZ ? 2 * n : DG_PART_SZ));     // also holds the 2(n-1) Givens parameters of a drop step
   { double* t; PLACE(t, (n + 1) / 2 + 1); W.Q.act = (int*)t; PLACE(t, (m + 1) / 2 + 1); W.Q.is_act = (int*)t; }
   const bool pool_ok = go == 0;                 // nothing of the pool fell back to global memory
   // ---- ARENA: matA | matB.  Three placements: both matrices in shared memory; matA alone (split: matA carries the

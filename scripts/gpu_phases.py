@@ -16,6 +16,15 @@ if os.environ.get("DG_WORKLOAD") == "merge":
     from dgsqp_b200.montecarlo import sample_merge
     game, params = dg.merge_game(), dg.merge_params()
     x0, u_ws = sample_merge(game, B, seed=1)
+elif os.environ.get("DG_WORKLOAD", "").startswith("agents"):
+    from dgsqp_b200.montecarlo import sample_agents
+    M = int(os.environ["DG_WORKLOAD"][6:])
+    game, params = dg.agents_game(M=M, N=25), dg.agents_params(25)
+    x0, u_ws = sample_agents(game, B, seed=0)
+elif os.environ.get("DG_WORKLOAD", "").startswith("curve"):
+    th = float(os.environ["DG_WORKLOAD"][5:] or 45)
+    game, params = dg.curve_game(th, 25), dg.curve_params(25)
+    x0, u_ws = sample_head_to_head(game, B, seed=1)
 else:
     game, params = dg.chicane_game(), dg.chicane_params()
     x0, u_ws = sample_head_to_head(game, B, seed=0)
@@ -28,7 +37,7 @@ for rep in range(2):
     torch.cuda.synchronize(); t = time.time()
     r = solver.solve_batch(x0d, ud); torch.cuda.synchronize(); el = time.time() - t
 st = r.status.cpu().numpy(); it = r.num_iters.cpu().numpy(); qp = r.qp_solves.cpu().numpy()
-print(f"B {B} threads {threads} ctas/SM {ctas}: {el:.3f} s -> {B/el:.1f} solves/s, converged {int((st<=1).sum())}, iters/s {it.sum()/el:.0f}")
+print(os.environ.get("DG_WORKLOAD", "chicane"), f"B {B} threads {threads} ctas/SM {ctas}: {el:.3f} s -> {B/el:.1f} solves/s, converged {int((st<=1).sum())}, iters/s {it.sum()/el:.0f}")
 print("status hist", np.bincount(st, minlength=5), "mean iters", it.mean(), "mean qp", qp.mean())
 d = solver.last_diag(B)
 print("diag mean [full evals, grad evals, GI iters, max nneg, indef QPs, sum nneg, sum active, ls trials]:", d.mean(axis=0), "max", d.max(axis=0))
