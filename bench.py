@@ -142,6 +142,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="chicane", choices=["chicane", "merge"])
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: NCCL's own prints (version banner, NCCL_DEBUG output) go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -283,6 +285,15 @@ def main():
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
         except Exception:
             pass
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (per instance, scaled to the
+        # launch): profiles/ncu_traffic.json, written from the raw page of the same kernel on one wave of instances
+        traffic, traffic_src = None, None
+        try:
+            tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text()).get(config["workload"])
+            if tj:
+                traffic, traffic_src = tj["dram_bytes_per_instance"] * B, tj["source"]
+        except Exception:
+            pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_ach = algorithmic_bytes(game, B) * K / t_dev / 1e9
         line = dict(
@@ -293,7 +304,7 @@ def main():
             e2e=dict(value=conv_tot * K / t_e2e_max, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
             gpu_launches=int(launches),
             roofline=dict(bound="fp64", achieved=ach_tf, peak=peak_tf, unit="TFLOP/s",
-                          frac=(ach_tf / peak_tf if peak_tf else None), traffic=None,
+                          frac=(ach_tf / peak_tf if peak_tf else None), traffic=traffic, traffic_source=traffic_src,
                           note="peak = FP64 FMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 "
                                "figure); achieved = algorithmic flops from per-instance work counters / "
                                "CUDA-event time of dgsqp_solve_kernel"),

@@ -36,8 +36,70 @@ __global__ void dgsqp_fp64_probe_kernel(double* out, int iters, double a, double
   if (s == 123.456) out[0] = s;      // never true; keeps the chain alive
 }
 
+// Per-shard statistics of a solved batch, reduced on the device: the additive / max entries of the table
+// scripts/process_data_curve.py:98-110 and process_data_merge.py:58-67 print.  out[16]: count, the six status counts,
+// sum / sum of squares of SQP iterations, sum of QP solves, the same three over converged instances, max p_feas and max
+// stat over converged instances, reserved.  One warp-shuffle + shared-memory reduction per block, one atomic per entry.
+#define DG_NSTAT 16
+__global__ void dgsqp_stats_kernel(const int* __restrict__ status, const int* __restrict__ iters, const int* __restrict__ qp,
+                                   const double* __restrict__ cond, int B, double* __restrict__ out) {
+  double v[DG_NSTAT];
+  for (int k = 0; k < DG_NSTAT; ++k) v[k] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+    const int st = status[i];
+    const double it = (double)iters[i], q = (double)qp[i];
+    v[0] += 1.0;
+    if (st >= 0 && st < 6) v[1 + st] += 1.0;
+    v[7] += it; v[8] += it * it; v[9] += q;
+    if (st <= 1) {
+      v[10] += it; v[11] += it * it; v[12] += q;
+      if (cond) { v[13] = fmax(v[13], cond[3 * i]); v[14] = fmax(v[14], cond[3 * i + 2]); }
+    }
+  }
+  __shared__ double sh[32][DG_NSTAT];
+  for (int k = 0; k < DG_NSTAT; ++k) {
+    double x = v[k];
+    const bool is_max = k == 13 || k == 14;
+    for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(0xffffffffu, x, o); x = is_max ? fmax(x, y) : x + y; }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < DG_NSTAT) {
+    const int k = threadIdx.x;
+    const bool is_max = k == 13 || k == 14;
+    double x = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) x = is_max ? fmax(x, sh[w][k]) : x + sh[w][k];
+    if (is_max) {
+      // p_feas and |stat| are non-negative: the ordering of the bit patterns is the ordering of the values
+      atomicMax((unsigned long long*)&out[k], (unsigned long long)__double_as_longlong(x));
+    } else atomicAdd(&out[k], x);
+  }
+}
 
 extern "C" {
+
+int dgsqp_batch_stats(int device, int32_t B, const int32_t* status, const int32_t* num_iters, const int32_t* qp_solves,
+                      const double* cond, double* out16, void* stream) {
+  if (!status || !num_iters || !qp_solves || !out16) return dg_set_err(DGSQP_EINVAL, "NULL buffer");
+  if (B < 0) return dg_set_err(DGSQP_EINVAL, "negative batch size");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  double* d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * DG_NSTAT));
+  cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(double) * DG_NSTAT, st);
+  if (e == cudaSuccess && B > 0) {
+    int blocks = (B + 255) / 256;
+    if (blocks > 296) blocks = 296;
+    dgsqp_stats_kernel<<<blocks, 256, 0, st>>>(status, num_iters, qp_solves, cond, B, d_out);
+    dg_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out16, d_out, sizeof(double) * DG_NSTAT, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return dg_set_err(DGSQP_ECUDA, std::string("dgsqp_batch_stats: ") + cudaGetErrorString(e));
+  return DGSQP_OK;
+}
 
 const char* dgsqp_last_error(void) { return g_last_error.c_str(); }
 const char* dgsqp_version(void) { return DGSQP_VERSION_STR; }

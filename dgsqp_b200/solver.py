@@ -241,6 +241,22 @@ class DGSQP:
                 torch.empty((B, g.M), **f), torch.empty((B, 3), **f), torch.empty(B, **i), torch.empty(B, **i),
                 torch.empty(B, **i))
 
+    def batch_stats(self, res: BatchResult, stream: Optional[int] = None) -> np.ndarray:
+        """Additive statistics vector (``dgsqp_b200.sharding.STAT_KEYS``) of a device-path result, reduced on the GPU:
+        only 16 doubles cross the bus (the table ``scripts/process_data_curve.py:98-110`` prints is built from it)."""
+        if not hasattr(res.status, "is_cuda"):
+            from .sharding import shard_stats
+            return shard_stats(res.status, res.num_iters, res.qp_solves, res.cond)
+        import torch
+        out = np.zeros(16)
+        v = lambda t: C.c_void_p(t.data_ptr())
+        if stream is None:
+            stream = torch.cuda.current_stream(res.status.device).cuda_stream
+        _abi.check(self._lib.dgsqp_batch_stats(self.device, int(res.status.shape[0]), v(res.status), v(res.num_iters),
+                                               v(res.qp_solves), v(res.cond), out.ctypes.data_as(C.c_void_p),
+                                               C.c_void_p(stream)))
+        return out
+
     def last_diag(self, B):
         """[B, 4] int32: full evaluations, gradient-only evaluations, QP active-set iterations,
         max number of negative Hessian eigenvalues -- of the last solve_batch."""

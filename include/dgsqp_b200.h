@@ -173,6 +173,15 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
                             double* l_out, double* x_out, double* cost_out, double* cond_out, int32_t* num_iters,
                             int32_t* status, int32_t* qp_solves, void* stream);
 
+/* Statistics of a solved batch reduced on the device, so that a Monte-Carlo sweep that only wants the summary table of
+ * scripts/process_data_curve.py:98-110 / process_data_merge.py:58-67 does not have to copy B x (n + m) doubles back.
+ * status / num_iters / qp_solves / cond are DEVICE pointers as written by dgsqp_solve_batch(memspace = 1) (cond may be
+ * NULL); out16 is a HOST array: count, #conv_abs_tol, #conv_rel_tol, #max_it, #diverged, #qp_fail, #time_limit,
+ * sum iters, sum iters^2, sum qp_solves, the same three sums over converged instances, max p_feas and max stat over
+ * converged instances, reserved.  The additive layout is what the per-GPU shards all_gather at the end of a run. */
+int dgsqp_batch_stats(int device, int32_t B, const int32_t* status, const int32_t* num_iters, const int32_t* qp_solves,
+                      const double* cond, double* out16, void* stream);
+
 /* Per-instance work counters of the LAST solve_batch on this handle (device->host copy), DGSQP_NDIAG = 8 ints each:
  * full evaluations, gradient-only evaluations, QP active-set iterations, max #negative eigenvalues of a Hessian,
  * QPs whose Hessian was indefinite, sum of #negative eigenvalues, sum of final active-set sizes, line-search trials. */

@@ -309,7 +309,10 @@ def test_merge_vs_golden():
     for l0 in (data["l_init"], None):
         res = solver.solve_batch(x0, u_ws, l0)
         same = np.array([res.msg[i] == meta["msg"][i] and int(res.num_iters[i]) == meta["num_iters"][i] for i in range(B)])
-        assert same.mean() >= 0.99, f"identical (status, iters): {same.sum()}/{B}"
+        # reg = 0: a rare instance meets the 1e-3 KKT test an iteration earlier / later depending on summation order
+        # (159 of 160 instances identical between the kernel source and the oracle); allow one such instance here
+        assert same.sum() >= B - 1, f"identical (status, iters): {same.sum()}/{B}"
+        assert all(res.msg[i] == meta["msg"][i] for i in range(B))
         for i in np.where(same)[0]:
             assert int(res.qp_solves[i]) == meta["qp_solves"][i]
             assert _rel(res.x[i], data["x"][i]) < 1e-6 and _rel(res.cost[i], data["cost"][i]) < 1e-6
@@ -401,3 +404,19 @@ def test_v2_sum_obj_merit_live_oracle():
                 assert int(res.qp_solves[i]) == r["qp_solves"]
                 if r["status"]:
                     assert _rel(res.u[i], r["u"]) < 1e-6 and _rel(res.x[i], r["x"].ravel()) < 1e-6
+
+
+def test_device_statistics_match_host_statistics(big_batch):
+    """dgsqp_batch_stats (statistics reduced on the device) == the host-side shard statistics of the same results."""
+    import torch
+    from dgsqp_b200.sharding import shard_stats, combine_stats
+    game, params, solver, x0, u_ws, res = big_batch
+    dev = torch.device("cuda:0")
+    r = solver.solve_batch(torch.from_numpy(x0[:3000]).to(dev), torch.from_numpy(u_ws[:3000]).to(dev))
+    dv = solver.batch_stats(r)
+    hv = shard_stats(res.status[:3000], res.num_iters[:3000], res.qp_solves[:3000], res.cond[:3000])
+    assert np.array_equal(dv[:13], hv[:13])                    # counts and integer sums are exact in double
+    assert dv[13] == hv[13] and dv[14] == hv[14]
+    s = combine_stats([dv])
+    assert s["count"] == 3000 and s["converged"] == int((res.status[:3000] <= 1).sum())
+    assert np.array_equal(solver.batch_stats(res)[:13], shard_stats(res.status, res.num_iters, res.qp_solves, res.cond)[:13])
