@@ -136,7 +136,6 @@ struct EvalBuf {
   double* cf;    // M*N*3   per (a,k) coefficients for G' w
   double* lbuf;  // m       staged copy of the multipliers the evaluation runs with
   int* rowtab;   // m       packed row decode (global memory, read-only after game_row_table)
-  double* qs;    // n       grad_u sum_f J^f, only filled for the v2 merit 'sum_obj_l1' (DGSQP_v2.py:1149-1151)
   const GameDesc* G;   // lane normals are needed by the matrix-free G products (set by game_bind)
 };
 
@@ -475,7 +474,7 @@ DG_DEVN void game_costates(Cta& c, const GameDesc& G, const Dims& D_, const Eval
 // q (cost gradient, f_q) and G'l from the costates: thread per input (a,k,cc)
 template <bool SM>
 DG_DEVN void game_gradients(Cta& c, const GameDesc& G, const Dims& D_, const EvalBuf& E_, const double* u,
-                            const double* up, const double* l, bool sum_obj) {
+                            const double* up, const double* l, double* qs) {
   const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
   DG_FOR(t, D.n) {
     int a = t / D.twoN, j = t - a * D.twoN, k = j >> 1, cc = j & 1;
@@ -485,14 +484,14 @@ DG_DEVN void game_gradients(Cta& c, const GameDesc& G, const Dims& D_, const Eva
     double bj = 0.0, bc = 0.0;
     for (int i = 0; i < DG_NQA; ++i) { bj += Bk[i * 6 + 4 + cc] * pJ[i]; bc += Bk[i * 6 + 4 + cc] * pC[i]; }
     E.q[t] = G.w_u[cc] * u[t] + bj;
-    if (sum_obj) {
+    if (qs) {      // grad_u sum_f J^f, only wanted by the v2 merit 'sum_obj_l1' (DGSQP_v2.py:1149-1151)
       double bs = bj;
       for (int f = 0; f < D.M; ++f) {
         if (f == a) continue;
         const double* pF = E.cst + f * (D.N + 1) * D.nq + (k + 1) * D.nq + a * DG_NQA;
         for (int i = 0; i < DG_NQA; ++i) bs += Bk[i * 6 + 4 + cc] * pF[i];
       }
-      E.qs[t] = G.w_u[cc] * u[t] + bs;
+      qs[t] = G.w_u[cc] * u[t] + bs;
     }
     E.gtl[t] = game_GT_direct(D, l, a, k, cc) + bc;
   }

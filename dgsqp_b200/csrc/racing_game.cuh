@@ -156,7 +156,6 @@ struct EvalBuf {
   double* cf;    // M*N*3   per (a,k) coefficients for G' w
   double* lbuf;  // m       staged copy of the multipliers the evaluation runs with
   int* rowtab;   // m       packed row decode (global memory, read-only after game_row_table)
-  double* qs;    // n       grad_u sum_f J^f, only filled for the v2 merit 'sum_obj_l1' (DGSQP_v2.py:1149-1151)
 };
 
 
@@ -520,7 +519,7 @@ DG_DEVN void game_costates(Cta& c, const GameDesc& G, const Dims& D_, const Eval
 // q (cost gradient, f_q) and G'l from the costates: thread per input (a,k,cc)
 template <bool SM>
 DG_DEVN void game_gradients(Cta& c, const GameDesc& G, const Dims& D_, const EvalBuf& E_, const double* u,
-                            const double* up, const double* l, bool sum_obj) {
+                            const double* up, const double* l, double* qs) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
   const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
   DG_FOR(t, D.n) {
@@ -535,7 +534,7 @@ DG_DEVN void game_gradients(Cta& c, const GameDesc& G, const Dims& D_, const Eva
     double val = G.w_u[cc] * uk + G.w_du[cc] * (uk - um);
     if (k + 1 < D.N) val -= G.w_du[cc] * (u[t + 2] - uk);
     E.q[t] = val + bj;
-    if (sum_obj) {
+    if (qs) {      // grad_u sum_f J^f, only wanted by the v2 merit 'sum_obj_l1' (DGSQP_v2.py:1149-1151)
       // every agent's terminal cost reaches u^a through the states: sum over the cost costates of all functions
       double bs = bj;
       for (int f = 0; f < D.M; ++f) {
@@ -543,7 +542,7 @@ DG_DEVN void game_gradients(Cta& c, const GameDesc& G, const Dims& D_, const Eva
         const double* pF = E.cst + f * (D.N + 1) * D.nq + (k + 1) * D.nq + a * DG_NQA;
         for (int i = 0; i < DG_NQA; ++i) bs += Bk[i * 8 + 6 + cc] * pF[i];
       }
-      E.qs[t] = val + bs;
+      qs[t] = val + bs;
     }
     E.gtl[t] = game_GT_direct(D, l, a, k, cc) + bc;
   }

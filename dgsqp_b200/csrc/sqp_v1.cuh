@@ -33,6 +33,7 @@ struct SqpBuf {
   double* up;                        // nu (zeros: v1 resets u_prev every solve, DGSQP.py:305)
   // v2 only: iterate at the start of the running iteration, record of the last appended iteration
   double *c_u, *c_l, *r_u, *r_du, *r_l, *r_dl, *r_s, *r_ds;
+  double* qs;                        // n: grad_u sum_f J^f at the evaluated point (v2 merit 'sum_obj_l1' only)
 };
 
 struct Workspace { EvalBuf E; LinBuf B; QpBuf Q; LsqrBuf L; SqpBuf S; };
@@ -120,7 +121,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   // ---- SQP iterate vectors, hottest first
   PLACE(W.S.u, n); PLACE(W.S.du, n); PLACE(W.S.l, m); PLACE(W.S.dl, m); PLACE(W.Q.lam, m);
   PLACE(W.S.u_c, n); PLACE(W.S.l_c, m); PLACE(W.S.s, m); PLACE(W.S.ds, m); PLACE(W.S.Gdu, m);
-  PLACE(W.S.tn, n); PLACE(W.S.tn2, n); PLACE(W.E.qs, n);
+  PLACE(W.S.tn, n); PLACE(W.S.tn2, n);
   // ---- global only
   GTAKE(W.E.Q, n * n); GTAKE(W.B.Zg, n * n);
   { double* t; GTAKE(t, (m + 1) / 2 + 1); W.E.rowtab = (int*)t; }
@@ -130,6 +131,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   GTAKE(W.S.u_t, n); GTAKE(W.S.l_t, m); GTAKE(W.S.du_t, n); GTAKE(W.S.dl_t, m); GTAKE(W.S.s_t, m); GTAKE(W.S.ds_t, m);
   GTAKE(W.S.c_u, n); GTAKE(W.S.c_l, m); GTAKE(W.S.r_u, n); GTAKE(W.S.r_du, n); GTAKE(W.S.r_l, m); GTAKE(W.S.r_dl, m);
   GTAKE(W.S.r_s, m); GTAKE(W.S.r_ds, m);
+  GTAKE(W.S.qs, n);
 #undef GTAKE
 #undef STAKE
 #undef PLACE
@@ -168,7 +170,7 @@ DG_DEVN void eval_full(Cta& c, SolveCtx& X, const double* u, const double* l_in)
   game_sens<SM>(c, D, E);
   c.sync();
   game_contract<SM>(c, D, E);
-  game_gradients<SM>(c, *X.G, D, E, u, X.W.S.up, l, X.P->merit_obj != 0);
+  game_gradients<SM>(c, *X.G, D, E, u, X.W.S.up, l, X.P->merit_obj ? X.W.S.qs : nullptr);
   c.sync();
   c.lap(PH_ADJ_FULL);
   game_hessian<SM>(c, *X.G, D, E, l);
@@ -193,7 +195,7 @@ DG_DEVN void eval_grad(Cta& c, SolveCtx& X, const double* u, const double* l_in,
   game_costates<SM>(c, *X.G, D, E, l);
   if (with_sens) game_sens<SM>(c, D, E);
   c.sync();
-  game_gradients<SM>(c, *X.G, D, E, u, X.W.S.up, l, X.P->merit_obj != 0);
+  game_gradients<SM>(c, *X.G, D, E, u, X.W.S.up, l, X.P->merit_obj ? X.W.S.qs : nullptr);
   c.sync();
   c.lap(PH_ADJ_GRAD);
   if (c.tid() == 0) ++X.n_evals_grad;

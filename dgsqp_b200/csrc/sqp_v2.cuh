@@ -42,7 +42,7 @@ DG_DEVN double v2_dstat(Cta& c, SolveCtx& X, const double* du, const double* dl)
   if (X.P->merit_obj) {
     // d(sum of costs) along du (:1150-1151); the multipliers do not enter
     double p = 0.0;
-    DG_FOR(i, n) p += E.qs[i] * du[i];
+    DG_FOR(i, n) p += S.qs[i] * du[i];
     p = c.sum(p);
     c.lap(PH_MERIT);
     return p;
