@@ -36,6 +36,16 @@ __global__ void dgsqp_fp64_probe_kernel(double* out, int iters, double a, double
   if (s == 123.456) out[0] = s;      // never true; keeps the chain alive
 }
 
+// PID warm-start roll-outs: one thread per sampled agent, see pid_rollout.cuh
+#include "pid_rollout.cuh"
+__global__ void dgsqp_pid_rollout_kernel(RolloutParams P, int K, const double* __restrict__ s0, const double* __restrict__ xt0,
+                                         const double* __restrict__ v0, double* __restrict__ q0, double* __restrict__ xy,
+                                         double* __restrict__ u_ws) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  ro_agent(P, s0[i], xt0[i], v0[i], q0 + (size_t)i * 6, xy + (size_t)i * (P.N + 1) * 2, u_ws + (size_t)i * P.N * 2);
+}
+
 // Per-shard statistics of a solved batch, reduced on the device: the additive / max entries of the table
 // scripts/process_data_curve.py:98-110 and process_data_merge.py:58-67 print.  out[16]: count, the six status counts,
 // sum / sum of squares of SQP iterations, sum of QP solves, the same three over converged instances, max p_feas and max
@@ -98,6 +108,43 @@ int dgsqp_batch_stats(int device, int32_t B, const int32_t* status, const int32_
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(d_out);
   if (e != cudaSuccess) return dg_set_err(DGSQP_ECUDA, std::string("dgsqp_batch_stats: ") + cudaGetErrorString(e));
+  return DGSQP_OK;
+}
+
+int dgsqp_pid_rollout(const dgsqp_racing_game* game, const double* key_pts, int device, int32_t K, const double* s0,
+                      const double* xt0, const double* v0, double* q0, double* xy, double* u_ws, int32_t memspace, void* stream) {
+  RolloutParams P;
+  if (ro_fill(game, key_pts, &P) != 0) return dg_set_err(DGSQP_EINVAL, "invalid game / key points");
+  if (K < 0 || (memspace != 0 && memspace != 1)) return dg_set_err(DGSQP_EINVAL, "bad argument");
+  if (K == 0) return DGSQP_OK;
+  if (!s0 || !xt0 || !v0 || !q0 || !xy || !u_ws) return dg_set_err(DGSQP_EINVAL, "NULL buffer");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t k = (size_t)K, nxy = (size_t)(P.N + 1) * 2, nu = (size_t)P.N * 2;
+  double* d = nullptr;          // host path: one staging block [s0 | xt0 | v0 | q0 | xy | u_ws]
+  const double *ds0 = s0, *dxt = xt0, *dv0 = v0;
+  double *dq0 = q0, *dxy = xy, *du = u_ws;
+  if (memspace == 0) {
+    CUDA_TRY(cudaMalloc(&d, sizeof(double) * k * (3 + 6 + nxy + nu)));
+    double* in = d;
+    dq0 = d + 3 * k; dxy = dq0 + 6 * k; du = dxy + nxy * k;
+    cudaError_t e = cudaMemcpyAsync(in, s0, sizeof(double) * k, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(in + k, xt0, sizeof(double) * k, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(in + 2 * k, v0, sizeof(double) * k, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cudaFree(d); return dg_set_err(DGSQP_ECUDA, std::string("dgsqp_pid_rollout: ") + cudaGetErrorString(e)); }
+    ds0 = in; dxt = in + k; dv0 = in + 2 * k;
+  }
+  dgsqp_pid_rollout_kernel<<<(K + 127) / 128, 128, 0, st>>>(P, K, ds0, dxt, dv0, dq0, dxy, du);
+  dg_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && memspace == 0) {
+    e = cudaMemcpyAsync(q0, dq0, sizeof(double) * k * 6, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(xy, dxy, sizeof(double) * k * nxy, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(u_ws, du, sizeof(double) * k * nu, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (d) cudaFree(d);
+  if (e != cudaSuccess) return dg_set_err(DGSQP_ECUDA, std::string("dgsqp_pid_rollout: ") + cudaGetErrorString(e));
   return DGSQP_OK;
 }
 

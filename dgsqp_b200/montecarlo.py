@@ -95,6 +95,22 @@ def pid_rollout(game: RacingGame, s0, xt0, v0):
     return q0, xy, u_ws
 
 
+def pid_rollout_device(game: RacingGame, s0, xt0, v0, device=0):
+    """Same roll-out on the GPU (``dgsqp_pid_rollout``, one thread per agent): NumPy in, NumPy out.  Agrees with
+    :func:`pid_rollout` to rounding (CUDA and NumPy transcendental functions differ in the last ulp)."""
+    import ctypes as C
+    from . import _abi
+    lib = _abi.load()
+    s0, xt0, v0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (s0, xt0, v0))
+    K, N = len(s0), game.N
+    q0, xy, u_ws = np.empty((K, 6)), np.empty((K, N + 1, 2)), np.empty((K, N, NUA))
+    kp = np.ascontiguousarray(game.track.key_pts, dtype=np.float64)
+    gs = game.to_struct()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _abi.check(lib.dgsqp_pid_rollout(C.byref(gs), p(kp), int(device), K, p(s0), p(xt0), p(v0), p(q0), p(xy), p(u_ws), 0, None))
+    return q0, xy, u_ws
+
+
 def _collision_free(xys, radii):
     M = len(xys)
     ok = np.ones(xys[0].shape[0], dtype=bool)
@@ -105,9 +121,11 @@ def _collision_free(xys, radii):
     return ok
 
 
-def sample_head_to_head(game: RacingGame, B, seed=0):
-    """B accepted 2-agent instances: x0 [B,12], u_ws [B,n] agent-major."""
+def sample_head_to_head(game: RacingGame, B, seed=0, device=None):
+    """B accepted 2-agent instances: x0 [B,12], u_ws [B,n] agent-major.  ``device``: CUDA ordinal to run the PID
+    roll-outs on the GPU (``pid_rollout_device``) instead of NumPy."""
     assert game.M == 2
+    pid_rollout = globals()["pid_rollout"] if device is None else (lambda g, s, xt, v: pid_rollout_device(g, s, xt, v, device))
     rng = np.random.default_rng(seed)
     first_seg_len = game.track.cl_segs[0, 0]
     hw = game.half_width
@@ -134,8 +152,9 @@ def sample_head_to_head(game: RacingGame, B, seed=0):
     return np.ascontiguousarray(np.vstack(x0s)[:B]), np.ascontiguousarray(np.vstack(uws)[:B])
 
 
-def sample_agents(game: RacingGame, B, seed=0):
-    """B accepted M-agent instances: x0 [B,6M], u_ws [B,n] agent-major."""
+def sample_agents(game: RacingGame, B, seed=0, device=None):
+    """B accepted M-agent instances: x0 [B,6M], u_ws [B,n] agent-major (``device`` as in sample_head_to_head)."""
+    pid_rollout = globals()["pid_rollout"] if device is None else (lambda g, s, xt, v: pid_rollout_device(g, s, xt, v, device))
     rng = np.random.default_rng(seed)
     first_seg_len = game.track.cl_segs[0, 0]
     hw = game.half_width

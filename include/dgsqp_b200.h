@@ -173,6 +173,16 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
                             double* l_out, double* x_out, double* cost_out, double* cond_out, int32_t* num_iters,
                             int32_t* status, int32_t* qp_solves, void* stream);
 
+/* Warm-start generation on the device: the PID lane-follower roll-out the Monte-Carlo drivers run for every sampled agent
+ * before a solve (scripts/DGSQP_ALGAMES_monte_carlo_chicane.py:411-467, DGSQP/solvers/PID.py:74-138,187-238, one-step
+ * simulation DGSQP/dynamics/dynamics_models.py:161-186 with classical RK4 x 4 sub-steps, local_to_global
+ * DGSQP/tracks/radius_arclength_track.py:752-807).  K agents start at (s0, x_tran0, v0), e_psi = 0.
+ *   key_pts  HOST [(track_nseg+1) * 6]  x, y, psi, cumulative s, segment length, curvature (get_track_key_pts, :361-408)
+ *   q0 [K, 6]  state2q of the initial states;  xy [K, N+1, 2] global positions of the roll-out (collision pre-check);
+ *   u_ws [K, N, 2] inputs = the warm start of that agent.        memspace: 0 host pointers, 1 device pointers. */
+int dgsqp_pid_rollout(const dgsqp_racing_game* game, const double* key_pts, int device, int32_t K, const double* s0,
+                      const double* xt0, const double* v0, double* q0, double* xy, double* u_ws, int32_t memspace, void* stream);
+
 /* Statistics of a solved batch reduced on the device, so that a Monte-Carlo sweep that only wants the summary table of
  * scripts/process_data_curve.py:98-110 / process_data_merge.py:58-67 does not have to copy B x (n + m) doubles back.
  * status / num_iters / qp_solves / cond are DEVICE pointers as written by dgsqp_solve_batch(memspace = 1) (cond may be

@@ -9,6 +9,17 @@
 #include "../../dgsqp_b200/csrc/sqp_v2.cuh"
 #include "../../dgsqp_b200/csrc/host_setup.h"
 
+#ifndef DG_GAME_MERGE
+#include "../../dgsqp_b200/csrc/pid_rollout.cuh"
+extern "C" int hs_pid_rollout(const dgsqp_racing_game* g, const double* key_pts, int K, const double* s0, const double* xt0,
+                              const double* v0, double* q0, double* xy, double* u_ws) {
+  RolloutParams P;
+  if (ro_fill(g, key_pts, &P) != 0) return -1;
+  for (int i = 0; i < K; ++i) ro_agent(P, s0[i], xt0[i], v0[i], q0 + (size_t)i * 6, xy + (size_t)i * (P.N + 1) * 2, u_ws + (size_t)i * P.N * 2);
+  return 0;
+}
+#endif
+
 extern "C" {
 
 struct HsHandle { GameDesc G; SolverParams P; Dims D; std::vector<double> ws, sh; Workspace W; };
