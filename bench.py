@@ -68,6 +68,34 @@ def cpu_oracle_throughput(x0, u_ws, cores):
     return conv / dt, iters / dt, dt, conv
 
 
+def _native_worker(args):
+    x0, u_ws, merge = args
+    sys.path.insert(0, str(ROOT / "tests"))
+    import dgsqp_b200 as dg
+    from hostsim_lib import HostSim
+    global _NATIVE
+    try:
+        _NATIVE
+    except NameError:
+        _NATIVE = HostSim(dg.merge_game(), dg.merge_params()) if merge else HostSim(dg.chicane_game(), dg.chicane_params())
+    r = _NATIVE.solve(x0, u_ws)
+    return int(r["status"]) <= 1, int(r["num_iters"])
+
+
+def cpu_native_throughput(x0, u_ws, cores, merge):
+    """The SAME solver source compiled for the host (tests/hostsim: single-thread C++ build of csrc/*.cuh), one
+    instance per core.  Not the reference and not the product: an honest yardstick for what a CPU does with this
+    algorithm once Python/NumPy overhead is gone."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_native_worker, [(x0[i], u_ws[i], merge) for i in range(min(cores, len(x0)))])
+        t0 = time.perf_counter()
+        out = pool.map(_native_worker, [(x0[i], u_ws[i], merge) for i in range(len(x0))], chunksize=2)
+        dt = time.perf_counter() - t0
+    return sum(o[0] for o in out) / dt, len(out) / dt, sum(o[1] for o in out) / dt, dt
+
+
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler(threading.Thread):
     def __init__(self, index):
@@ -330,6 +358,15 @@ def main():
                     same += 1
                     if st_o:
                         worst = max(worst, float(np.abs(u_gpu[i] - u_o).max() / max(1.0, np.abs(u_o).max())))
+            try:
+                n_n = 16 * cores
+                cv, av, iv, ndt = cpu_native_throughput(x0[:n_n], u_ws[:n_n], cores, args.workload == "merge")
+                line["cpu_native"] = dict(value=cv, unit=UNIT, solves_per_sec_all=av, sqp_iters_per_sec=iv, cores=cores,
+                                          kind="kernel source compiled for the host (tests/hostsim, single-thread C++ "
+                                               "build of the same solver), one instance per core",
+                                          sample=f"first {n_n} instances of the same batch, {ndt:.1f} s wall")
+            except Exception as e:                      # the yardstick is optional (needs g++ artefacts of the tests)
+                line["cpu_native"] = dict(unavailable=str(e)[:200])
             line["parity"] = dict(sample=n_s, identical_status_and_iters=same, max_rel_err_u_converged=worst,
                                   against="oracle port (own LSQR dual initialisation on both sides)")
         print(json.dumps(line))
