@@ -38,6 +38,11 @@ struct SqpBuf {
 
 struct Workspace { EvalBuf E; LinBuf B; QpBuf Q; LsqrBuf L; SqpBuf S; };
 
+#ifdef DG_PLAN_GUARD
+static double* dg_guard_at[512];
+static int dg_guard_n = 0;
+#endif
+
 struct MemPlan { size_t smem, gmem; int mats_in_smem, matA_in_smem, sens_in_smem, hot_in_smem; };   // doubles used in each space
 
 // Memory plan of one CTA (= one game instance in flight).  Everything a latency-bound phase walks through
@@ -57,9 +62,18 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   size_t so = 0, go = 0;
   const size_t n = D.n, m = D.m, nq = D.nq, N = D.N, M = D.M, ld = D.ld;
   auto rnd = [](size_t c) { return (c + 1) & ~(size_t)1; };
-#define GTAKE(ptr, cnt) do { (ptr) = gbase ? gbase + go : nullptr; go += rnd(cnt); } while (0)
-#define STAKE(ptr, cnt) do { (ptr) = sbase ? sbase + so : nullptr; so += rnd(cnt); } while (0)
-#define PLACE(ptr, cnt) do { if (so + rnd(cnt) <= sbudget) STAKE(ptr, cnt); else GTAKE(ptr, cnt); } while (0)
+  // DG_PLAN_GUARD (tests/hostsim only): every buffer is followed by a gap of DG_PLAN_GUARD doubles whose position is
+  // recorded, so that the test harness can fill the gaps with a canary and detect writes past the end of a buffer
+#ifdef DG_PLAN_GUARD
+#define DG_GPAD ((size_t)(DG_PLAN_GUARD))
+#define DG_GNOTE(p, cnt) do { if ((p) && dg_guard_n < 512) dg_guard_at[dg_guard_n++] = (p) + rnd(cnt); } while (0)
+#else
+#define DG_GPAD ((size_t)0)
+#define DG_GNOTE(p, cnt) do { } while (0)
+#endif
+#define GTAKE(ptr, cnt) do { (ptr) = gbase ? gbase + go : nullptr; go += rnd(cnt) + DG_GPAD; DG_GNOTE(ptr, cnt); } while (0)
+#define STAKE(ptr, cnt) do { (ptr) = sbase ? sbase + so : nullptr; so += rnd(cnt) + DG_GPAD; DG_GNOTE(ptr, cnt); } while (0)
+#define PLACE(ptr, cnt) do { if (so + rnd(cnt) + DG_GPAD <= sbudget) STAKE(ptr, cnt); else GTAKE(ptr, cnt); } while (0)
   MemPlan P; P.mats_in_smem = 0; P.sens_in_smem = 0;
   // ---- POOL
   PLACE(W.E.x, (N + 1) * nq); PLACE(W.E.g, m); PLACE(W.E.q, n); PLACE(W.E.gtl, n);
@@ -95,9 +109,9 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   double** ev_ptr[7] = {&W.E.AB, &W.E.cst, &W.E.Hc, &W.E.Vbuf, &W.E.Wrow, &W.E.T2, &W.E.lbuf};
   P.matA_in_smem = 0;
   // (the split is only taken when the sensitivity rows still fit beside matA: every active-set iteration walks them)
-  if (so + szA + szB <= sbudget || so + szA + rnd(M * D.sens_sz) > sbudget) {
+  if (so + szA + szB + DG_GPAD <= sbudget || so + szA + rnd(M * D.sens_sz) + 2 * DG_GPAD > sbudget) {
     // one block: the evaluation data is carved from its start (no matrix is alive while the game is evaluated)
-    if (so + szA + szB <= sbudget) { STAKE(arA, szA + szB); P.mats_in_smem = 1; P.matA_in_smem = 1; } else GTAKE(arA, szA + szB);
+    if (so + szA + szB + DG_GPAD <= sbudget) { STAKE(arA, szA + szB); P.mats_in_smem = 1; P.matA_in_smem = 1; } else GTAKE(arA, szA + szB);
     arB = arA ? arA + szA : nullptr;
     size_t o = 0;
     for (int i = 0; i < 7; ++i) { *ev_ptr[i] = arA ? arA + o : nullptr; o += ev_sz[i]; }
@@ -117,7 +131,7 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   }
   W.B.ld = (int)ld; W.B.matA = arA; W.B.matB = arB;
   // ---- SENS
-  if (so + rnd(M * D.sens_sz) <= sbudget) { STAKE(W.E.S, M * D.sens_sz); P.sens_in_smem = 1; } else GTAKE(W.E.S, M * D.sens_sz);
+  if (so + rnd(M * D.sens_sz) + DG_GPAD <= sbudget) { STAKE(W.E.S, M * D.sens_sz); P.sens_in_smem = 1; } else GTAKE(W.E.S, M * D.sens_sz);
   // ---- SQP iterate vectors, hottest first
   PLACE(W.S.u, n); PLACE(W.S.du, n); PLACE(W.S.l, m); PLACE(W.S.dl, m); PLACE(W.Q.lam, m);
   PLACE(W.S.u_c, n); PLACE(W.S.l_c, m); PLACE(W.S.s, m); PLACE(W.S.ds, m); PLACE(W.S.Gdu, m);
@@ -133,6 +147,8 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   GTAKE(W.S.r_s, m); GTAKE(W.S.r_ds, m);
   GTAKE(W.S.qs, n);
 #undef GTAKE
+#undef DG_GPAD
+#undef DG_GNOTE
 #undef STAKE
 #undef PLACE
   P.smem = so; P.gmem = go;

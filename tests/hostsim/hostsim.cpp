@@ -22,7 +22,8 @@ extern "C" int hs_pid_rollout(const dgsqp_racing_game* g, const double* key_pts,
 
 extern "C" {
 
-struct HsHandle { GameDesc G; SolverParams P; Dims D; std::vector<double> ws, sh; Workspace W; };
+struct HsHandle { GameDesc G; SolverParams P; Dims D; std::vector<double> ws, sh; Workspace W; std::vector<double*> guards; };
+static const double HS_CANARY = -7.25e77;
 
 static void* hs_create_common(const dg_game_struct* g, const dgsqp_params* p, const dgsqp_v2_params* p2) {
   HsHandle* h = new HsHandle();
@@ -34,13 +35,33 @@ static void* hs_create_common(const dg_game_struct* g, const dgsqp_params* p, co
   MemPlan pl = plan_memory(h->D, nullptr, nullptr, budget, tmp);
   h->ws.assign(pl.gmem + 2, 0.0);
   h->sh.assign(pl.smem + 2, 0.0);
+#ifdef DG_PLAN_GUARD
+  dg_guard_n = 0;
+#endif
   plan_memory(h->D, h->ws.data(), h->sh.data(), budget, h->W);
+#ifdef DG_PLAN_GUARD
+  // guard mode: every buffer of the plan is followed by DG_PLAN_GUARD canary doubles (see plan_memory)
+  h->guards.assign(dg_guard_at, dg_guard_at + dg_guard_n);
+  for (double* g : h->guards) for (int i = 0; i < DG_PLAN_GUARD; ++i) g[i] = HS_CANARY;
+#endif
   game_bind(h->W.E, &h->G);
   { Cta c; game_row_table<false>(c, h->D, h->W.E.rowtab); }
   return h;
 }
 void* hs_create(const dg_game_struct* g, const dgsqp_params* p) { return hs_create_common(g, p, nullptr); }
 void* hs_create_v2(const dg_game_struct* g, const dgsqp_v2_params* p) { return hs_create_common(g, nullptr, p); }
+// number of canary doubles behind the buffers of the memory plan that no longer hold the canary (guard build only)
+int hs_guard_check(void* hp) {
+  HsHandle* h = (HsHandle*)hp;
+  int bad = 0;
+#ifdef DG_PLAN_GUARD
+  for (double* g : h->guards) for (int i = 0; i < DG_PLAN_GUARD; ++i) bad += g[i] != HS_CANARY;
+  if (h->guards.empty()) return -1;
+#else
+  bad = -1;
+#endif
+  return bad;
+}
 void hs_set_l0_perturb(void* hp, double v) { ((HsHandle*)hp)->P.dbg_l0_perturb = v; }
 void hs_destroy(void* hp) { delete (HsHandle*)hp; }
 void hs_dims(void* hp, int* out) { HsHandle* h = (HsHandle*)hp; out[0] = h->D.nq; out[1] = h->D.nu; out[2] = h->D.n; out[3] = h->D.m; }

@@ -14,8 +14,8 @@ HERE = pathlib.Path(__file__).resolve().parent / "hostsim"
 _libs = {}
 
 
-def build(asan=False, merge=False):
-    out = HERE / ("libhostsim" + ("_merge" if merge else "") + ("_asan" if asan else "") + ".so")
+def build(asan=False, merge=False, guard=False):
+    out = HERE / ("libhostsim" + ("_merge" if merge else "") + ("_asan" if asan else "") + ("_guard" if guard else "") + ".so")
     srcs = [HERE / "hostsim.cpp"] + sorted((HERE.parents[1] / "dgsqp_b200" / "csrc").glob("*.cuh")) \
         + sorted((HERE.parents[1] / "dgsqp_b200" / "csrc").glob("*.h"))
     if out.exists() and all(out.stat().st_mtime >= s.stat().st_mtime for s in srcs):
@@ -23,14 +23,16 @@ def build(asan=False, merge=False):
     flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if asan else ["-O2"]
     if merge:
         flags = flags + ["-DDG_GAME_MERGE=1"]
+    if guard:
+        flags = flags + ["-DDG_PLAN_GUARD=16"]      # canary gaps behind every buffer of the memory plan (hs_guard_check)
     subprocess.check_call(["g++", *flags, "-shared", "-fPIC", "-std=c++17", "-o", str(out), str(HERE / "hostsim.cpp")])
     return out
 
 
-def load(asan=False, merge=False):
-    if (asan, merge) in _libs:
-        return _libs[(asan, merge)]
-    lib = C.CDLL(str(build(asan, merge)))
+def load(asan=False, merge=False, guard=False):
+    if (asan, merge, guard) in _libs:
+        return _libs[(asan, merge, guard)]
+    lib = C.CDLL(str(build(asan, merge, guard)))
     gs = MergeGameStruct if merge else RacingGameStruct
     lib.hs_create.restype = C.c_void_p
     lib.hs_create.argtypes = [C.POINTER(gs), C.POINTER(ParamsStruct)]
@@ -42,7 +44,9 @@ def load(asan=False, merge=False):
     lib.hs_nearest_pd.restype = C.c_int
     lib.hs_qp.restype = C.c_int
     lib.hs_lsqr.restype = C.c_int
-    _libs[(asan, merge)] = lib
+    lib.hs_guard_check.restype = C.c_int
+    lib.hs_guard_check.argtypes = [C.c_void_p]
+    _libs[(asan, merge, guard)] = lib
     return lib
 
 
@@ -51,8 +55,8 @@ def _p(a):
 
 
 class HostSim:
-    def __init__(self, game, params, asan=False):
-        self.lib = load(asan, merge=isinstance(game, MergeGame))
+    def __init__(self, game, params, asan=False, guard=False):
+        self.lib = load(asan, merge=isinstance(game, MergeGame), guard=guard)
         self.game = game
         gs = game.to_struct()
         if isinstance(params, DGSQPV2Params):
@@ -70,6 +74,10 @@ class HostSim:
         if getattr(self, "h", None) is not None and self.h.value:
             self.lib.hs_destroy(self.h)
             self.h = None
+
+    def guard_check(self):
+        """Guard build only: number of damaged canary doubles behind the buffers of the memory plan (0 = no overrun)."""
+        return int(self.lib.hs_guard_check(self.h))
 
     def evaluate(self, x0, u, l):
         n, m = self.n, self.m

@@ -247,3 +247,31 @@ def test_large_sample_fixture_subset():
                 assert np.abs(h["u"] - d["u"][i]).max() < 1e-6 * max(1.0, np.abs(d["u"][i]).max())
                 assert np.abs(h["cost"] - d["cost"][i]).max() < 1e-6 * max(1.0, np.abs(d["cost"][i]).max())
     assert same >= 93
+
+
+@pytest.mark.parametrize("budget", ["28000", "0"])
+def test_no_buffer_overruns_guard_build(budget, monkeypatch):
+    """Guard build of the kernel source: every buffer of the memory plan is followed by 16 canary doubles.  Full solves
+    of short- and full-horizon games (n = 40 .. 150, both placements, v1 and v2, racing and merge) must leave all of them
+    intact.  (This is the check that would have caught the eigenvector-scratch overrun of nearest_pd for n < 97.)"""
+    from dgsqp_b200.montecarlo import sample_head_to_head, sample_agents, sample_merge
+    monkeypatch.setenv("DG_HOSTSIM_SMEM_DOUBLES", budget)
+    cases = [(dg.chicane_game(N=10), dg.chicane_params(10), lambda g: sample_head_to_head(g, 3, seed=2)),
+             (dg.chicane_game(), dg.chicane_params(), lambda g: sample_head_to_head(g, 3, seed=0)),
+             (dg.curve_game(45.0, 15), dg.curve_params(15), lambda g: sample_head_to_head(g, 3, seed=1)),
+             (dg.agents_game(3, 90.0, 15), dg.agents_params(15), lambda g: sample_agents(g, 2, seed=0)),
+             (dg.agents_game(3, 90.0, 25), dg.agents_params(25), lambda g: sample_agents(g, 1, seed=0)),
+             (dg.merge_game(N=10), dg.merge_params(10), lambda g: sample_merge(g, 3, seed=1)),
+             (dg.merge_game(), dg.merge_params(), lambda g: sample_merge(g, 2, seed=1)),
+             (dg.chicane_game(N=10), dg.DGSQPV2Params(N=10, reg=1e-1, reg_decay=0.8, nms_frequency=2, sqp_iters=30),
+              lambda g: sample_head_to_head(g, 2, seed=3)),
+             (dg.merge_game(N=10), dg.DGSQPV2Params(N=10, reg=1e-3, nms=False, sqp_iters=20, merit_function="sum_obj_l1"),
+              lambda g: sample_merge(g, 2, seed=1))]
+    for game, params, sampler in cases:
+        hs = HostSim(game, params, guard=True)
+        assert hs.guard_check() == 0
+        x0, u_ws = sampler(game)
+        for i in range(x0.shape[0]):
+            r = hs.solve(x0[i], u_ws[i])
+            assert r["status"] in (0, 1, 2, 3, 4)
+            assert hs.guard_check() == 0, f"buffer overrun in {game.name} (n = {game.n})"
