@@ -62,7 +62,7 @@ class ParamsV2Struct(C.Structure):
                 ("mu_vio_thresh", C.c_double)]
 
 
-EXPORTS = ["dgsqp_create", "dgsqp_create_v2", "dgsqp_create_merge", "dgsqp_create_merge_v2", "dgsqp_destroy", "dgsqp_dims", "dgsqp_solve_batch", "dgsqp_solve_batch_async",
+EXPORTS = ["dgsqp_create", "dgsqp_create_v2", "dgsqp_create_merge", "dgsqp_create_merge_v2", "dgsqp_destroy", "dgsqp_dims", "dgsqp_solve_batch", "dgsqp_solve_batch_up", "dgsqp_solve_batch_async",
            "dgsqp_batch_stats", "dgsqp_pid_rollout", "dgsqp_last_diag", "dgsqp_phase_count", "dgsqp_last_phase_cycles", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_memory_plan", "dgsqp_set_smem_limit", "dgsqp_last_error", "dgsqp_version"]
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "libdgsqp_b200.so"
@@ -100,6 +100,8 @@ def load():
     batch_args = [vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.dgsqp_solve_batch.argtypes = batch_args + [C.c_int32, vp]
     lib.dgsqp_solve_batch.restype = C.c_int
+    lib.dgsqp_solve_batch_up.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp]
+    lib.dgsqp_solve_batch_up.restype = C.c_int
     lib.dgsqp_solve_batch_async.argtypes = batch_args + [vp]
     lib.dgsqp_solve_batch_async.restype = C.c_int
     lib.dgsqp_pid_rollout.argtypes = [C.POINTER(RacingGameStruct), vp, C.c_int, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int32, vp]

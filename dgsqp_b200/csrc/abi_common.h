@@ -9,9 +9,9 @@ struct dgsqp_handle_vtbl {
   int (*destroy)(dgsqp_handle*);
   int (*dims)(const dgsqp_handle*, int32_t*);
   int (*configure)(dgsqp_handle*, int32_t, int32_t);
-  int (*solve_batch_async)(dgsqp_handle*, int32_t, const double*, const double*, const double*, double*, double*, double*, double*,
+  int (*solve_batch_async)(dgsqp_handle*, int32_t, const double*, const double*, const double*, const double*, double*, double*, double*, double*,
                            double*, int32_t*, int32_t*, int32_t*, void*);
-  int (*solve_batch)(dgsqp_handle*, int32_t, const double*, const double*, const double*, double*, double*, double*, double*,
+  int (*solve_batch)(dgsqp_handle*, int32_t, const double*, const double*, const double*, const double*, double*, double*, double*, double*,
                      double*, int32_t*, int32_t*, int32_t*, int32_t, void*);
   int (*last_diag)(dgsqp_handle*, int32_t, int32_t*);
   int (*set_smem_limit)(dgsqp_handle*, int64_t);

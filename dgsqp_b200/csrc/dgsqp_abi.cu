@@ -177,14 +177,21 @@ int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const 
                             double* l_out, double* x_out, double* cost_out, double* cond_out, int32_t* num_iters,
                             int32_t* status, int32_t* qp_solves, void* stream) {
   if (!h) return dg_set_err(DGSQP_EINVAL, "NULL handle");
-  return h->vt->solve_batch_async(h, B, x0, u_ws, l_ws, u_out, l_out, x_out, cost_out, cond_out, num_iters, status, qp_solves, stream);
+  return h->vt->solve_batch_async(h, B, x0, u_ws, l_ws, nullptr, u_out, l_out, x_out, cost_out, cond_out, num_iters, status, qp_solves, stream);
 }
 
 int dgsqp_solve_batch(dgsqp_handle* h, int32_t B, const double* x0, const double* u_ws, const double* l_ws, double* u_out, double* l_out,
                       double* x_out, double* cost_out, double* cond_out, int32_t* num_iters, int32_t* status,
                       int32_t* qp_solves, int32_t memspace, void* stream) {
   if (!h) return dg_set_err(DGSQP_EINVAL, "NULL handle");
-  return h->vt->solve_batch(h, B, x0, u_ws, l_ws, u_out, l_out, x_out, cost_out, cond_out, num_iters, status, qp_solves, memspace, stream);
+  return h->vt->solve_batch(h, B, x0, u_ws, l_ws, nullptr, u_out, l_out, x_out, cost_out, cond_out, num_iters, status, qp_solves, memspace, stream);
+}
+
+int dgsqp_solve_batch_up(dgsqp_handle* h, int32_t B, const double* x0, const double* u_ws, const double* l_ws, const double* u_prev,
+                         double* u_out, double* l_out, double* x_out, double* cost_out, double* cond_out, int32_t* num_iters,
+                         int32_t* status, int32_t* qp_solves, int32_t memspace, void* stream) {
+  if (!h) return dg_set_err(DGSQP_EINVAL, "NULL handle");
+  return h->vt->solve_batch(h, B, x0, u_ws, l_ws, u_prev, u_out, l_out, x_out, cost_out, cond_out, num_iters, status, qp_solves, memspace, stream);
 }
 
 int dgsqp_measure_fp64_peak(int device, double* tflops) {

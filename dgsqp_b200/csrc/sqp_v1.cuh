@@ -162,6 +162,7 @@ struct SolveCtx {
   Dims D;
   Workspace W;
   const double* x0;
+  const double* up_in;   // previous input u_{-1} of this instance [nu] or null (v2 only: DGSQP_v2.py:328 keeps u_prev; v1 zeroes it, DGSQP.py:305)
   // work counters (maintained by thread 0: the context is shared by the CTA)
   int n_evals_full, n_evals_grad, n_gi_iters, n_neg_max, n_qp_indef, n_neg_sum, n_act_sum, n_ls_trials;
 };

@@ -136,7 +136,7 @@ DG_DEVN void sqp_solve_v2(Cta& c, SolveCtx& X, const double* u_ws, const double*
   game_row_table<SM>(c, D, E.rowtab);
   DG_FOR(j, n) S.u[j] = u_ws[j];
   DG_FOR(r, m) S.l[r] = 0.0;
-  DG_FOR(j, D.nu) S.up[j] = 0.0;
+  DG_FOR(j, D.nu) S.up[j] = X.up_in ? X.up_in[j] : 0.0;          // u_prev of the solver object (:328)
   c.sync();
   // dual initialisation (:333-337) and the first entry of the merit memory (:342-343)
   eval_grad<SM>(c, X, S.u, S.l, true);

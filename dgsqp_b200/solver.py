@@ -115,9 +115,10 @@ class DGSQP:
 
     def solve(self, states: List[VehicleState], parameters: np.ndarray = np.array([])):
         t0 = time.time()
-        self.u_prev = np.zeros(self.n_u)
+        if not self.v2:
+            self.u_prev = np.zeros(self.n_u)           # v1 zeroes u_prev in solve (DGSQP.py:305); v2 keeps it (DGSQP_v2.py:328)
         x0 = self.game.state2q(states)
-        res = self.solve_batch(x0[None], self.u_ws[None])
+        res = self.solve_batch(x0[None], self.u_ws[None], u_prev=np.asarray(self.u_prev, dtype=np.float64)[None] if self.v2 else None)
         msg = res.msg[0]
         self.q_pred = res.x[0].reshape(self.N + 1, self.n_q)
         self.u_pred = self.agent_to_stage_major(res.u)[0]
@@ -175,15 +176,16 @@ class DGSQP:
             pred.t = t
 
     # ------------------------------------------------------------------ batched entry point
-    def solve_batch(self, x0, u_ws, l_ws=None, stream: Optional[int] = None) -> BatchResult:
-        """Solve B instances.  ``x0`` [B, n_q], ``u_ws`` [B, n] agent-major.
+    def solve_batch(self, x0, u_ws, l_ws=None, stream: Optional[int] = None, u_prev=None) -> BatchResult:
+        """Solve B instances.  ``x0`` [B, n_q], ``u_ws`` [B, n] agent-major.  ``u_prev`` [B, n_u]: previous input of every
+        instance for receding-horizon use of the v2 policy (``DGSQP_v2.py:311,328``; v1 zeroes it, ``DGSQP.py:305``).
 
         NumPy inputs take the host path (H2D / D2H copies inside the library call); torch CUDA
         tensors take the device path (no copies, outputs are torch tensors on the same device)."""
         g = self.game
         is_torch = hasattr(x0, "is_cuda")
         if is_torch:
-            return self._solve_batch_device(x0, u_ws, l_ws, stream)
+            return self._solve_batch_device(x0, u_ws, l_ws, stream, u_prev=u_prev)
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         u_ws = np.ascontiguousarray(u_ws, dtype=np.float64)
         B = x0.shape[0]
@@ -194,18 +196,25 @@ class DGSQP:
             l_ws = np.ascontiguousarray(l_ws, dtype=np.float64)
             if l_ws.shape != (B, g.m):
                 raise RuntimeError('Dual warm start of shape %s is incompatible with required (B,%i)' % (l_ws.shape, g.m))
+        if u_prev is not None:
+            u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+            if u_prev.shape != (B, g.n_u):
+                raise RuntimeError('Previous inputs of shape %s are incompatible with required (B,%i)' % (u_prev.shape, g.n_u))
         u, l = np.empty((B, g.n)), np.empty((B, g.m))
         x = np.empty((B, (g.N + 1) * g.n_q))
         cost, cond = np.empty((B, g.M)), np.empty((B, 3))
         it, st, qp = (np.empty(B, dtype=np.int32) for _ in range(3))
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         t0 = time.perf_counter()
-        _abi.check(self._lib.dgsqp_solve_batch(self._h, B, p(x0), p(u_ws), p(l_ws) if l_ws is not None else None,
-                                               p(u), p(l), p(x), p(cost), p(cond), p(it), p(st), p(qp), 0,
-                                               C.c_void_p(stream or 0)))
+        lw = p(l_ws) if l_ws is not None else None
+        tail = (p(u), p(l), p(x), p(cost), p(cond), p(it), p(st), p(qp), 0, C.c_void_p(stream or 0))
+        if u_prev is None:
+            _abi.check(self._lib.dgsqp_solve_batch(self._h, B, p(x0), p(u_ws), lw, *tail))
+        else:
+            _abi.check(self._lib.dgsqp_solve_batch_up(self._h, B, p(x0), p(u_ws), lw, p(u_prev), *tail))
         return BatchResult(u, l, x, cost, cond, it, st, qp, time.perf_counter() - t0)
 
-    def _solve_batch_device(self, x0, u_ws, l_ws=None, stream=None, out=None, sync=True):
+    def _solve_batch_device(self, x0, u_ws, l_ws=None, stream=None, out=None, sync=True, u_prev=None):
         import torch
         g = self.game
         B = x0.shape[0]
@@ -223,8 +232,14 @@ class DGSQP:
             stream = torch.cuda.current_stream(dev).cuda_stream
         v = lambda t: C.c_void_p(t.data_ptr())
         lw = v(l_ws.contiguous()) if l_ws is not None else None
+        if u_prev is not None and not sync:
+            raise RuntimeError("u_prev needs the synchronous device call")
+        upv = v(u_prev.contiguous()) if u_prev is not None else None
         t0 = time.perf_counter()
-        if sync:
+        if sync and u_prev is not None:
+            _abi.check(self._lib.dgsqp_solve_batch_up(self._h, B, v(x0), v(u_ws), lw, upv, v(u), v(l), v(x), v(cost),
+                                                      v(cond), v(it), v(st), v(qp), 1, C.c_void_p(stream)))
+        elif sync:
             _abi.check(self._lib.dgsqp_solve_batch(self._h, B, v(x0), v(u_ws), lw, v(u), v(l), v(x), v(cost), v(cond),
                                                    v(it), v(st), v(qp), 1, C.c_void_p(stream)))
         else:

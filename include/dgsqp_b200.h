@@ -167,6 +167,14 @@ int dgsqp_solve_batch(dgsqp_handle* h, int32_t B, const double* x0, const double
                       double* x_out, double* cost_out, double* cond_out, int32_t* num_iters, int32_t* status,
                       int32_t* qp_solves, int32_t memspace, void* stream);
 
+/* dgsqp_solve_batch with the previous input u_{-1} of every instance (u_prev [B, n_u] or NULL = zeros; same memory space
+ * as the other buffers): the receding-horizon use of the v2 class, whose solve() keeps u_prev between calls
+ * (DGSQP_v2.py:311,328) -- it enters the input-rate costs and rate constraints of stage 0.  Handles created with
+ * DGSQPParams (v1) ignore it: v1's solve() zeroes u_prev on entry (DGSQP.py:305). */
+int dgsqp_solve_batch_up(dgsqp_handle* h, int32_t B, const double* x0, const double* u_ws, const double* l_ws, const double* u_prev,
+                         double* u_out, double* l_out, double* x_out, double* cost_out, double* cond_out, int32_t* num_iters,
+                         int32_t* status, int32_t* qp_solves, int32_t memspace, void* stream);
+
 /* Same as dgsqp_solve_batch with device pointers but only enqueues (no synchronisation). */
 int dgsqp_solve_batch_async(dgsqp_handle* h, int32_t B, const double* x0, const double* u_ws, const double* l_ws,
                             double* u_out,

@@ -70,7 +70,7 @@ void hs_dims(void* hp, int* out) { HsHandle* h = (HsHandle*)hp; out[0] = h->D.nq
 void hs_evaluate(void* hp, const double* x0, const double* u, const double* l, double* Q, double* q, double* gtl,
                  double* g, double* x) {
   HsHandle* h = (HsHandle*)hp; Cta c;
-  SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0;
+  SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0; X.up_in = nullptr;
   for (int i = 0; i < h->D.nu; ++i) h->W.S.up[i] = 0.0;
   eval_full<false>(c, X, u, l);
   memcpy(Q, h->W.E.Q, sizeof(double) * h->D.n * h->D.n);
@@ -106,16 +106,16 @@ int hs_qp(void* hp, double* H, const double* q, double* du, double* lam, int* it
 }
 int hs_lsqr(void* hp, const double* x0, const double* u, double* l_out) {
   HsHandle* h = (HsHandle*)hp; Cta c;
-  SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0;
+  SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0; X.up_in = nullptr;
   for (int i = 0; i < h->D.nu; ++i) h->W.S.up[i] = 0.0;
   std::vector<double> l0(h->D.m, 0.0);
   eval_grad<false>(c, X, u, l0.data(), true);
   return lsqr_dual_init<false>(c, h->D, h->W.E, h->W.L, h->W.E.q, l_out);
 }
-void hs_solve(void* hp, const double* x0, const double* u_ws, const double* l_ws, double* u, double* l, double* x, double* cost, double* cond,
+void hs_solve(void* hp, const double* x0, const double* u_ws, const double* l_ws, const double* u_prev, double* u, double* l, double* x, double* cost, double* cond,
               int* num_iters, int* status, int* qp_solves, int* diag, double* l_init) {
   HsHandle* h = (HsHandle*)hp; Cta c;
-  SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0;
+  SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0; X.up_in = u_prev;
   SolveOut O; O.u = u; O.l = l; O.x = x; O.cost = cost; O.cond = cond; O.num_iters = num_iters; O.status = status;
   O.qp_solves = qp_solves; O.diag = diag; O.l_init = l_init;
   if (h->P.policy == 2) sqp_solve_v2<false>(c, X, u_ws, l_ws, O);

@@ -124,7 +124,7 @@ class HostSim:
         itn = self.lib.hs_lsqr(self.h, _p(x0), _p(u), _p(l))
         return l, itn
 
-    def solve(self, x0, u_ws, l_ws=None):
+    def solve(self, x0, u_ws, l_ws=None, u_prev=None):
         n, m = self.n, self.m
         x0, u_ws = (np.ascontiguousarray(v, dtype=np.float64) for v in (x0, u_ws))
         u, l, x = np.zeros(n), np.zeros(m), np.zeros((self.game.N + 1, self.nq))
@@ -134,7 +134,10 @@ class HostSim:
         l_init = np.zeros(m)
         if l_ws is not None:
             l_ws = np.ascontiguousarray(l_ws, dtype=np.float64)
-        self.lib.hs_solve(self.h, _p(x0), _p(u_ws), _p(l_ws) if l_ws is not None else None, _p(u), _p(l), _p(x), _p(cost), _p(cond), C.byref(it),
+        if u_prev is not None:
+            u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+        self.lib.hs_solve(self.h, _p(x0), _p(u_ws), _p(l_ws) if l_ws is not None else None,
+                          _p(u_prev) if u_prev is not None else None, _p(u), _p(l), _p(x), _p(cost), _p(cond), C.byref(it),
                           C.byref(st), C.byref(qp), _p(diag), _p(l_init))
         return dict(u=u, l=l, x=x, cost=cost, cond=cond, num_iters=it.value, status=st.value, qp_solves=qp.value,
                     diag=diag, l_init=l_init)

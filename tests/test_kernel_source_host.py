@@ -275,3 +275,26 @@ def test_no_buffer_overruns_guard_build(budget, monkeypatch):
             r = hs.solve(x0[i], u_ws[i])
             assert r["status"] in (0, 1, 2, 3, 4)
             assert hs.guard_check() == 0, f"buffer overrun in {game.name} (n = {game.n})"
+
+
+def test_v2_u_prev_matches_oracle():
+    """Receding-horizon input of the v2 policy: u_prev (DGSQP_v2.py:311,328) enters the stage-0 rate cost and rate
+    constraints; kernel source == oracle, and the v1 policy ignores it (DGSQP.py:305 zeroes u_prev)."""
+    from oracle.dgsqp_v2 import OracleDGSQPV2
+    from oracle.sampler import sample_head_to_head
+    N = 10
+    kw = dict(reg=1e-2, reg_decay=0.8, nms_frequency=2, sqp_iters=40, p_tol=1e-4, d_tol=1e-4)
+    game, og = dg.chicane_game(N=N), RacingGame(chicane_track(), M=2, N=N)
+    hs, sol = HostSim(game, dg.DGSQPV2Params(N=N, **kw)), OracleDGSQPV2(og, **kw)
+    hs1 = HostSim(game, dg.chicane_params(N))
+    rng = np.random.default_rng(0)
+    up = np.array([1.5, 0.3, -1.0, -0.2])
+    for i in range(3):
+        x0, u_ws = sample_head_to_head(og, rng)
+        r0, r = sol.solve(x0, u_ws), sol.solve(x0, u_ws, u_prev=up)
+        h = hs.solve(x0, u_ws, u_prev=up)
+        assert MSG[h["status"]] == r["msg"] and h["num_iters"] == r["num_iters"]
+        assert np.abs(h["u"] - r["u"]).max() < 1e-9 and np.abs(h["cost"] - r["cost"]).max() < 1e-9
+        assert np.abs(r["u"] - r0["u"]).max() > 1e-2                      # the previous input matters
+        a, b = hs1.solve(x0, u_ws), hs1.solve(x0, u_ws, u_prev=up)
+        assert np.array_equal(a["u"], b["u"])                              # v1: ignored
