@@ -37,14 +37,15 @@ def test_struct_layout_matches_header():
     src = textwrap.dedent("""
         #include <stdio.h>
         #include "dgsqp_b200.h"
-        int main(void) { printf("%zu %zu %zu\\n", sizeof(dgsqp_racing_game), sizeof(dgsqp_params), sizeof(dgsqp_v2_params)); return 0; }
+        int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(dgsqp_racing_game), sizeof(dgsqp_params), sizeof(dgsqp_v2_params), sizeof(dgsqp_merge_game), sizeof(dgsqp_lane_row)); return 0; }
     """)
     with tempfile.TemporaryDirectory() as d:
         p = pathlib.Path(d)
         (p / "t.c").write_text(src)
         subprocess.check_call(["gcc", "-I", str(ROOT / "include"), "-o", str(p / "t"), str(p / "t.c")])
-        a, b, c2 = map(int, subprocess.check_output([str(p / "t")]).split())
+        a, b, c2, d2, e2 = map(int, subprocess.check_output([str(p / "t")]).split())
     assert (a, b, c2) == (C.sizeof(_abi.RacingGameStruct), C.sizeof(_abi.ParamsStruct), C.sizeof(_abi.ParamsV2Struct))
+    assert (d2, e2) == (C.sizeof(_abi.MergeGameStruct), C.sizeof(_abi.LaneRowStruct))
 
 
 def test_create_fails_loudly_without_gpu():
