@@ -2,6 +2,7 @@
 // The track tables restate RadiusArclengthTrack.get_track_key_pts / get_curvature_casadi_fn /
 // get_tangent_angle_casadi_fn (DGSQP/tracks/radius_arclength_track.py:361-408,199-225).
 #pragma once
+#include <cstdlib>
 #include "../../include/dgsqp_b200.h"
 #include "game.cuh"
 #include "sqp_v2.cuh"
@@ -75,6 +76,7 @@ static inline int dg_fill_params(const dgsqp_params* p, SolverParams* P) {
   P->dbg_l0_perturb = 0.0;
   P->mu_vio_thresh = p->mu_vio_thresh;
   P->merit_obj = 0;
+  { const char* e = getenv("DGSQP_QP_WARM"); P->qp_warm = (e && e[0] == '1') ? 1 : 0; }    // experimental, off by default
   P->policy = 1; P->nms = 0; P->nms_frequency = 0; P->nms_memory = 1; P->armijo = 1; P->has_merit_parameter = 0;
   P->reg_decay = 1.0; P->sigma = 0.0; P->gamma = 1.0; P->merit_parameter = 0.0;
   return 0;
@@ -96,6 +98,7 @@ static inline int dg_fill_params_v2(const dgsqp_v2_params* p, SolverParams* P) {
   P->dbg_l0_perturb = 0.0;
   P->mu_vio_thresh = p->mu_vio_thresh;
   P->merit_obj = p->merit_function == 1;
+  { const char* e = getenv("DGSQP_QP_WARM"); P->qp_warm = (e && e[0] == '1') ? 1 : 0; }
   P->policy = 2; P->nms = p->nms != 0; P->nms_frequency = p->nms_frequency; P->nms_memory = p->nms_memory_size;
   P->armijo = p->merit_decrease_condition == 0; P->has_merit_parameter = p->has_merit_parameter != 0;
   P->reg_decay = p->reg_decay; P->sigma = p->merit_decrease; P->gamma = p->delta_decay; P->merit_parameter = p->merit_parameter;

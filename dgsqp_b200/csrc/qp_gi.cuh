@@ -65,11 +65,134 @@ DG_DEV void gi_cols_times(Cta& c, int n, int ld, const double* DG_RESTRICT Y, co
   }
 }
 
+// Warm start of the dual active-set method from the active set of the previous QP of this instance (SolverParams::qp_warm,
+// off by default; successive SQP iterations share most of their active set).  Starting from the unconstrained minimiser
+// x0 in Q.xq and Y = L^-1:
+//   (1) the previous constraints are added to the factorisation one by one (same Householder update as a full step,
+//       linearly dependent ones are skipped) without the step-length logic;
+//   (2) the equality-constrained minimiser on that set follows from two triangular solves:
+//       r = g_W + G_W x0,  t = R^-T r,  lam = R^-1 t,  x = x0 + J1 t;
+//   (3) constraints whose multiplier comes out negative are dropped (most negative first, Givens re-triangularisation)
+//       and (2) is repeated, until (x, lam >= 0, W) is an S-pair from which the method continues unchanged.
+// The QP is strictly convex, so the solution is the same as from a cold start (up to rounding); only the path differs.
+// Returns the number of active constraints; Q.act / Q.is_act / Q.lam_act / Q.xq are set accordingly.
+// Prototype: plain CTA-wide loops, not tuned.
+template <bool SM>
+DG_DEVN int gi_warm_start(Cta& c, const Dims& D_, const EvalBuf& E_, const QpBuf& Q_, const LinBuf& B_, int nprev) {
+  const EvalBuf E = E_; const QpBuf Q = Q_; const LinBuf B = B_; const Dims D = D_;
+  const int n = D.n, ld = B.ld;
+  double* Y = B.matB;
+  double* Rm = B.matA;
+  int iq = 0;
+  for (int k = 0; k < nprev; ++k) {
+    const int p = Q.act[k];
+    c.sync();
+    if (p < 0 || p >= D.m) continue;
+    game_G_row<SM>(c, D, E, p, Q.npv);
+    for (int j = c.warp(); j < n; j += c.nwarps()) {
+      double acc = 0.0;
+      for (int i = c.lane(); i < n; i += c.wsz) acc += Y[j * ld + i] * Q.npv[i];
+      acc = c.warp_sum(acc);
+      if (c.lane() == 0) Q.dv[j] = -acc;
+    }
+    c.sync();
+    double zn = 0.0, dall = 0.0;
+    DG_FOR(j, n) { const double dj = Q.dv[j]; dall += dj * dj; if (j >= iq) zn += dj * dj; }
+    c.sum2(zn, dall);
+    if (!(zn > DG_QP_DEP_TOL * dall && zn > 0.0)) continue;          // linearly dependent on the ones already in
+    const int len = n - iq;
+    const double d0 = Q.dv[iq];
+    double alpha = sqrt(zn);
+    if (d0 > 0.0) alpha = -alpha;
+    const double vv = 2.0 * (zn - alpha * d0);
+    c.sync();
+    if (vv > 0.0) {
+      const double sc = 2.0 / vv;
+      DG_FOR(i, n) {
+        double acc = (d0 - alpha) * Y[iq * ld + i];
+        for (int j = 1; j < len; ++j) acc += Q.dv[iq + j] * Y[(iq + j) * ld + i];
+        Q.zv[i] = acc * sc;
+      }
+      c.sync();
+      DG_FOR(i, n) {
+        const double wi = Q.zv[i];
+        Y[iq * ld + i] -= (d0 - alpha) * wi;
+        for (int j = 1; j < len; ++j) Y[(iq + j) * ld + i] -= Q.dv[iq + j] * wi;
+      }
+    }
+    DG_FOR(i, iq) Rm[i * ld + iq] = Q.dv[i];
+    if (c.tid() == 0) { Rm[iq * ld + iq] = alpha; Q.act[iq] = p; Q.is_act[p] = 1; }
+    ++iq;
+    c.sync();
+  }
+  if (iq == 0) return 0;
+  game_G_times<SM>(c, D, E, Q.xq, Q.sl);                             // G x0
+  while (iq > 0) {
+    // r = g_W + G_W x0;  t = R^-T r (into zv);  lam = R^-1 t (into lam_act)      -- serial prototype on one thread
+    if (c.tid() == 0) {
+      for (int k = 0; k < iq; ++k) {
+        double v = E.g[Q.act[k]] + Q.sl[Q.act[k]];
+        for (int i = 0; i < k; ++i) v -= Rm[i * ld + k] * Q.zv[i];
+        Q.zv[k] = v / Rm[k * ld + k];
+      }
+      for (int k = iq - 1; k >= 0; --k) {
+        double v = Q.zv[k];
+        for (int j = k + 1; j < iq; ++j) v -= Rm[k * ld + j] * Q.lam_act[j];
+        Q.lam_act[k] = v / Rm[k * ld + k];
+      }
+    }
+    c.sync();
+    double worst = 0.0; int ldrop = -1;
+    for (int k = 0; k < iq; ++k) { const double lk = Q.lam_act[k]; if (lk < worst) { worst = lk; ldrop = k; } }
+    if (ldrop < 0) break;
+    c.sync();
+    // drop ldrop: same re-triangularisation as a partial step of the main loop
+    if (c.tid() == 0) {
+      Q.is_act[Q.act[ldrop]] = 0;
+      for (int k = ldrop; k < iq - 1; ++k) Q.act[k] = Q.act[k + 1];
+    }
+    DG_FOR(i, iq) {
+      for (int j = ldrop; j < iq - 1; ++j) Rm[i * ld + j] = Rm[i * ld + j + 1];
+      Rm[i * ld + iq - 1] = 0.0;
+    }
+    c.sync();
+    for (int j = ldrop; j < iq - 1; ++j) {
+      const double a = Rm[j * ld + j], b = Rm[(j + 1) * ld + j];
+      const double h = hypot(a, b);
+      c.sync();
+      if (h != 0.0) {
+        const double cs = a / h, sn = b / h;
+        for (int col = j + c.tid(); col < iq - 1; col += c.nt()) {
+          const double r0 = Rm[j * ld + col], r1 = Rm[(j + 1) * ld + col];
+          Rm[j * ld + col] = cs * r0 + sn * r1;
+          Rm[(j + 1) * ld + col] = -sn * r0 + cs * r1;
+        }
+        DG_FOR(i, n) {
+          const double j0 = Y[j * ld + i], j1 = Y[(j + 1) * ld + i];
+          Y[j * ld + i] = cs * j0 + sn * j1;
+          Y[(j + 1) * ld + i] = -sn * j0 + cs * j1;
+        }
+      }
+      c.sync();
+    }
+    --iq;
+  }
+  // x = x0 + J1 t
+  c.sync();
+  DG_FOR(i, n) {
+    double acc = 0.0;
+    for (int j = 0; j < iq; ++j) acc += Y[j * ld + i] * Q.zv[j];
+    Q.xq[i] += acc;
+  }
+  c.sync();
+  return iq;
+}
+
 // H (symmetric positive definite) is expected in B.matA and is destroyed.
 // returns 0 ok, 1 not PD, 2 infeasible, 3 iteration limit.  Output: Q.xq (du), Q.lam (l_hat).
 template <bool SM>
 DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double* DG_RESTRICT qv,
-                        const QpBuf& Q_, const LinBuf& B_, int* n_iter_out, int* n_active_out) {
+                        const QpBuf& Q_, const LinBuf& B_, int* n_iter_out, int* n_active_out, int warm = 0) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
   const EvalBuf E = E_; DG_SH_EVAL(E); const QpBuf Q = Q_; DG_SH_QP(Q); const LinBuf B = B_; DG_SH_LIN(B); const Dims D = D_;
   const int n = D.n, m = D.m, ld = B.ld;
@@ -92,6 +215,8 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
   gi_cols_times<SM>(c, n, ld, Y, Q.dv, 0, B.part, Q.xq, -1.0);
   c.lap(PH_TRINV);
   int iq = 0, it = 0;
+  // active set of the previous QP of this instance: ids in Q.act[0..), count parked in Q.act[n] (see sqp_solve_*)
+  if (warm) { const int nprev = Q.act[n]; c.sync(); if (nprev > 0 && nprev <= n) iq = gi_warm_start<SM>(c, D, E, Q, B, nprev); }
   const int max_iter = 10 * (n + m);
   const Split2 sp = split2(c, n);                 // one decomposition for every n-wide sweep of the loop (integer divisions)
   int status = 0;
@@ -342,6 +467,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
     DG_FOR(k, iq) Q.lam[Q.act[k]] = Q.lam_act[k];
     c.sync();
   }
+  if (c.tid() == 0) Q.act[n] = status == 0 ? iq : 0;               // remembered for a warm start of the next QP
   if (n_iter_out) *n_iter_out = it;
   if (n_active_out) *n_active_out = iq;
   c.lap(PH_GI);

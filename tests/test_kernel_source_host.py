@@ -298,3 +298,25 @@ def test_v2_u_prev_matches_oracle():
         assert np.abs(r["u"] - r0["u"]).max() > 1e-2                      # the previous input matters
         a, b = hs1.solve(x0, u_ws), hs1.solve(x0, u_ws, u_prev=up)
         assert np.array_equal(a["u"], b["u"])                              # v1: ignored
+
+
+def test_experimental_qp_warm_start(monkeypatch):
+    """DGSQP_QP_WARM=1 (off by default): the active-set QP starts from the previous QP's active set (qp_gi.cuh:
+    gi_warm_start).  The strictly convex QP has one solution, so full solves must reach the same equilibria as the cold
+    start with far fewer active-set iterations."""
+    from dgsqp_b200.montecarlo import sample_head_to_head, sample_merge
+    for game, params, (x0, u_ws) in ((dg.chicane_game(N=15), dg.chicane_params(15), sample_head_to_head(dg.chicane_game(N=15), 6, seed=2)),
+                                      (dg.merge_game(N=10), dg.merge_params(10), sample_merge(dg.merge_game(N=10), 4, seed=1))):
+        monkeypatch.setenv("DGSQP_QP_WARM", "0")
+        cold = HostSim(game, params)
+        monkeypatch.setenv("DGSQP_QP_WARM", "1")
+        warm = HostSim(game, params)
+        it_c = it_w = agree = 0
+        for i in range(x0.shape[0]):
+            a, b = cold.solve(x0[i], u_ws[i]), warm.solve(x0[i], u_ws[i])
+            it_c, it_w = it_c + a["diag"][2], it_w + b["diag"][2]
+            if a["status"] == b["status"] and a["num_iters"] == b["num_iters"]:
+                agree += 1
+                if a["status"] == 0:
+                    assert np.abs(a["x"] - b["x"]).max() < 1e-5 * max(1.0, np.abs(a["x"]).max())
+        assert agree >= x0.shape[0] - 1 and it_w < 0.6 * it_c
