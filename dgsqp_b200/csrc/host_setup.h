@@ -76,7 +76,9 @@ static inline int dg_fill_params(const dgsqp_params* p, SolverParams* P) {
   P->dbg_l0_perturb = 0.0;
   P->mu_vio_thresh = p->mu_vio_thresh;
   P->merit_obj = 0;
+#ifdef DG_QP_WARM_START
   { const char* e = getenv("DGSQP_QP_WARM"); P->qp_warm = (e && e[0] == '1') ? 1 : 0; }    // experimental, off by default
+#endif
   P->policy = 1; P->nms = 0; P->nms_frequency = 0; P->nms_memory = 1; P->armijo = 1; P->has_merit_parameter = 0;
   P->reg_decay = 1.0; P->sigma = 0.0; P->gamma = 1.0; P->merit_parameter = 0.0;
   return 0;
@@ -98,7 +100,9 @@ static inline int dg_fill_params_v2(const dgsqp_v2_params* p, SolverParams* P) {
   P->dbg_l0_perturb = 0.0;
   P->mu_vio_thresh = p->mu_vio_thresh;
   P->merit_obj = p->merit_function == 1;
+#ifdef DG_QP_WARM_START
   { const char* e = getenv("DGSQP_QP_WARM"); P->qp_warm = (e && e[0] == '1') ? 1 : 0; }
+#endif
   P->policy = 2; P->nms = p->nms != 0; P->nms_frequency = p->nms_frequency; P->nms_memory = p->nms_memory_size;
   P->armijo = p->merit_decrease_condition == 0; P->has_merit_parameter = p->has_merit_parameter != 0;
   P->reg_decay = p->reg_decay; P->sigma = p->merit_decrease; P->gamma = p->delta_decay; P->merit_parameter = p->merit_parameter;

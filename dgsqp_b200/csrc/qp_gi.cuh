@@ -65,6 +65,7 @@ DG_DEV void gi_cols_times(Cta& c, int n, int ld, const double* DG_RESTRICT Y, co
   }
 }
 
+#ifdef DG_QP_WARM_START
 // Warm start of the dual active-set method from the active set of the previous QP of this instance (SolverParams::qp_warm,
 // off by default; successive SQP iterations share most of their active set).  Starting from the unconstrained minimiser
 // x0 in Q.xq and Y = L^-1:
@@ -187,12 +188,19 @@ DG_DEVN int gi_warm_start(Cta& c, const Dims& D_, const EvalBuf& E_, const QpBuf
   c.sync();
   return iq;
 }
+#define DG_WARM_PARAM , int warm = 0
+#define DG_WARM_ARG(x) , (x)
+#else
+// (the experimental warm start is compiled out of the product: even unused, the extra call site cost 5 % in this function)
+#define DG_WARM_PARAM
+#define DG_WARM_ARG(x)
+#endif
 
 // H (symmetric positive definite) is expected in B.matA and is destroyed.
 // returns 0 ok, 1 not PD, 2 infeasible, 3 iteration limit.  Output: Q.xq (du), Q.lam (l_hat).
 template <bool SM>
 DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double* DG_RESTRICT qv,
-                        const QpBuf& Q_, const LinBuf& B_, int* n_iter_out, int* n_active_out, int warm = 0) {
+                        const QpBuf& Q_, const LinBuf& B_, int* n_iter_out, int* n_active_out DG_WARM_PARAM) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
   const EvalBuf E = E_; DG_SH_EVAL(E); const QpBuf Q = Q_; DG_SH_QP(Q); const LinBuf B = B_; DG_SH_LIN(B); const Dims D = D_;
   const int n = D.n, m = D.m, ld = B.ld;
@@ -215,8 +223,10 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
   gi_cols_times<SM>(c, n, ld, Y, Q.dv, 0, B.part, Q.xq, -1.0);
   c.lap(PH_TRINV);
   int iq = 0, it = 0;
+#ifdef DG_QP_WARM_START
   // active set of the previous QP of this instance: ids in Q.act[0..), count parked in Q.act[n] (see sqp_solve_*)
   if (warm) { const int nprev = Q.act[n]; c.sync(); if (nprev > 0 && nprev <= n) iq = gi_warm_start<SM>(c, D, E, Q, B, nprev); }
+#endif
   const int max_iter = 10 * (n + m);
   const Split2 sp = split2(c, n);                 // one decomposition for every n-wide sweep of the loop (integer divisions)
   int status = 0;
@@ -467,7 +477,9 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
     DG_FOR(k, iq) Q.lam[Q.act[k]] = Q.lam_act[k];
     c.sync();
   }
+#ifdef DG_QP_WARM_START
   if (c.tid() == 0) Q.act[n] = status == 0 ? iq : 0;               // remembered for a warm start of the next QP
+#endif
   if (n_iter_out) *n_iter_out = it;
   if (n_active_out) *n_active_out = iq;
   c.lap(PH_GI);

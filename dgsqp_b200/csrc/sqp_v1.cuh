@@ -21,7 +21,9 @@ struct SolverParams {
   // v2 step policy (DGSQPV2Params, DGSQP_v2.py:55-230); policy = 1: v1 (sqp_v1.cuh), 2: v2 (sqp_v2.cuh)
   int policy, nms, nms_frequency, nms_memory, armijo, has_merit_parameter;
   int merit_obj;           // v2 merit 'sum_obj_l1' (sum of the agents' costs) instead of 'stat_l1'
+#ifdef DG_QP_WARM_START
   int qp_warm;             // experimental: warm-start the active-set QP from the previous active set (qp_gi.cuh: gi_warm_start)
+#endif
   double reg_decay, sigma, gamma, merit_parameter;
 };
 
@@ -291,7 +293,7 @@ DG_DEVN int solve_qp_here(Cta& c, SolveCtx& X) {
     if (nneg > 0) { ++X.n_qp_indef; X.n_neg_sum += nneg; }
   }
   int it = 0, na = 0;
-  int st = qp_solve_gi<SM>(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na, X.P->qp_warm);
+  int st = qp_solve_gi<SM>(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na DG_WARM_ARG(X.P->qp_warm));
   if (c.tid() == 0) { X.n_gi_iters += it; X.n_act_sum += na; }
   return st;
 }
@@ -417,7 +419,10 @@ template <bool SM>
 DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double* l_ws, const SolveOut& O) {
   const Dims D = X.D; const SqpBuf S = X.W.S; const EvalBuf E = X.W.E; DG_SH_EVAL(E); const SolverParams P = *X.P;
   const int n = D.n, m = D.m;
-  if (c.tid() == 0) { X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0; X.W.Q.act[n] = 0; }
+  if (c.tid() == 0) { X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0; }
+#ifdef DG_QP_WARM_START
+  if (c.tid() == 0) X.W.Q.act[n] = 0;
+#endif
   game_row_table<SM>(c, D, E.rowtab);
   DG_FOR(j, n) S.u[j] = u_ws[j];
   DG_FOR(r, m) S.l[r] = 0.0;

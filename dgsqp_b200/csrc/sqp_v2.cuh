@@ -132,7 +132,10 @@ template <bool SM>
 DG_DEVN void sqp_solve_v2(Cta& c, SolveCtx& X, const double* u_ws, const double* l_ws, const SolveOut& O) {
   const Dims D = X.D; const SqpBuf S = X.W.S; const EvalBuf E = X.W.E; DG_SH_EVAL(E); const SolverParams P = *X.P;
   const int n = D.n, m = D.m;
-  if (c.tid() == 0) { X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0; X.W.Q.act[n] = 0; }
+  if (c.tid() == 0) { X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0; }
+#ifdef DG_QP_WARM_START
+  if (c.tid() == 0) X.W.Q.act[n] = 0;
+#endif
   game_row_table<SM>(c, D, E.rowtab);
   DG_FOR(j, n) S.u[j] = u_ws[j];
   DG_FOR(r, m) S.l[r] = 0.0;
@@ -186,7 +189,7 @@ DG_DEVN void sqp_solve_v2(Cta& c, SolveCtx& X, const double* u_ws, const double*
     int nneg = nearest_pd<SM>(c, n, E.Q, X.W.B, P.eig_floor, reg, true);
     if (c.tid() == 0) { if (nneg > X.n_neg_max) X.n_neg_max = nneg; if (nneg > 0) { ++X.n_qp_indef; X.n_neg_sum += nneg; } }
     int gi_it = 0, gi_na = 0;
-    const int qp_st = qp_solve_gi<SM>(c, D, E, E.q, X.W.Q, X.W.B, &gi_it, &gi_na, P.qp_warm);
+    const int qp_st = qp_solve_gi<SM>(c, D, E, E.q, X.W.Q, X.W.B, &gi_it, &gi_na DG_WARM_ARG(P.qp_warm));
     if (c.tid() == 0) { X.n_gi_iters += gi_it; X.n_act_sum += gi_na; }
     ++total_qp;
     bool d_step = false, m_step = false;

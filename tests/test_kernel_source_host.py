@@ -301,16 +301,16 @@ def test_v2_u_prev_matches_oracle():
 
 
 def test_experimental_qp_warm_start(monkeypatch):
-    """DGSQP_QP_WARM=1 (off by default): the active-set QP starts from the previous QP's active set (qp_gi.cuh:
-    gi_warm_start).  The strictly convex QP has one solution, so full solves must reach the same equilibria as the cold
+    """Experimental, compiled out of the product (-DDG_QP_WARM_START, then DGSQP_QP_WARM=1): the active-set QP starts
+    from the previous QP's active set (qp_gi.cuh: gi_warm_start).  The strictly convex QP has one solution, so full solves must reach the same equilibria as the cold
     start with far fewer active-set iterations."""
     from dgsqp_b200.montecarlo import sample_head_to_head, sample_merge
     for game, params, (x0, u_ws) in ((dg.chicane_game(N=15), dg.chicane_params(15), sample_head_to_head(dg.chicane_game(N=15), 6, seed=2)),
                                       (dg.merge_game(N=10), dg.merge_params(10), sample_merge(dg.merge_game(N=10), 4, seed=1))):
         monkeypatch.setenv("DGSQP_QP_WARM", "0")
-        cold = HostSim(game, params)
+        cold = HostSim(game, params, warm=True)
         monkeypatch.setenv("DGSQP_QP_WARM", "1")
-        warm = HostSim(game, params)
+        warm = HostSim(game, params, warm=True)
         it_c = it_w = agree = 0
         for i in range(x0.shape[0]):
             a, b = cold.solve(x0[i], u_ws[i]), warm.solve(x0[i], u_ws[i])
