@@ -320,3 +320,26 @@ def test_experimental_qp_warm_start(monkeypatch):
                 if a["status"] == 0:
                     assert np.abs(a["x"] - b["x"]).max() < 1e-5 * max(1.0, np.abs(a["x"]).max())
         assert agree >= x0.shape[0] - 1 and it_w < 0.6 * it_c
+
+
+@pytest.mark.parametrize("nonmono,merit", [(True, "stat_l1"), (False, "stat_l1"), (True, "stat"), (False, "stat")])
+def test_ablation_variants_match_oracle(nonmono, merit):
+    """The four solver variants of scripts/DGSQP_monte_carlo_ablation.py:166-225 (watchdog on / off x merit with / without
+    the l1 penalty): kernel source == oracle."""
+    from oracle.sampler import sample_head_to_head
+    N = 15
+    game, og = dg.chicane_game(N=N), RacingGame(chicane_track(), M=2, N=N)
+    params = dg.DGSQPParams(dt=0.1, N=N, reg=1e-3, nonmono_ls=nonmono, merit_function=merit, line_search_iters=50,
+                            sqp_iters=50, p_tol=1e-3, d_tol=1e-3, beta=0.01, tau=0.5)
+    hs, sol = HostSim(game, params), OracleDGSQP(og, reg=1e-3, nonmono_ls=nonmono, merit_function=merit)
+    rng = np.random.default_rng(7)
+    same = 0
+    for i in range(5):
+        x0, u_ws = sample_head_to_head(og, rng)
+        r, h = sol.solve(x0, u_ws), hs.solve(x0, u_ws)
+        if MSG[h["status"]] == r["msg"] and h["num_iters"] == r["num_iters"]:
+            same += 1
+            assert h["qp_solves"] == r["qp_solves"]
+            if r["msg"] == "conv_abs_tol":
+                assert np.abs(h["u"] - r["u"]).max() < 1e-6 * max(1.0, np.abs(r["u"]).max())
+    assert same >= 4
