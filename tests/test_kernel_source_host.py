@@ -343,3 +343,23 @@ def test_ablation_variants_match_oracle(nonmono, merit):
             if r["msg"] == "conv_abs_tol":
                 assert np.abs(h["u"] - r["u"]).max() < 1e-6 * max(1.0, np.abs(r["u"]).max())
     assert same >= 4
+
+
+@pytest.mark.parametrize("theta,N", [(45.0, 10), (75.0, 15), (90.0, 20)])
+def test_curve_sweep_cells_match_oracle(theta, N):
+    """Cells of the curve sweep (scripts/DGSQP_ALGAMES_monte_carlo_curve.py:134-146: theta x N, seed 1, reg = 0) with
+    short horizons (n = 40, 60, 80): kernel source == oracle, status and iteration count; trajectories on KKT-converged
+    instances (reg = 0: tolerance as for the merge game)."""
+    from oracle.sampler import sample_head_to_head
+    og = RacingGame(curve_track(curve_angle=theta * np.pi / 180), M=2, N=N, rate_ub=(10.0, 4.5), rate_lb=(-10.0, -4.5), obs_r=0.2)
+    hs, sol = HostSim(dg.curve_game(theta, N), dg.curve_params(N)), OracleDGSQP(og, reg=0.0)
+    rng = np.random.default_rng(1)
+    same = 0
+    for i in range(3):
+        x0, u_ws = sample_head_to_head(og, rng)
+        r, h = sol.solve(x0, u_ws), hs.solve(x0, u_ws)
+        if MSG[h["status"]] == r["msg"] and h["num_iters"] == r["num_iters"]:
+            same += 1
+            if r["msg"] == "conv_abs_tol":
+                assert np.abs(h["x"] - r["x"]).max() < 1e-5 * max(1.0, np.abs(r["x"]).max())
+    assert same >= 2
