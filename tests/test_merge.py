@@ -187,3 +187,30 @@ def test_host_class_surface_merge():
     assert s.lane[0][0].brk == float("inf") and s.goal[1][0] == 4.5 and s.term_scale == 10.0
     with pytest.raises(ValueError):
         dg.MergeGame(M=3, obs_r=[0.1, 0.1])
+
+
+@pytest.mark.parametrize("M,idx", [(2, [0, 2]), (4, [0, 1, 2, 2])])
+def test_merge_game_other_agent_counts(M, idx):
+    """The merge record is not tied to three cars: two (one straight-lane car + the ramp car) and four agents, kernel
+    source == oracle for the evaluation and for a full solve (same status; the 4-car start is infeasible: 'qp_fail')."""
+    from dgsqp_b200.games import merge_lanes as product_lanes
+    from oracle.merge_game import merge_lanes as oracle_lanes
+    N = 8
+    goals = [(4.0, .15, .3, 0), (4.5, .15, .3, 0), (4.25, .15, .3, 0), (3.5, .15, .3, 0)][:M]
+    pl, ol = product_lanes(), oracle_lanes()
+    g = dg.MergeGame(M=M, N=N, goals=goals, obs_r=[0.1] * M, lanes=[pl[i] for i in idx])
+    og = MergeGame(M=M, N=N, goals=goals, obs_r=[0.1] * M, lanes=[ol[i] for i in idx])
+    assert (g.n, g.m, g.n_c) == (og.n, og.m, og.n_c)
+    hs = HostSim(g, dg.DGSQPParams(N=N, reg=1e-3))
+    x3 = oracle_sample_merge(1, seed=1)[0].reshape(3, 4)
+    x0 = np.concatenate([x3[i] + (0.0 if k < 3 else np.array([-0.6, 0, 0, 0])) for k, i in enumerate(idx)])
+    rng = np.random.default_rng(0)
+    u, l = rng.normal(size=og.n) * 0.3, np.abs(rng.normal(size=og.m)) * 0.2
+    Q, q, G, gg, x = og.evaluate(u, l, x0, np.zeros(og.n_u))
+    Qh, qh, gtl, gh, xh = hs.evaluate(x0, u, l)
+    assert np.abs(Q - Qh).max() < 1e-12 and np.abs(q - qh).max() < 1e-12 and np.abs(gg - gh).max() < 1e-13
+    assert np.abs(G - hs.G_dense()).max() < 1e-13 and np.abs(G.T @ l - gtl).max() < 1e-12
+    r, h = OracleDGSQP(og, reg=1e-3).solve(x0, np.zeros(og.n)), hs.solve(x0, np.zeros(og.n))
+    assert MSG[h["status"]] == r["msg"] and h["num_iters"] == r["num_iters"]
+    if r["status"]:
+        assert _rel(h["u"], r["u"]) < 1e-8
