@@ -37,7 +37,7 @@ def nearest_pd(A, floor=1e-10):
 class OracleDGSQP:
     def __init__(self, game, reg=1e-3, line_search_iters=50, nonmono_ls=True, sqp_iters=50,
                  p_tol=1e-3, d_tol=1e-3, beta=0.01, tau=0.5, merit_function="stat_l1",
-                 conv_approx=True, mu_vio_thresh=1e-10, dual_init_method="reorth"):
+                 conv_approx=True, mu_vio_thresh=1e-10, dual_init_method="reorth", qp_method="gi", osqp_kw=None):
         self.game = game
         self.reg, self.line_search_iters, self.nonmono_ls = reg, line_search_iters, nonmono_ls
         self.sqp_iters, self.p_tol, self.d_tol, self.beta, self.tau = sqp_iters, p_tol, d_tol, beta, tau
@@ -46,6 +46,10 @@ class OracleDGSQP:
         # `thresh` in _get_mu (DGSQP.py:560) is 0 in the reference; see module docstring
         self.mu_vio_thresh = mu_vio_thresh
         self.dual_init_method = dual_init_method        # 'reorth' (canonical) or 'scipy' (the literal call)
+        # 'gi': exact KKT point (canonical, deviation D1); 'osqp': OSQP restated at its defaults with polish
+        # (oracle/osqp_admm.py) -- the literal mode; like v1 it uses whatever iterate comes back (DGSQP.py:246-249)
+        self.qp_method = qp_method
+        self.osqp_kw = dict(osqp_kw or {})
         self.qp_stats = []            # per-QP diagnostics (active-set size, negative eigenvalues, ...)
         self.trace = None
 
@@ -61,6 +65,14 @@ class OracleDGSQP:
         if self.reg > 0:
             H = H + self.reg * np.eye(H.shape[0])
         st = dict(n_neg=n_neg)
+        if self.qp_method == "osqp":
+            from .osqp_admm import solve_osqp
+            r = solve_osqp(H, q, G, -g, **self.osqp_kw)
+            st.update(osqp_status=r.status, iters=r.iters, polished=r.polished, rho_updates=r.rho_updates)
+            self.qp_stats.append(st)
+            if not (np.all(np.isfinite(r.x)) and np.all(np.isfinite(r.y))):
+                return None, None
+            return r.x, r.y
         try:
             du, l_hat = solve_qp_gi(H, q, G, g, stats=st)
         except QPFailure as e:
