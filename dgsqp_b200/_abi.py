@@ -12,7 +12,9 @@ MAX_TRACK_SEGS = 8
 
 NDIAG = 8   # DGSQP_NDIAG
 PHASES = ["lin_full", "adj_full", "hessian", "pd_tridiag", "pd_eig", "cholesky", "tri_inverse", "active_set", "lsqr",
-          "lin_grad", "adj_grad", "merit", "other"]
+          "lin_grad", "adj_grad", "merit", "other",
+          # sub-phases, non-zero only in the profiling build (-DDG_FINE_PHASES, scripts/build_prof.sh)
+          "pd_sym", "pd_eigval", "pd_invit", "pd_back", "gi_slack", "gi_dz", "gi_step", "gi_add", "gi_drop", "qp_x0", "qp_warm"]
 
 STATUS_MSG = {0: "conv_abs_tol", 1: "conv_rel_tol", 2: "max_it", 3: "diverged", 4: "qp_fail", 5: "time_limit"}
 
@@ -48,7 +50,8 @@ class ParamsStruct(C.Structure):
                 ("beta", C.c_double), ("tau", C.c_double),
                 ("line_search_iters", C.c_int32), ("sqp_iters", C.c_int32), ("nonmono_ls", C.c_int32),
                 ("merit_function", C.c_int32), ("conv_approx", C.c_int32),
-                ("mu_vio_thresh", C.c_double)]
+                ("mu_vio_thresh", C.c_double), ("time_limit", C.c_double), ("qp_warm_start", C.c_int32),
+                ("iter_log", C.c_int32)]
 
 
 class ParamsV2Struct(C.Structure):
@@ -59,11 +62,12 @@ class ParamsV2Struct(C.Structure):
                 ("nms", C.c_int32), ("nms_frequency", C.c_int32), ("nms_memory_size", C.c_int32),
                 ("merit_function", C.c_int32), ("has_merit_parameter", C.c_int32), ("merit_parameter", C.c_double),
                 ("merit_decrease", C.c_double), ("merit_decrease_condition", C.c_int32), ("delta_decay", C.c_double),
-                ("mu_vio_thresh", C.c_double)]
+                ("mu_vio_thresh", C.c_double), ("time_limit", C.c_double), ("qp_warm_start", C.c_int32),
+                ("iter_log", C.c_int32)]
 
 
 EXPORTS = ["dgsqp_create", "dgsqp_create_v2", "dgsqp_create_merge", "dgsqp_create_merge_v2", "dgsqp_destroy", "dgsqp_dims", "dgsqp_solve_batch", "dgsqp_solve_batch_up", "dgsqp_solve_batch_async",
-           "dgsqp_batch_stats", "dgsqp_pid_rollout", "dgsqp_last_diag", "dgsqp_phase_count", "dgsqp_last_phase_cycles", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_memory_plan", "dgsqp_set_smem_limit", "dgsqp_last_error", "dgsqp_version"]
+           "dgsqp_batch_stats", "dgsqp_pid_rollout", "dgsqp_last_diag", "dgsqp_iter_log_capacity", "dgsqp_last_iter_data", "dgsqp_phase_count", "dgsqp_last_phase_cycles", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_memory_plan", "dgsqp_set_smem_limit", "dgsqp_last_error", "dgsqp_version"]
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "libdgsqp_b200.so"
 _lib = None
@@ -110,6 +114,10 @@ def load():
     lib.dgsqp_batch_stats.restype = C.c_int
     lib.dgsqp_last_diag.argtypes = [vp, C.c_int32, vp]
     lib.dgsqp_last_diag.restype = C.c_int
+    lib.dgsqp_iter_log_capacity.argtypes = [vp]
+    lib.dgsqp_iter_log_capacity.restype = C.c_int
+    lib.dgsqp_last_iter_data.argtypes = [vp, C.c_int32, vp]
+    lib.dgsqp_last_iter_data.restype = C.c_int
     lib.dgsqp_phase_count.argtypes = []
     lib.dgsqp_phase_count.restype = C.c_int
     lib.dgsqp_last_phase_cycles.argtypes = [vp, C.c_int32, vp]

@@ -17,6 +17,8 @@ struct dgsqp_handle_vtbl {
   int (*set_smem_limit)(dgsqp_handle*, int64_t);
   int (*memory_plan)(const dgsqp_handle*, int64_t*);
   int (*last_phase_cycles)(dgsqp_handle*, int32_t, int64_t*);
+  int (*iter_log_capacity)(const dgsqp_handle*);
+  int (*last_iter_data)(dgsqp_handle*, int32_t, double*);
 };
 struct dgsqp_handle { const dgsqp_handle_vtbl* vt = nullptr; };
 

@@ -15,7 +15,11 @@
 
 // phases of the per-instance profile (cycles, dgsqp_last_phase_cycles)
 enum { PH_LIN_FULL = 0, PH_ADJ_FULL, PH_HESS, PH_PD_TRIDIAG, PH_PD_EIG, PH_CHOL, PH_TRINV, PH_GI, PH_LSQR,
-       PH_LIN_GRAD, PH_ADJ_GRAD, PH_MERIT, PH_OTHER, DG_NPHASE };
+       PH_LIN_GRAD, PH_ADJ_GRAD, PH_MERIT, PH_OTHER,
+       // sub-phases, only counted by the profiling build (-DDG_FINE_PHASES: c.lapf); in the product build their time
+       // stays in the coarse phase around them (pd_eig / active_set / tri_inverse)
+       PH_PD_SYM, PH_PD_EIGVAL, PH_PD_INVIT, PH_PD_BACK, PH_GI_SLACK, PH_GI_DZ, PH_GI_STEP, PH_GI_ADD, PH_GI_DROP, PH_QP_X0, PH_QP_WARM,
+       DG_NPHASE };
 
 #ifdef DG_HOSTSIM
 #define DG_RSQRT(x) (1.0 / sqrt(x))
@@ -47,7 +51,10 @@ struct Cta {
   inline void sum2(double& a, double& b) {}
   inline void sum3(double& a, double& b, double& d) {}
   inline void sum4(double& a, double& b, double& d, double& e) {}
+  inline int bcast0(int v) { return v; }
   inline void lap(int) {}
+  inline void lapf(int) {}
+  inline void lap2(int, int) {}
 };
 #else
 #define DG_RSQRT(x) rsqrt(x)
@@ -80,6 +87,13 @@ struct Cta {
   __device__ __forceinline__ void lap(int id) {
     if (tid() == 0) { long long t = clock64(); dg_s_ph[id] += t - dg_s_ph[DG_NPHASE]; dg_s_ph[DG_NPHASE] = t; }
   }
+#ifdef DG_FINE_PHASES
+  __device__ __forceinline__ void lapf(int id) { lap(id); }
+  __device__ __forceinline__ void lap2(int, int fine) { lap(fine); }      // the profiling build charges the sub-phase
+#else
+  __device__ __forceinline__ void lapf(int) {}
+  __device__ __forceinline__ void lap2(int coarse, int) { lap(coarse); }
+#endif
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -161,6 +175,13 @@ struct Cta {
     a0 = r0; a1 = r1; a2 = r2;
   }
   __device__ __forceinline__ double min(double v) { return -max(-v); }
+  // value of thread 0 to every thread (CTA-uniform decisions taken from something only one thread reads, e.g. a clock)
+  __device__ __forceinline__ int bcast0(int v) {
+    int* b = (int*)next_buf();
+    if (tid() == 0) b[0] = v;
+    __syncthreads();
+    return b[0];
+  }
   __device__ __forceinline__ int imin(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
@@ -208,6 +229,14 @@ struct Cta {
 #define DG_ASSUME_SHARED(p) do { } while (0)
 #else
 #define DG_ASSUME_SHARED(p) do { if (SM) __builtin_assume(__isShared((const void*)(p))); } while (0)
+#endif
+
+// nanoseconds of a monotonic clock (device: %globaltimer; host build: steady_clock) for DGSQPParams.time_limit
+#ifdef DG_HOSTSIM
+#include <chrono>
+static inline double dg_now_ns() { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#else
+__device__ __forceinline__ double dg_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (double)t; }
 #endif
 
 #define DG_FOR(i, n) for (int i = c.tid(); i < (n); i += c.nt())

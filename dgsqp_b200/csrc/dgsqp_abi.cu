@@ -237,6 +237,16 @@ int dgsqp_memory_plan(const dgsqp_handle* h, int64_t out[4]) {
   return h->vt->memory_plan(h, out);
 }
 
+int dgsqp_iter_log_capacity(const dgsqp_handle* h) {
+  if (!h) return dg_set_err(DGSQP_EINVAL, "NULL handle");
+  return h->vt->iter_log_capacity(h);
+}
+
+int dgsqp_last_iter_data(dgsqp_handle* h, int32_t B, double* out) {
+  if (!h || !out) return dg_set_err(DGSQP_EINVAL, "NULL argument");
+  return h->vt->last_iter_data(h, B, out);
+}
+
 int dgsqp_phase_count(void) { return DG_NPHASE; }
 
 int dgsqp_last_phase_cycles(dgsqp_handle* h, int32_t B, int64_t* cycles) {

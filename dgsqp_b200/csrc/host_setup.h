@@ -63,6 +63,13 @@ static inline int dg_fill_game(const dgsqp_racing_game* g, GameDesc* G) {
 }
 #endif
 
+static inline void dg_fill_common(double time_limit, int qp_warm_start, int iter_log, SolverParams* P) {
+  P->time_limit_ns = time_limit > 0.0 ? time_limit * 1e9 : 0.0;
+  P->qp_warm = qp_warm_start != 0;
+  { const char* e = getenv("DGSQP_QP_WARM"); if (e && (e[0] == '0' || e[0] == '1')) P->qp_warm = e[0] == '1'; }   // A/B override
+  P->iter_log = iter_log != 0;
+}
+
 static inline int dg_fill_params(const dgsqp_params* p, SolverParams* P) {
   if (!p || p->line_search_iters < 1 || p->sqp_iters < 1 || !(p->mu_vio_thresh >= 0.0)) return -1;
   P->reg = p->reg; P->p_tol = p->p_tol; P->d_tol = p->d_tol; P->beta = p->beta; P->tau = p->tau;
@@ -76,9 +83,7 @@ static inline int dg_fill_params(const dgsqp_params* p, SolverParams* P) {
   P->dbg_l0_perturb = 0.0;
   P->mu_vio_thresh = p->mu_vio_thresh;
   P->merit_obj = 0;
-#ifdef DG_QP_WARM_START
-  { const char* e = getenv("DGSQP_QP_WARM"); P->qp_warm = (e && e[0] == '1') ? 1 : 0; }    // experimental, off by default
-#endif
+  dg_fill_common(p->time_limit, p->qp_warm_start, p->iter_log, P);
   P->policy = 1; P->nms = 0; P->nms_frequency = 0; P->nms_memory = 1; P->armijo = 1; P->has_merit_parameter = 0;
   P->reg_decay = 1.0; P->sigma = 0.0; P->gamma = 1.0; P->merit_parameter = 0.0;
   return 0;
@@ -100,9 +105,7 @@ static inline int dg_fill_params_v2(const dgsqp_v2_params* p, SolverParams* P) {
   P->dbg_l0_perturb = 0.0;
   P->mu_vio_thresh = p->mu_vio_thresh;
   P->merit_obj = p->merit_function == 1;
-#ifdef DG_QP_WARM_START
-  { const char* e = getenv("DGSQP_QP_WARM"); P->qp_warm = (e && e[0] == '1') ? 1 : 0; }
-#endif
+  dg_fill_common(p->time_limit, p->qp_warm_start, p->iter_log, P);
   P->policy = 2; P->nms = p->nms != 0; P->nms_frequency = p->nms_frequency; P->nms_memory = p->nms_memory_size;
   P->armijo = p->merit_decrease_condition == 0; P->has_merit_parameter = p->has_merit_parameter != 0;
   P->reg_decay = p->reg_decay; P->sigma = p->merit_decrease; P->gamma = p->delta_decay; P->merit_parameter = p->merit_parameter;

@@ -294,7 +294,7 @@ DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
 // picks the instantiation whose scratch fits: 4*RMAX <= 3n and n <= 2*RMAX
 template <bool SM>
 DG_DEV bool sym_tridiag_regs_dispatch(Cta& c, int n, const LinBuf& B) {
-  if (!SM || c.nt() != 256) return false;
+  if (c.nt() != 256) return false;
   if (n >= 27 && n <= 40) { sym_tridiag_regs<20, SM>(c, n, B); return true; }
   if (n >= 43 && n <= 64) { sym_tridiag_regs<32, SM>(c, n, B); return true; }
   if (n >= 70 && n <= 104) { sym_tridiag_regs<52, SM>(c, n, B); return true; }
@@ -308,21 +308,36 @@ DG_DEV bool sym_tridiag_regs_dispatch(Cta& c, int n, const LinBuf& B) {
 // the ratio form q_i = p_i / p_{i-1} that LAPACK's dstebz counts): one dependent FMA per row instead of a
 // division.  The pair (p_{i-1}, p_i) is rescaled by powers of two, which leaves the signs untouched; an exact zero
 // is replaced like dstebz's pivmin rule (q = -pivmin).
+// Every thread of the CTA walks its own chain (one probe each), so what matters is the length of the dependent chain
+// per row: the product e^2 p_{i-2} is formed off the chain, the pivmin rule is a select, and the range check runs once
+// per four rows behind a rarely taken branch.  (With M = max(1, 2|T|) the pair grows by at most 2M per row, so between
+// two checks it stays below 2^512 (2M)^4 < 2^1023 as long as |T| < 2^60; larger matrices check every row.)
 DG_DEV int sturm_count(int n, const double* DG_RESTRICT dg, const double* DG_RESTRICT od2, double x, double pivmin) {
   const double BIG = 1.3407807929942597e154 /* 2^512 */, SMALL = 7.458340731200207e-155 /* 2^-512 */;
   int cnt = 0;
   double pm = 1.0, pc = dg[0] - x;
   if (fabs(pc) < pivmin) pc = -pivmin;
   cnt += pc < 0.0;
-  for (int i = 1; i < n; ++i) {
-    double pn = (dg[i] - x) * pc - od2[i - 1] * pm;
-    if (fabs(pn) < pivmin * fabs(pc)) pn = -pivmin * pc;
-    cnt += (pn < 0.0) != (pc < 0.0);
-    pm = pc; pc = pn;
-    const double ap = fabs(pc);
-    if (ap > BIG) { pc *= SMALL; pm *= SMALL; }
-    else if (ap < SMALL) { pc *= BIG; pm *= BIG; }
+  const bool wide = !(pivmin < 2.2250738585072014e-308 * 1.3e36);     // pivmin = tiny * max(1, |T|^2): |T| >= 2^60
+#define DG_STURM_ROW(i) { \
+    const double t = od2[(i) - 1] * pm, lim = pivmin * fabs(pc); \
+    double pn = fma(dg[(i)] - x, pc, -t); \
+    pn = fabs(pn) < lim ? -pivmin * pc : pn; \
+    cnt += (pn < 0.0) != (pc < 0.0); \
+    pm = pc; pc = pn; }
+#define DG_STURM_RANGE() { \
+    const double ap = fabs(pc); \
+    if (ap > BIG) { pc *= SMALL; pm *= SMALL; } else if (ap < SMALL) { pc *= BIG; pm *= BIG; } }
+  int i = 1;
+  if (!wide) {
+    for (; i + 3 < n; i += 4) {
+      DG_STURM_ROW(i) DG_STURM_ROW(i + 1) DG_STURM_ROW(i + 2) DG_STURM_ROW(i + 3)
+      DG_STURM_RANGE()
+    }
   }
+  for (; i < n; ++i) { DG_STURM_ROW(i) DG_STURM_RANGE() }
+#undef DG_STURM_ROW
+#undef DG_STURM_RANGE
   return cnt;
 }
 
@@ -440,6 +455,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
       Hm[i * ld + j] = 0.5 * (Qraw[i * n + j] + Qraw[j * n + i]);
     }
     c.sync();
+    c.lapf(PH_PD_SYM);
 #ifndef DG_HOSTSIM
     if (!sym_tridiag_regs_dispatch<SM>(c, n, B))
 #endif
@@ -464,6 +480,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
       const long cap = ((long)n * ld - (Zs - scr)) / n;    // eigenvectors that fit behind the scratch
       double* Z = nneg <= cap ? Zs : B.Zg;
       negative_eigenvalues<SM>(c, n, B, nneg, tnorm, pivmin, B.pv, B.wv, cnts);
+      c.lapf(PH_PD_EIGVAL);
       // --- eigenvectors in chunks: inverse iteration (thread per vector), Gram-Schmidt inside clusters
       const double tiny = fmax(tnorm, 1.0) * 1.1e-16;
       for (int j0 = 0; j0 < nneg; j0 += CH) {
@@ -512,6 +529,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
         for (int e = c.tid(); e < kc * n; e += c.nt()) { int jj = e / n, i = e - jj * n; Z[(size_t)(j0 + jj) * n + i] = Zt[i * CH + jj]; }
         c.sync();
       }
+      c.lapf(PH_PD_INVIT);
       // back-transform y = H_0 H_1 ... H_{n-2} z (last reflector first): one warp per eigenvector, no CTA barrier inside
       for (int jv = c.warp(); jv < nneg; jv += c.nwarps()) {
         double* DG_RESTRICT z = Z + (size_t)jv * n;
@@ -528,6 +546,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
         }
       }
       c.sync();
+      c.lapf(PH_PD_BACK);
       Zall = Z;
     }
   }
@@ -631,6 +650,83 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, doubl
   }
   return true;
 }
+
+#ifndef DG_HOSTSIM
+// ---- register-resident Cholesky (256-thread CTAs, n <= 2*RMAX <= 128) ------------------------------------------------
+// Same thread mapping as sym_tridiag_regs: thread (i = tid & 127, g = tid >> 7) keeps column i of the rows j = g, g+2, ..
+// of the (full, symmetric) trailing matrix in a[r].  Right-looking step k:
+//   row k (= column k) is peeled out of the registers of the parity-(k&1) threads and published in a parity-split buffer
+//                                                                                                   -> ONE barrier
+//   every thread reads the pivot d = A[k][k] (non-positive: not PD), the owners store L[i][k] = A[k][i] / sqrt(d),
+//   A[j][i] -= A[k][j] * (A[k][i] / d) over the thread's rows: one FMA per entry, the row broadcast with 128-bit loads.
+// The row buffers alternate between steps, so a thread that runs ahead never overwrites a row that is still being read.
+// Rows <= k are dead: whole 4-row chunks of them are skipped by the CTA-uniform switch of the tridiagonalisation, what
+// remains of them only collects values nobody reads.  The blocked shared-memory version this replaces (cholesky_lower)
+// spends four barriers and a one-warp 8x8 factorisation per panel: 196 kcycles at n = 100 against ~2 n^3/3 / 64 = 10.
+// Needs 4*RMAX doubles in B.part.
+template <int RMAX, int CB>
+DG_DEV void chol_sweep(double (&a)[RMAX], const double* DG_RESTRICT xg, double nci) {
+#pragma unroll
+  for (int cb = CB; cb < RMAX; cb += 4) {
+    const double2 x01 = *reinterpret_cast<const double2*>(xg + cb), x23 = *reinterpret_cast<const double2*>(xg + cb + 2);
+    a[cb + 0] = fma(x01.x, nci, a[cb + 0]); a[cb + 1] = fma(x01.y, nci, a[cb + 1]);
+    a[cb + 2] = fma(x23.x, nci, a[cb + 2]); a[cb + 3] = fma(x23.y, nci, a[cb + 3]);
+  }
+}
+template <int RMAX, bool SM>
+DG_DEVN bool cholesky_regs(Cta& c, int n, const LinBuf& B_) {
+  static_assert(RMAX % 4 == 0 && RMAX <= 64, "RMAX: multiple of the 4-row chunk, at most 64 rows per thread");
+  const LinBuf B = B_; DG_SH_LIN_T(B);
+  double* DG_RESTRICT W = B.matA;
+  const int ld = B.ld;
+  const int i = c.tid() & 127, g = c.tid() >> 7;
+  constexpr int XS = RMAX;
+#define DG_PS(j) ((((j) & 1) * XS) + ((j) >> 1))
+  double* DG_RESTRICT buf = B.part;                               // two parity-split row buffers of 2*XS doubles
+  const int r_end = (n - g + 1) >> 1;
+  const bool col_ok = i < n;
+  double a[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) a[r] = 0.0;
+  if (col_ok) {
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) if (r < r_end) a[r] = W[(g + 2 * r) * ld + i];
+  }
+  DG_FOR(t, 4 * XS) buf[t] = 0.0;
+  c.sync();
+  for (int k = 0; k < n; ++k) {
+    const int seg = k >> 3;                                        // CTA-uniform chunk offset CB = 4*seg <= first live row
+    const bool own = g == (k & 1);
+    const int r_k = (k - g) >> 1;                                  // owners: row k sits at r_k, within 4 rows of CB
+    double rowv = 0.0;
+    DG_TRI_SWITCH(seg, rowv = tri_peel<RMAX, CB>(a, own ? r_k - CB : 0))
+    double* DG_RESTRICT rb = buf + (k & 1) * 2 * XS;
+    if (own && col_ok) rb[DG_PS(i)] = rowv;
+    c.sync();
+    const double d = rb[DG_PS(k)];
+    if (!(d > 0.0)) return false;
+    const double inv = DG_RSQRT(d);
+    if (own && col_ok && i >= k) W[i * ld + k] = rowv * inv;
+    const double nci = col_ok ? -(rb[DG_PS(i)] * inv) * inv : 0.0;
+    const double* DG_RESTRICT xg = rb + g * XS;
+    DG_TRI_SWITCH(seg, (chol_sweep<RMAX, CB>(a, xg, nci)))
+  }
+  c.sync();
+#undef DG_PS
+  return true;
+}
+
+// picks the instantiation whose scratch fits; false = not applicable (the caller runs cholesky_lower)
+template <bool SM>
+DG_DEV bool cholesky_regs_dispatch(Cta& c, int n, const LinBuf& B, bool& ok) {
+  if (c.nt() != 256) return false;
+  if (n >= 27 && n <= 40) { ok = cholesky_regs<20, SM>(c, n, B); return true; }
+  if (n >= 43 && n <= 64) { ok = cholesky_regs<32, SM>(c, n, B); return true; }
+  if (n >= 70 && n <= 104) { ok = cholesky_regs<52, SM>(c, n, B); return true; }
+  if (n >= 105 && n <= 128) { ok = cholesky_regs<64, SM>(c, n, B); return true; }
+  return false;
+}
+#endif
 
 // Y = L^{-1} (lower triangular; L and Y row-major with leading dimension ld: Y[i][c]; the strict upper triangle of Y
 // is zero-filled because the active-set solver treats Y as dense).  Blocked by NB = 8 rows:

@@ -65,151 +65,261 @@ DG_DEV void gi_cols_times(Cta& c, int n, int ld, const double* DG_RESTRICT Y, co
   }
 }
 
-#ifdef DG_QP_WARM_START
-// Warm start of the dual active-set method from the active set of the previous QP of this instance (SolverParams::qp_warm,
-// off by default; successive SQP iterations share most of their active set).  Starting from the unconstrained minimiser
-// x0 in Q.xq and Y = L^-1:
-//   (1) the previous constraints are added to the factorisation one by one (same Householder update as a full step,
-//       linearly dependent ones are skipped) without the step-length logic;
-//   (2) the equality-constrained minimiser on that set follows from two triangular solves:
-//       r = g_W + G_W x0,  t = R^-T r,  lam = R^-1 t,  x = x0 + J1 t;
-//   (3) constraints whose multiplier comes out negative are dropped (most negative first, Givens re-triangularisation)
-//       and (2) is repeated, until (x, lam >= 0, W) is an S-pair from which the method continues unchanged.
-// The QP is strictly convex, so the solution is the same as from a cold start (up to rounding); only the path differs.
+// ---- warm start of the dual active-set method from the active set of the previous QP of this instance ------------------
+// (SolverParams::qp_warm; BASELINE north_star: "per-instance warm start").  Successive QPs of one instance -- the next SQP
+// iteration, the relaxed steps of the watchdog -- share most of their active set, and the cold method spends one
+// O(n^2) iteration per constraint it adds.  Starting from the unconstrained minimiser x0 in Q.xq and Y = L^-1:
+//   (1) D = J' N_W = -Y G_W' for all previous constraints at once (one product per column, no step-length logic);
+//   (2) Householder QR of D (n x k, in matA, right-looking; a column that is linearly dependent on the accepted ones --
+//       same test as the main loop -- is skipped): R is the factor the main loop continues with, the reflectors
+//       below the diagonal are applied to Y in ONE barrier-free pass, thread = column of Y;
+//   (3) the equality-constrained minimiser on that set in the cancellation-free form of gi_polish:
+//       c = J'q,  t = R^-T g_W,  lam = R^-1 (t + c1),  x = J1 t - J2 c2;
+//   (4) while a multiplier is negative: drop the most negative one (Givens re-triangularisation, c rotated alike) and
+//       redo (3).
+// (x, lam >= 0, W) is then an S-pair, from which the method continues unchanged.  The QP is strictly convex, so the
+// solution is the one the cold start reaches (up to rounding); only the path differs.
+// Scratch: previous ids in Q.rv (as ints), reflector scalars v0 / 2/(v'v) in Q.dv / Q.zv (then c / [t; -c2]), g_W in
+// Q.npv; the entering row of (1) goes through Q.lam, which is only written after the main loop.
 // Returns the number of active constraints; Q.act / Q.is_act / Q.lam_act / Q.xq are set accordingly.
-// Prototype: plain CTA-wide loops, not tuned.
 template <bool SM>
-DG_DEVN int gi_warm_start(Cta& c, const Dims& D_, const EvalBuf& E_, const QpBuf& Q_, const LinBuf& B_, int nprev) {
-  const EvalBuf E = E_; const QpBuf Q = Q_; const LinBuf B = B_; const Dims D = D_;
+DG_DEVN int gi_warm_start(Cta& c, const Dims& D_, const EvalBuf& E_, const double* DG_RESTRICT qv, const QpBuf& Q_, const LinBuf& B_, int nprev) {
+  const EvalBuf E = E_; DG_SH_EVAL(E); const QpBuf Q = Q_; DG_SH_QP(Q); const LinBuf B = B_; DG_SH_LIN(B); const Dims D = D_;
   const int n = D.n, ld = B.ld;
-  double* Y = B.matB;
-  double* Rm = B.matA;
+  double* DG_RESTRICT Y = B.matB;
+  double* DG_RESTRICT Rm = B.matA;
+  int* DG_RESTRICT ids = (int*)Q.rv;
+  double* DG_RESTRICT v0s = Q.dv;
+  double* DG_RESTRICT scs = Q.zv;
+  double* DG_RESTRICT row = Q.lam;                 // m >= n doubles, free until the end of the QP
+  double* DG_RESTRICT rt = Q.npv;
+  c.sync();
+  DG_FOR(k, nprev) ids[k] = Q.act[k];
+  c.sync();
+  // (1) D[:, k] = -Y G[p_k, :]'  into Rm[j*ld + k];  rt[k] = g_p
+  const Split2 sp = split2(c, n);
+  for (int k = 0; k < nprev; ++k) {
+    const int p = ids[k];
+    game_G_row<SM>(c, D, E, p, row);
+    if constexpr (!SM) {
+      // Y may live in the L2-resident workspace: warp per row, lanes along the row (coalesced)
+      for (int j = c.warp(); j < n; j += c.nwarps()) {
+        double acc = 0.0;
+        for (int i = c.lane(); i < n; i += c.wsz) acc += Y[j * ld + i] * row[i];
+        acc = c.warp_sum(acc);
+        if (c.lane() == 0) Rm[j * ld + k] = -acc;
+      }
+    } else {
+      for (int j = sp.i0; j < n; j += sp.istep) {
+        const double* DG_RESTRICT Yj = Y + j * ld;
+        double a0 = 0.0, a1 = 0.0;
+        int i = sp.g;
+        for (; i + sp.G < n; i += 2 * sp.G) { a0 += Yj[i] * row[i]; a1 += Yj[i + sp.G] * row[i + sp.G]; }
+        if (i < n) a0 += Yj[i] * row[i];
+        if (sp.G == 1) Rm[j * ld + k] = -(a0 + a1);
+        else B.part[sp.g * sp.istep + j] = a0 + a1;
+      }
+      if (sp.G > 1) {
+        c.sync();
+        if (sp.g == 0) {
+          for (int j = sp.i0; j < n; j += sp.istep) {
+            double acc = B.part[j];
+            for (int g = 1; g < sp.G; ++g) acc += B.part[g * sp.istep + j];
+            Rm[j * ld + k] = -acc;
+          }
+        }
+      }
+    }
+    if (c.tid() == 0) rt[k] = E.g[p];
+    c.sync();                                      // the next row overwrites `row` / `part`
+  }
+  // (2) Householder QR with the dependence test of the main loop; accepted column iq <- source column k
   int iq = 0;
   for (int k = 0; k < nprev; ++k) {
-    const int p = Q.act[k];
-    c.sync();
-    if (p < 0 || p >= D.m) continue;
-    game_G_row<SM>(c, D, E, p, Q.npv);
-    for (int j = c.warp(); j < n; j += c.nwarps()) {
-      double acc = 0.0;
-      for (int i = c.lane(); i < n; i += c.wsz) acc += Y[j * ld + i] * Q.npv[i];
-      acc = c.warp_sum(acc);
-      if (c.lane() == 0) Q.dv[j] = -acc;
-    }
-    c.sync();
     double zn = 0.0, dall = 0.0;
-    DG_FOR(j, n) { const double dj = Q.dv[j]; dall += dj * dj; if (j >= iq) zn += dj * dj; }
+    DG_FOR(j, n) { const double dj = Rm[j * ld + k]; dall += dj * dj; if (j >= iq) zn += dj * dj; }
     c.sum2(zn, dall);
-    if (!(zn > DG_QP_DEP_TOL * dall && zn > 0.0)) continue;          // linearly dependent on the ones already in
-    const int len = n - iq;
-    const double d0 = Q.dv[iq];
+    if (!(zn > DG_QP_DEP_TOL * dall && zn > 0.0)) continue;          // linearly dependent on the accepted ones
+    const double d0 = Rm[iq * ld + k];
     double alpha = sqrt(zn);
     if (d0 > 0.0) alpha = -alpha;
+    const double v0 = d0 - alpha;
     const double vv = 2.0 * (zn - alpha * d0);
-    c.sync();
-    if (vv > 0.0) {
-      const double sc = 2.0 / vv;
-      DG_FOR(i, n) {
-        double acc = (d0 - alpha) * Y[iq * ld + i];
-        for (int j = 1; j < len; ++j) acc += Q.dv[iq + j] * Y[(iq + j) * ld + i];
-        Q.zv[i] = acc * sc;
-      }
-      c.sync();
-      DG_FOR(i, n) {
-        const double wi = Q.zv[i];
-        Y[iq * ld + i] -= (d0 - alpha) * wi;
-        for (int j = 1; j < len; ++j) Y[(iq + j) * ld + i] -= Q.dv[iq + j] * wi;
-      }
+    const double sc = vv > 0.0 ? 2.0 / vv : 0.0;
+    c.sync();                                                       // d0 read by everyone before the column moves
+    // apply (I - sc v v') to the remaining source columns: warp per column, lanes along the rows
+    for (int k2 = k + 1 + c.warp(); k2 < nprev; k2 += c.nwarps()) {
+      double acc = 0.0;
+      for (int j = iq + c.lane(); j < n; j += c.wsz) acc += (j == iq ? v0 : Rm[j * ld + k]) * Rm[j * ld + k2];
+      acc = c.warp_sum(acc) * sc;
+      for (int j = iq + c.lane(); j < n; j += c.wsz) Rm[j * ld + k2] -= (j == iq ? v0 : Rm[j * ld + k]) * acc;
     }
-    DG_FOR(i, iq) Rm[i * ld + iq] = Q.dv[i];
-    if (c.tid() == 0) { Rm[iq * ld + iq] = alpha; Q.act[iq] = p; Q.is_act[p] = 1; }
+    c.sync();
+    // move the column into place: rows < iq of R, alpha on the diagonal, the reflector below it
+    if (iq != k) { DG_FOR(j, n) if (j != iq) Rm[j * ld + iq] = Rm[j * ld + k]; }
+    if (c.tid() == 0) {
+      Rm[iq * ld + iq] = alpha; v0s[iq] = v0; scs[iq] = sc;
+      Q.act[iq] = ids[k]; Q.is_act[ids[k]] = 1; rt[iq] = rt[k];
+    }
     ++iq;
     c.sync();
   }
   if (iq == 0) return 0;
-  game_G_times<SM>(c, D, E, Q.xq, Q.sl);                             // G x0
-  while (iq > 0) {
-    // r = g_W + G_W x0;  t = R^-T r (into zv);  lam = R^-1 t (into lam_act)      -- serial prototype on one thread
-    if (c.tid() == 0) {
-      for (int k = 0; k < iq; ++k) {
-        double v = E.g[Q.act[k]] + Q.sl[Q.act[k]];
-        for (int i = 0; i < k; ++i) v -= Rm[i * ld + k] * Q.zv[i];
-        Q.zv[k] = v / Rm[k * ld + k];
+  // Y <- P_{iq-1} .. P_0 Y: reflector k acts on rows k..n-1; the columns of Y are independent -> thread per column,
+  // no barrier.  Column i of Y = column i of the rows of J', i.e. J[:, k:] <- J[:, k:] P_k like a full step of the loop.
+  DG_FOR(i, n) {
+    for (int k = 0; k < iq; ++k) {
+      const double v0 = v0s[k];
+      double a0 = v0 * Y[k * ld + i], a1 = 0.0;
+      int j = k + 1;
+      for (; j + 1 < n; j += 2) { a0 += Rm[j * ld + k] * Y[j * ld + i]; a1 += Rm[(j + 1) * ld + k] * Y[(j + 1) * ld + i]; }
+      if (j < n) a0 += Rm[j * ld + k] * Y[j * ld + i];
+      const double w = (a0 + a1) * scs[k];
+      Y[k * ld + i] -= v0 * w;
+      for (j = k + 1; j < n; ++j) Y[j * ld + i] -= Rm[j * ld + k] * w;
+    }
+  }
+  c.sync();
+  // c = J'q = Y q into Q.dv (the reflector scalars are dead now)
+  double* DG_RESTRICT cv = Q.dv;
+  if constexpr (!SM) {
+    for (int j = c.warp(); j < n; j += c.nwarps()) {
+      double acc = 0.0;
+      for (int i = c.lane(); i < n; i += c.wsz) acc += Y[j * ld + i] * qv[i];
+      acc = c.warp_sum(acc);
+      if (c.lane() == 0) cv[j] = acc;
+    }
+  } else {
+    for (int j = sp.i0; j < n; j += sp.istep) {
+      const double* DG_RESTRICT Yj = Y + j * ld;
+      double a0 = 0.0, a1 = 0.0;
+      int i = sp.g;
+      for (; i + sp.G < n; i += 2 * sp.G) { a0 += Yj[i] * qv[i]; a1 += Yj[i + sp.G] * qv[i + sp.G]; }
+      if (i < n) a0 += Yj[i] * qv[i];
+      B.part[sp.g * sp.istep + j] = a0 + a1;
+    }
+    c.sync();
+    if (sp.g == 0) {
+      for (int j = sp.i0; j < n; j += sp.istep) {
+        double acc = B.part[j];
+        for (int g = 1; g < sp.G; ++g) acc += B.part[g * sp.istep + j];
+        cv[j] = acc;
       }
+    }
+  }
+  c.sync();
+  // (3)/(4) multipliers on the accepted set; drop negative ones
+  double* DG_RESTRICT tv = Q.zv;                   // t = R^-T g_W
+  double* DG_RESTRICT rinv = B.part + 256;         // 1 / R_kk  (part holds max(512, 2n) doubles; the rotations use part[0..2n))
+  while (true) {
+    if (c.warp() == 0) {
+      for (int k = c.lane(); k < iq; k += c.wsz) { tv[k] = rt[k]; rinv[k] = 1.0 / Rm[k * ld + k]; }
+      c.syncwarp();
+      // forward substitution with R' (right-looking: row k of R is contiguous)
+      for (int k = 0; k < iq; ++k) {
+        const double tk = tv[k] * rinv[k];
+        c.syncwarp();
+        if (c.lane() == 0) tv[k] = tk;
+        for (int j = k + 1 + c.lane(); j < iq; j += c.wsz) tv[j] -= Rm[k * ld + j] * tk;
+        c.syncwarp();
+      }
+      // back substitution lam = R^-1 (t + c1) (column-oriented, like the main loop)
+      for (int k = c.lane(); k < iq; k += c.wsz) Q.lam_act[k] = tv[k] + cv[k];
+      c.syncwarp();
       for (int k = iq - 1; k >= 0; --k) {
-        double v = Q.zv[k];
-        for (int j = k + 1; j < iq; ++j) v -= Rm[k * ld + j] * Q.lam_act[j];
-        Q.lam_act[k] = v / Rm[k * ld + k];
+        const double lk = Q.lam_act[k] * rinv[k];
+        c.syncwarp();
+        if (c.lane() == 0) Q.lam_act[k] = lk;
+        for (int j = c.lane(); j < k; j += c.wsz) Q.lam_act[j] -= Rm[j * ld + k] * lk;
+        c.syncwarp();
       }
     }
     c.sync();
-    double worst = 0.0; int ldrop = -1;
-    for (int k = 0; k < iq; ++k) { const double lk = Q.lam_act[k]; if (lk < worst) { worst = lk; ldrop = k; } }
-    if (ldrop < 0) break;
-    c.sync();
-    // drop ldrop: same re-triangularisation as a partial step of the main loop
+    double worst; int ldrop;
+    {
+      double bv = 0.0; int bk = 0x7fffffff;
+      DG_FOR(k, iq) { const double lk = Q.lam_act[k]; if (lk < bv) { bv = lk; bk = k; } }
+      c.argmin(bv, bk, worst, ldrop);
+    }
+    if (!(worst < 0.0)) break;
+    // drop ldrop: shift the columns of R, re-triangularise with Givens rotations, rotate the rows of Y (and c) alike
     if (c.tid() == 0) {
       Q.is_act[Q.act[ldrop]] = 0;
-      for (int k = ldrop; k < iq - 1; ++k) Q.act[k] = Q.act[k + 1];
+      for (int k = ldrop; k < iq - 1; ++k) { Q.act[k] = Q.act[k + 1]; rt[k] = rt[k + 1]; }
     }
     DG_FOR(i, iq) {
       for (int j = ldrop; j < iq - 1; ++j) Rm[i * ld + j] = Rm[i * ld + j + 1];
       Rm[i * ld + iq - 1] = 0.0;
     }
     c.sync();
-    for (int j = ldrop; j < iq - 1; ++j) {
-      const double a = Rm[j * ld + j], b = Rm[(j + 1) * ld + j];
-      const double h = hypot(a, b);
+    if (ldrop < iq - 1) {
+      double* DG_RESTRICT rot = B.part;
+      if (c.warp() == 0) {
+        for (int j = ldrop; j < iq - 1; ++j) {
+          const double a = Rm[j * ld + j], b = Rm[(j + 1) * ld + j];
+          const double h = hypot(a, b);
+          double cs = 1.0, sn = 0.0;
+          if (h != 0.0) { cs = a / h; sn = b / h; }
+          c.syncwarp();
+          if (h != 0.0) {
+            for (int col = j + c.lane(); col < iq - 1; col += c.wsz) {
+              double r0 = Rm[j * ld + col], r1 = Rm[(j + 1) * ld + col];
+              Rm[j * ld + col] = cs * r0 + sn * r1;
+              Rm[(j + 1) * ld + col] = -sn * r0 + cs * r1;
+            }
+          }
+          if (c.lane() == 0) {
+            rot[2 * (j - ldrop)] = cs; rot[2 * (j - ldrop) + 1] = sn;
+            const double c0 = cv[j], c1 = cv[j + 1];
+            cv[j] = cs * c0 + sn * c1; cv[j + 1] = -sn * c0 + cs * c1;
+          }
+          c.syncwarp();
+        }
+      }
       c.sync();
-      if (h != 0.0) {
-        const double cs = a / h, sn = b / h;
-        for (int col = j + c.tid(); col < iq - 1; col += c.nt()) {
-          const double r0 = Rm[j * ld + col], r1 = Rm[(j + 1) * ld + col];
-          Rm[j * ld + col] = cs * r0 + sn * r1;
-          Rm[(j + 1) * ld + col] = -sn * r0 + cs * r1;
+      DG_FOR(i, n) {
+        double t = Y[ldrop * ld + i];
+        for (int j = ldrop; j < iq - 1; ++j) {
+          const double cs = rot[2 * (j - ldrop)], sn = rot[2 * (j - ldrop) + 1];
+          const double u1 = Y[(j + 1) * ld + i];
+          if (cs == 1.0 && sn == 0.0) { Y[j * ld + i] = t; t = u1; }
+          else { Y[j * ld + i] = cs * t + sn * u1; t = -sn * t + cs * u1; }
         }
-        DG_FOR(i, n) {
-          const double j0 = Y[j * ld + i], j1 = Y[(j + 1) * ld + i];
-          Y[j * ld + i] = cs * j0 + sn * j1;
-          Y[(j + 1) * ld + i] = -sn * j0 + cs * j1;
-        }
+        Y[(iq - 1) * ld + i] = t;
       }
       c.sync();
     }
     --iq;
+    if (iq == 0) break;
   }
-  // x = x0 + J1 t
+  // x = J1 t - J2 c2 = Y' [t; -c2]
   c.sync();
-  DG_FOR(i, n) {
-    double acc = 0.0;
-    for (int j = 0; j < iq; ++j) acc += Y[j * ld + i] * Q.zv[j];
-    Q.xq[i] += acc;
-  }
+  for (int j = iq + c.tid(); j < n; j += c.nt()) tv[j] = -cv[j];
   c.sync();
+  gi_cols_times<SM>(c, n, ld, Y, tv, 0, B.part, Q.xq, 1.0);
   return iq;
 }
-#define DG_WARM_PARAM , int warm = 0
-#define DG_WARM_ARG(x) , (x)
-#else
-// (the experimental warm start is compiled out of the product: even unused, the extra call site cost 5 % in this function)
-#define DG_WARM_PARAM
-#define DG_WARM_ARG(x)
-#endif
 
-// H (symmetric positive definite) is expected in B.matA and is destroyed.
-// returns 0 ok, 1 not PD, 2 infeasible, 3 iteration limit.  Output: Q.xq (du), Q.lam (l_hat).
+// Cholesky of H (in B.matA, destroyed), Y = L^-1 into B.matB, unconstrained minimiser into Q.xq, empty active set.
+// Returns false (uniformly) when H is not positive definite.
 template <bool SM>
-DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double* DG_RESTRICT qv,
-                        const QpBuf& Q_, const LinBuf& B_, int* n_iter_out, int* n_active_out DG_WARM_PARAM) {
+DG_DEVN bool qp_factor(Cta& c, const Dims& D_, const double* DG_RESTRICT qv, const QpBuf& Q_, const LinBuf& B_) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
-  const EvalBuf E = E_; DG_SH_EVAL(E); const QpBuf Q = Q_; DG_SH_QP(Q); const LinBuf B = B_; DG_SH_LIN(B); const Dims D = D_;
+  const QpBuf Q = Q_; DG_SH_QP(Q); const LinBuf B = B_; DG_SH_LIN(B); const Dims D = D_;
   const int n = D.n, m = D.m, ld = B.ld;
   double* DG_RESTRICT Y = B.matB;
-  double* DG_RESTRICT Rm = B.matA;
-  if (!cholesky_lower<SM>(c, n, ld, B.matA, B.sp, B.part)) return 1;
+  {
+    bool ok = false;
+#ifndef DG_HOSTSIM
+    if (!cholesky_regs_dispatch<SM>(c, n, B, ok))
+#endif
+    ok = cholesky_lower<SM>(c, n, ld, B.matA, B.sp, B.part);
+    if (!ok) return false;
+  }
   c.lap(PH_CHOL);
   tri_inverse<SM>(c, n, ld, B.matA, Y, B.sp, B.part);
   c.sync();
+  c.lapf(PH_TRINV);
   // x = -J J' q = -Y' (Y q):   t = Y q (warp per row), x_i = -sum_j Y[j][i] t_j
   for (int j = c.warp(); j < n; j += c.nwarps()) {
     const double* DG_RESTRICT Yj = Y + j * ld;
@@ -218,15 +328,25 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
     p = c.warp_sum(p);
     if (c.lane() == 0) Q.dv[j] = p;
   }
-  DG_FOR(r, m) { Q.is_act[r] = 0; Q.lam[r] = 0.0; }
+  DG_FOR(r, m) Q.is_act[r] = 0;
   c.sync();
   gi_cols_times<SM>(c, n, ld, Y, Q.dv, 0, B.part, Q.xq, -1.0);
-  c.lap(PH_TRINV);
-  int iq = 0, it = 0;
-#ifdef DG_QP_WARM_START
-  // active set of the previous QP of this instance: ids in Q.act[0..), count parked in Q.act[n] (see sqp_solve_*)
-  if (warm) { const int nprev = Q.act[n]; c.sync(); if (nprev > 0 && nprev <= n) iq = gi_warm_start<SM>(c, D, E, Q, B, nprev); }
-#endif
+  c.lap2(PH_TRINV, PH_QP_X0);
+  return true;
+}
+
+// The dual active-set iteration from the S-pair (Q.xq, Q.act[0..iq0), Q.lam_act) with factors Y = J' (B.matB) and R (B.matA).
+// returns 0 ok, 2 infeasible, 3 iteration limit.  Output: Q.xq (du), Q.lam (l_hat).
+template <bool SM>
+DG_DEVN int qp_gi_loop(Cta& c, const Dims& D_, const EvalBuf& E_, const QpBuf& Q_, const LinBuf& B_, int iq0,
+                       int* n_iter_out, int* n_active_out) {
+  // local copies: the tables live in shared memory and would otherwise be re-read after every store
+  const EvalBuf E = E_; DG_SH_EVAL(E); const QpBuf Q = Q_; DG_SH_QP(Q); const LinBuf B = B_; DG_SH_LIN(B); const Dims D = D_;
+  const int n = D.n, m = D.m, ld = B.ld;
+  double* DG_RESTRICT Y = B.matB;
+  double* DG_RESTRICT Rm = B.matA;
+  DG_FOR(r, m) Q.lam[r] = 0.0;
+  int iq = iq0, it = 0;
   const int max_iter = 10 * (n + m);
   const Split2 sp = split2(c, n);                 // one decomposition for every n-wide sweep of the loop (integer divisions)
   int status = 0;
@@ -245,6 +365,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
     if (!(best < -DG_QP_FEAS_TOL)) break;
     const int p = bi;
     game_G_row<SM>(c, D, E, p, Q.npv);                 // npv = G[p,:]  (normal is -npv)
+    c.lapf(PH_GI_SLACK);
     double lam_p = 0.0;
     bool added = false;
     while (!added) {
@@ -359,6 +480,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
         }
       }
       c.sync();
+      c.lapf(PH_GI_DZ);
       // dual step bound t1, primal step length t2
       double t1 = 1e300; int ldrop = -1;
       {
@@ -377,6 +499,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
       if (t2 < 1e300) { DG_FOR(i, n) Q.xq[i] += t * Q.zv[i]; }
       DG_FOR(k, iq) Q.lam_act[k] -= t * Q.rv[k];
       lam_p += t;
+      c.lapf(PH_GI_STEP);
       if (t2 <= t1) {
         // full step: add p.  Householder P on d[iq:] -> (alpha, 0, ..); J[:, iq:] <- J[:, iq:] P, and
         // J2 v = z - alpha J[:, iq] needs no extra product.
@@ -418,6 +541,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
         ++iq;
         added = true;
         c.sync();
+        c.lapf(PH_GI_ADD);
       } else {
         c.sync();
         // partial step: drop active constraint ldrop (Givens re-triangularisation), keep p
@@ -468,6 +592,7 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
           c.sync();
         }
         --iq;
+        c.lapf(PH_GI_DROP);
       }
     }
     if (status != 0) break;
@@ -477,11 +602,106 @@ DG_DEVN int qp_solve_gi(Cta& c, const Dims& D_, const EvalBuf& E_, const double*
     DG_FOR(k, iq) Q.lam[Q.act[k]] = Q.lam_act[k];
     c.sync();
   }
-#ifdef DG_QP_WARM_START
   if (c.tid() == 0) Q.act[n] = status == 0 ? iq : 0;               // remembered for a warm start of the next QP
-#endif
   if (n_iter_out) *n_iter_out = it;
   if (n_active_out) *n_active_out = iq;
   c.lap(PH_GI);
   return status;
+}
+
+// Polish: the KKT point of the final active set W re-evaluated from the final factors without the cancellation the
+// iteration carries.  The method starts at the unconstrained minimiser x0 = -H^-1 q and moves by x += t z; when H is
+// ill-conditioned (reg = 0 games: eigenvalues at the 1e-10 floor, condition 1e11) x0 is ~1e10 |q| along the near-null
+// directions and the steps cancel it, which leaves errors of 1e-5..1e-3 in x and 1e-2 in lam.  With J = [J1 J2], J'N = [R; 0]
+// (N = -G_W') and c = J'q the same point is
+//     x = J1 R^-T g_W - J2 c2,        lam_W = R^-1 (R^-T g_W + c1)
+// in which the large components c1 never meet (measured against an extended-precision KKT solve on the merge game: 1e-10
+// in x, 1e-8 in lam).  This is the role OSQP's polish step has in the reference (DGSQP.py:186, polish=True: reduced KKT
+// system of the active set + iterative refinement); the oracle applies the same formula (oracle/qp.py).
+template <bool SM>
+DG_DEVN void gi_polish(Cta& c, const Dims& D_, const EvalBuf& E_, const double* DG_RESTRICT qv, const QpBuf& Q_, const LinBuf& B_, int iq) {
+  const EvalBuf E = E_; DG_SH_EVAL(E); const QpBuf Q = Q_; DG_SH_QP(Q); const LinBuf B = B_; DG_SH_LIN(B); const Dims D = D_;
+  const int n = D.n, ld = B.ld;
+  double* DG_RESTRICT Y = B.matB;
+  double* DG_RESTRICT Rm = B.matA;
+  c.sync();
+  // c = J' q = Y q into Q.dv
+  if constexpr (!SM) {
+    for (int j = c.warp(); j < n; j += c.nwarps()) {
+      double acc = 0.0;
+      for (int i = c.lane(); i < n; i += c.wsz) acc += Y[j * ld + i] * qv[i];
+      acc = c.warp_sum(acc);
+      if (c.lane() == 0) Q.dv[j] = acc;
+    }
+    c.sync();
+  } else {
+    const Split2 sp = split2(c, n);
+    for (int j = sp.i0; j < n; j += sp.istep) {
+      const double* DG_RESTRICT Yj = Y + j * ld;
+      double a0 = 0.0, a1 = 0.0;
+      int i = sp.g;
+      for (; i + sp.G < n; i += 2 * sp.G) { a0 += Yj[i] * qv[i]; a1 += Yj[i + sp.G] * qv[i + sp.G]; }
+      if (i < n) a0 += Yj[i] * qv[i];
+      B.part[sp.g * sp.istep + j] = a0 + a1;
+    }
+    c.sync();
+    if (sp.g == 0) {
+      for (int j = sp.i0; j < n; j += sp.istep) {
+        double acc = B.part[j];
+        for (int g = 1; g < sp.G; ++g) acc += B.part[g * sp.istep + j];
+        Q.dv[j] = acc;
+      }
+    }
+    c.sync();
+  }
+  // w = [R^-T g_W ; -c2] into Q.zv,  lam_W = R^-1 (w1 + c1) into Q.lam_act
+  if (c.warp() == 0) {
+    double* DG_RESTRICT tv = Q.zv;
+    double* DG_RESTRICT rinv = B.part + 256;
+    for (int k = c.lane(); k < iq; k += c.wsz) { tv[k] = E.g[Q.act[k]]; rinv[k] = 1.0 / Rm[k * ld + k]; }
+    c.syncwarp();
+    for (int k = 0; k < iq; ++k) {
+      const double tk = tv[k] * rinv[k];
+      c.syncwarp();
+      if (c.lane() == 0) tv[k] = tk;
+      for (int j = k + 1 + c.lane(); j < iq; j += c.wsz) tv[j] -= Rm[k * ld + j] * tk;
+      c.syncwarp();
+    }
+    for (int k = c.lane(); k < iq; k += c.wsz) Q.lam_act[k] = tv[k] + Q.dv[k];
+    c.syncwarp();
+    for (int k = iq - 1; k >= 0; --k) {
+      const double lk = Q.lam_act[k] * rinv[k];
+      c.syncwarp();
+      if (c.lane() == 0) Q.lam_act[k] = lk;
+      for (int j = c.lane(); j < k; j += c.wsz) Q.lam_act[j] -= Rm[j * ld + k] * lk;
+      c.syncwarp();
+    }
+  } else {
+    for (int j = iq + c.tid() - c.wsz; j < n; j += c.nt() - c.wsz) Q.zv[j] = -Q.dv[j];
+  }
+  if (c.nt() <= c.wsz) { for (int j = iq; j < n; ++j) Q.zv[j] = -Q.dv[j]; }     // one-warp (and host) builds: warp 0 does both
+  c.sync();
+  gi_cols_times<SM>(c, n, ld, Y, Q.zv, 0, B.part, Q.xq, 1.0);
+  DG_FOR(k, iq) Q.lam[Q.act[k]] = Q.lam_act[k];
+  c.sync();
+}
+
+// _solve_qp's solver call.  H (symmetric positive definite) is expected in B.matA and is destroyed.
+// warm != 0: start from the active set of the previous QP of this instance (ids in Q.act[0..), count parked in Q.act[n];
+// the SQP drivers reset the count at the start of an instance).
+// returns 0 ok, 1 not PD, 2 infeasible, 3 iteration limit.  Output: Q.xq (du), Q.lam (l_hat).
+template <bool SM>
+DG_DEV int qp_solve_gi(Cta& c, const Dims& D, const EvalBuf& E, const double* qv, const QpBuf& Q, const LinBuf& B,
+                       int* n_iter_out, int* n_active_out, int warm) {
+  if (!qp_factor<SM>(c, D, qv, Q, B)) return 1;
+  int iq = 0;
+  if (warm) {
+    const int nprev = Q.act[D.n];
+    if (nprev > 0 && nprev <= D.n) { iq = gi_warm_start<SM>(c, D, E, qv, Q, B, nprev); c.lapf(PH_QP_WARM); }
+  }
+  int na = 0;
+  const int st = qp_gi_loop<SM>(c, D, E, Q, B, iq, n_iter_out, &na);
+  if (n_active_out) *n_active_out = na;
+  if (st == 0) { gi_polish<SM>(c, D, E, qv, Q, B, na); c.lap(PH_GI); }
+  return st;
 }

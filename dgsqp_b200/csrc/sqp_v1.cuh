@@ -21,9 +21,9 @@ struct SolverParams {
   // v2 step policy (DGSQPV2Params, DGSQP_v2.py:55-230); policy = 1: v1 (sqp_v1.cuh), 2: v2 (sqp_v2.cuh)
   int policy, nms, nms_frequency, nms_memory, armijo, has_merit_parameter;
   int merit_obj;           // v2 merit 'sum_obj_l1' (sum of the agents' costs) instead of 'stat_l1'
-#ifdef DG_QP_WARM_START
-  int qp_warm;             // experimental: warm-start the active-set QP from the previous active set (qp_gi.cuh: gi_warm_start)
-#endif
+  int qp_warm;             // warm-start the active-set QP from the active set of the instance's previous QP (qp_gi.cuh: gi_warm_start)
+  int iter_log;            // keep (p_feas, comp, stat, qp_solves) per SQP iteration (SolveOut::iter_log)
+  double time_limit_ns;    // DGSQPParams.time_limit (DGSQP.py:470-474) per instance in ns of %globaltimer; 0 = none
   double reg_decay, sigma, gamma, merit_parameter;
 };
 
@@ -293,7 +293,7 @@ DG_DEVN int solve_qp_here(Cta& c, SolveCtx& X) {
     if (nneg > 0) { ++X.n_qp_indef; X.n_neg_sum += nneg; }
   }
   int it = 0, na = 0;
-  int st = qp_solve_gi<SM>(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na DG_WARM_ARG(X.P->qp_warm));
+  int st = qp_solve_gi<SM>(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na, X.P->qp_warm);
   if (c.tid() == 0) { X.n_gi_iters += it; X.n_act_sum += na; }
   return st;
 }
@@ -412,7 +412,17 @@ struct SolveOut {
   int* num_iters; int* status; int* qp_solves;
   int* diag;      // DG_NDIAG work counters (may be null), see dgsqp_last_diag
   double* l_init; // m  (may be null): dual initialisation
+  double* iter_log; int iter_cap;   // [iter_cap][DG_ITER_REC] per-iteration record (may be null), see dgsqp_last_iter_data
 };
+
+#define DG_ITER_REC 5     // p_feas, comp, stat, qp_solves, seconds
+// iter_data.append(dict(cond, ..., qp_solves, it_time)) (DGSQP.py:445-452): one record per completed iteration
+DG_DEV void iter_log_put(const Cta& c, const SolveOut& O, int it, double pf, double comp, double stat, int qp, double t_ns) {
+  if (O.iter_log && c.tid() == 0 && it < O.iter_cap) {
+    double* r = O.iter_log + (size_t)it * DG_ITER_REC;
+    r[0] = pf; r[1] = comp; r[2] = stat; r[3] = (double)qp; r[4] = t_ns * 1e-9;
+  }
+}
 
 // l_ws: optional dual warm start (nullptr = the reference's LSQR initialisation, DGSQP.py:312-326)
 template <bool SM>
@@ -420,9 +430,7 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
   const Dims D = X.D; const SqpBuf S = X.W.S; const EvalBuf E = X.W.E; DG_SH_EVAL(E); const SolverParams P = *X.P;
   const int n = D.n, m = D.m;
   if (c.tid() == 0) { X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0; }
-#ifdef DG_QP_WARM_START
-  if (c.tid() == 0) X.W.Q.act[n] = 0;
-#endif
+  if (c.tid() == 0) X.W.Q.act[n] = 0;          // no previous active set yet (qp_solve_gi's warm start)
   game_row_table<SM>(c, D, E.rowtab);
   DG_FOR(j, n) S.u[j] = u_ws[j];
   DG_FOR(r, m) S.l[r] = 0.0;
@@ -444,7 +452,12 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
   if (O.l_init) { DG_FOR(r, m) O.l_init[r] = S.l[r]; }
   int sqp_it = 0, rel_its = 0, total_qp = 0, status = ST_MAX_IT;
   double p_feas = 0.0, comp = 0.0, stat = 0.0;
+  const bool timed = P.time_limit_ns > 0.0 || O.iter_log != nullptr;
+  const double t_start = timed && c.tid() == 0 ? dg_now_ns() : 0.0;
+  if (O.iter_log) { for (int t = c.tid(); t < O.iter_cap * DG_ITER_REC; t += c.nt()) O.iter_log[t] = 0.0; }
   while (true) {
+    const double t_it = timed && c.tid() == 0 ? dg_now_ns() : 0.0;
+    const int qp_before = total_qp;
     eval_full<SM>(c, X, S.u, S.l);
     double a1 = -1e300, a2 = 0.0, a3 = 0.0;
     // NaN must not look like convergence (fmax drops NaNs): map it to +inf -> 'diverged'
@@ -479,12 +492,15 @@ DG_DEVN void sqp_solve_v1(Cta& c, SolveCtx& X, const double* u_ws, const double*
     DG_FOR(r, m) { double d = S.l[r] - S.l_im1[r]; q2 += d * d; }
     c.sum2(q1, q2);
     double nu_ = sqrt(q1), nl_ = sqrt(q2);
+    iter_log_put(c, O, sqp_it, p_feas, comp, stat, total_qp - qp_before, timed && c.tid() == 0 ? dg_now_ns() - t_it : 0.0);
     if (nu_ < P.p_tol / 2 && nl_ < P.d_tol / 2) {
       ++rel_its;
       if (rel_its >= P.rel_tol_req && p_feas < P.p_tol) { status = ST_CONV_REL; break; }
     } else rel_its = 0;
     ++sqp_it;
     if (sqp_it >= P.sqp_iters) { status = ST_MAX_IT; break; }
+    // time_limit (DGSQP.py:470-474), per instance on the device clock; the decision is taken by thread 0 and broadcast
+    if (P.time_limit_ns > 0.0 && c.bcast0(c.tid() == 0 && dg_now_ns() - t_start > P.time_limit_ns)) { status = ST_TIME_LIMIT; break; }
   }
   // outputs: x_bar = evaluate_dynamics(u), costs f_J  (DGSQP.py:476-498)
   c.sync();

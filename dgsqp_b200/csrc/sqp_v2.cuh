@@ -133,9 +133,7 @@ DG_DEVN void sqp_solve_v2(Cta& c, SolveCtx& X, const double* u_ws, const double*
   const Dims D = X.D; const SqpBuf S = X.W.S; const EvalBuf E = X.W.E; DG_SH_EVAL(E); const SolverParams P = *X.P;
   const int n = D.n, m = D.m;
   if (c.tid() == 0) { X.n_evals_full = X.n_evals_grad = X.n_gi_iters = X.n_neg_max = X.n_qp_indef = X.n_neg_sum = X.n_act_sum = X.n_ls_trials = 0; }
-#ifdef DG_QP_WARM_START
-  if (c.tid() == 0) X.W.Q.act[n] = 0;
-#endif
+  if (c.tid() == 0) X.W.Q.act[n] = 0;          // no previous active set yet (qp_solve_gi's warm start)
   game_row_table<SM>(c, D, E.rowtab);
   DG_FOR(j, n) S.u[j] = u_ws[j];
   DG_FOR(r, m) S.l[r] = 0.0;
@@ -167,7 +165,11 @@ DG_DEVN void sqp_solve_v2(Cta& c, SolveCtx& X, const double* u_ws, const double*
   int sqp_it = 0, m_step_it = 0, rel_its = 0, total_qp = 0, status = ST_MAX_IT;
   bool finished = false;
   double p_feas = 0.0, comp = 0.0, stat = 0.0;
+  const bool timed = P.time_limit_ns > 0.0 || O.iter_log != nullptr;
+  const double t_start = timed && c.tid() == 0 ? dg_now_ns() : 0.0;
+  if (O.iter_log) { for (int t = c.tid(); t < O.iter_cap * DG_ITER_REC; t += c.nt()) O.iter_log[t] = 0.0; }
   while (true) {
+    const double t_it = timed && c.tid() == 0 ? dg_now_ns() : 0.0;
     c.sync();
     vcopy<SM>(c, n, S.c_u, S.u); vcopy<SM>(c, m, S.c_l, S.l);
     eval_full<SM>(c, X, S.u, S.l);
@@ -183,13 +185,19 @@ DG_DEVN void sqp_solve_v2(Cta& c, SolveCtx& X, const double* u_ws, const double*
     if (stat > P.diverge_tol) { status = ST_DIVERGED; finished = true; }
     if (p_feas < P.p_tol && comp < P.d_tol && stat < P.d_tol) { status = ST_CONV_ABS; finished = true; }
     if (m_step_it >= P.sqp_iters) { status = ST_MAX_IT; finished = true; }
+    // nms = False: no step is ever an m-step, so the reference's only bounds are convergence and time_limit (with the
+    // default time_limit = None it never returns for an instance that does not settle).  A persistent kernel cannot
+    // spin on one instance: without nms the total iteration count is capped at sqp_iters as well.
+    if (!P.nms && sqp_it >= P.sqp_iters) { status = ST_MAX_IT; finished = true; }
+    // time_limit_exceeded (DGSQP_v2.py:412), per instance on the device clock
+    if (P.time_limit_ns > 0.0 && c.bcast0(c.tid() == 0 && dg_now_ns() - t_start > P.time_limit_ns)) { status = ST_TIME_LIMIT; finished = true; }
     if (finished) break;
 
     const bool is_ckpt_iter = sqp_it == ck_index;
     int nneg = nearest_pd<SM>(c, n, E.Q, X.W.B, P.eig_floor, reg, true);
     if (c.tid() == 0) { if (nneg > X.n_neg_max) X.n_neg_max = nneg; if (nneg > 0) { ++X.n_qp_indef; X.n_neg_sum += nneg; } }
     int gi_it = 0, gi_na = 0;
-    const int qp_st = qp_solve_gi<SM>(c, D, E, E.q, X.W.Q, X.W.B, &gi_it, &gi_na DG_WARM_ARG(P.qp_warm));
+    const int qp_st = qp_solve_gi<SM>(c, D, E, E.q, X.W.Q, X.W.B, &gi_it, &gi_na, P.qp_warm);
     if (c.tid() == 0) { X.n_gi_iters += gi_it; X.n_act_sum += gi_na; }
     ++total_qp;
     bool d_step = false, m_step = false;
@@ -283,6 +291,8 @@ DG_DEVN void sqp_solve_v2(Cta& c, SolveCtx& X, const double* u_ws, const double*
     if (rec_src == 0) { v2_copy_rec<SM>(c, D, prv, cur); mu_prv = mu; }
     else if (rec_src == 1) { v2_copy_rec<SM>(c, D, prv, ckp); mu_prv = mu_ckp; }
     if (is_ckpt_iter) { c.sync(); v2_copy_rec<SM>(c, D, ckp, prv); mu_ckp = mu_prv; }
+    // IterationData: primal_feasibility, complementarity, stationarity, qp_solutions, iteration_time (DGSQP_v2.py:31-52)
+    iter_log_put(c, O, sqp_it, p_feas, comp, stat, 1, timed && c.tid() == 0 ? dg_now_ns() - t_it : 0.0);
     ++sqp_it;
   }
   // outputs (:604-647)

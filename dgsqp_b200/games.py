@@ -238,7 +238,17 @@ def merge_params(N=20):
 MU_VIO_THRESH = 1e-10     # see include/dgsqp_b200.h (dgsqp_params.mu_vio_thresh) and DESIGN.md D2
 
 
-def params_to_struct(params, mu_vio_thresh=MU_VIO_THRESH):
+def _common(p, params, mu_vio_thresh, qp_warm_start, iter_log):
+    p.mu_vio_thresh = mu_vio_thresh
+    tl = getattr(params, "time_limit", None)
+    if tl is not None and not tl > 0:
+        raise ValueError(f"time_limit must be positive or None, got {tl}")
+    p.time_limit = 0.0 if tl is None else float(tl)
+    p.qp_warm_start = int(bool(qp_warm_start))
+    p.iter_log = int(bool(iter_log))
+
+
+def params_to_struct(params, mu_vio_thresh=MU_VIO_THRESH, qp_warm_start=True, iter_log=False):
     from ._abi import ParamsStruct
     if params.merit_function not in ("stat_l1", "stat"):
         raise ValueError(f"Merit function option {params.merit_function} not recognized")
@@ -248,11 +258,11 @@ def params_to_struct(params, mu_vio_thresh=MU_VIO_THRESH):
     p.nonmono_ls = int(bool(params.nonmono_ls))
     p.merit_function = 0 if params.merit_function == "stat_l1" else 1
     p.conv_approx = int(bool(params.conv_approx))
-    p.mu_vio_thresh = mu_vio_thresh
+    _common(p, params, mu_vio_thresh, qp_warm_start, iter_log)
     return p
 
 
-def params_v2_to_struct(params, mu_vio_thresh=MU_VIO_THRESH):
+def params_v2_to_struct(params, mu_vio_thresh=MU_VIO_THRESH, qp_warm_start=True, iter_log=False):
     """DGSQPV2Params -> dgsqp_v2_params.  Unknown option strings raise like the reference (DGSQP_v2.py:1162-1163)."""
     from ._abi import ParamsV2Struct
     if params.merit_function not in ("stat_l1", "sum_obj_l1"):
@@ -272,5 +282,5 @@ def params_v2_to_struct(params, mu_vio_thresh=MU_VIO_THRESH):
     p.merit_decrease = params.merit_decrease
     p.merit_decrease_condition = 0 if params.merit_decrease_condition == "armijo" else 1
     p.delta_decay = params.delta_decay
-    p.mu_vio_thresh = mu_vio_thresh
+    _common(p, params, mu_vio_thresh, qp_warm_start, iter_log)
     return p

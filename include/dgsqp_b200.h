@@ -36,7 +36,7 @@ enum {
   DGSQP_MAX_IT = 2,       /* 'max_it'       */
   DGSQP_DIVERGED = 3,     /* 'diverged'     */
   DGSQP_QP_FAIL = 4,      /* 'qp_fail'      */
-  DGSQP_TIME_LIMIT = 5    /* 'time_limit' (never produced: no wall clock on device) */
+  DGSQP_TIME_LIMIT = 5    /* 'time_limit': the instance ran longer than params.time_limit (device clock, see dgsqp_params) */
 };
 
 /* Racing game of M kinematic bicycles on a constant-curvature-segment track.
@@ -106,9 +106,20 @@ typedef struct {
   int32_t merit_function;    /* 0 = 'stat_l1', 1 = 'stat' */
   int32_t conv_approx;
   /* `thresh` of DGSQP._get_mu (DGSQP.py:560): the l1 penalty weight mu is |d phi|/((1-rho)*viol) when the
-   * summed constraint violation exceeds thresh, else 0.  The reference hard-codes 0, which makes mu jump
-   * between 0 and ~1e18 on rounding noise at active linear constraints; the default here is 1e-10. */
+   * summed constraint violation exceeds thresh, else 0.  The reference hard-codes 0 and that is what the Python class
+   * passes for unchanged reference parameters; with 0, mu jumps between 0 and ~1e18 on rounding noise at active linear
+   * constraints, 1e-10 (dgsqp_b200.DGSQP(..., mu_vio_thresh=1e-10), the setting of the golden fixtures) makes the choice
+   * deterministic.  DESIGN.md deviation D2. */
   double mu_vio_thresh;
+  /* DGSQPParams.time_limit (DGSQP.py:470-474) in seconds, measured per instance on the device's global timer from the
+   * moment a CTA picks the instance up; <= 0 = no limit (the reference's default None). */
+  double time_limit;
+  /* 1 (default of the Python class): every QP starts from the active set of the instance's previous QP (qp_gi.cuh);
+   * 0: cold start of every QP like the reference (DGSQP.py:240-241).  Same solution, fewer active-set iterations. */
+  int32_t qp_warm_start;
+  /* 1: keep (p_feas, comp, stat, qp_solves) of every SQP iteration for dgsqp_last_iter_data -- the `cond` and
+   * `qp_solves` entries of the reference's iter_data (DGSQP.py:445-452, save_iter_data). */
+  int32_t iter_log;
 } dgsqp_params;
 
 /* Mirrors DGSQPV2Params (DGSQP/solvers/solver_types.py:130-174): the v2 step policy of DGSQP/solvers/DGSQP_v2.py
@@ -129,6 +140,9 @@ typedef struct {
   int32_t merit_decrease_condition; /* 0 = 'armijo', 1 = 'max' */
   double delta_decay;               /* gamma */
   double mu_vio_thresh;             /* see dgsqp_params */
+  double time_limit;                /* DGSQPV2Params.time_limit (DGSQP_v2.py:412), see dgsqp_params */
+  int32_t qp_warm_start;            /* see dgsqp_params */
+  int32_t iter_log;                 /* see dgsqp_params; IterationData of DGSQP_v2.py:31-52: cond, qp_solves */
 } dgsqp_v2_params;
 
 typedef struct dgsqp_handle dgsqp_handle;
@@ -205,6 +219,12 @@ int dgsqp_batch_stats(int device, int32_t B, const int32_t* status, const int32_
  * QPs whose Hessian was indefinite, sum of #negative eigenvalues, sum of final active-set sizes, line-search trials. */
 #define DGSQP_NDIAG 8
 int dgsqp_last_diag(dgsqp_handle* h, int32_t B, int32_t* diag);
+
+/* Per-iteration record of the LAST solve_batch on a handle created with params.iter_log = 1: out is a HOST array
+ * [B, dgsqp_iter_log_capacity(h), 4] of (p_feas, comp, stat, qp_solves of that iteration); rows past an instance's
+ * num_iters + 1 are zero.  What the reference keeps as iter_data[i]['cond' | 'qp_solves'] (DGSQP.py:445-452). */
+int dgsqp_iter_log_capacity(const dgsqp_handle* h);
+int dgsqp_last_iter_data(dgsqp_handle* h, int32_t B, double* out);
 
 /* Per-instance phase profile of the LAST solve_batch: dgsqp_phase_count() SM-clock cycle counters per
  * instance (order: rollout+derivatives [full], adjoints/sensitivities [full], Hessian DP, tridiagonalisation,

@@ -37,7 +37,8 @@ def nearest_pd(A, floor=1e-10):
 class OracleDGSQP:
     def __init__(self, game, reg=1e-3, line_search_iters=50, nonmono_ls=True, sqp_iters=50,
                  p_tol=1e-3, d_tol=1e-3, beta=0.01, tau=0.5, merit_function="stat_l1",
-                 conv_approx=True, mu_vio_thresh=1e-10, dual_init_method="reorth", qp_method="gi", osqp_kw=None):
+                 conv_approx=True, mu_vio_thresh=1e-10, dual_init_method="reorth", qp_method="gi", osqp_kw=None,
+                 l0_perturb=0.0):
         self.game = game
         self.reg, self.line_search_iters, self.nonmono_ls = reg, line_search_iters, nonmono_ls
         self.sqp_iters, self.p_tol, self.d_tol, self.beta, self.tau = sqp_iters, p_tol, d_tol, beta, tau
@@ -50,6 +51,9 @@ class OracleDGSQP:
         # (oracle/osqp_admm.py) -- the literal mode; like v1 it uses whatever iterate comes back (DGSQP.py:246-249)
         self.qp_method = qp_method
         self.osqp_kw = dict(osqp_kw or {})
+        # sensitivity studies only (scripts/literal_mode_study.py): relative perturbation of the dual initialisation,
+        # e.g. 2.2e-16 = one ulp; 0 in every parity run
+        self.l0_perturb = l0_perturb
         self.qp_stats = []            # per-QP diagnostics (active-set size, negative eigenvalues, ...)
         self.trace = None
 
@@ -209,6 +213,8 @@ class OracleDGSQP:
         if l_ws is None:
             q, G, _, _ = ev(u, None, False)
             l = self.dual_init(q, G)
+            if self.l0_perturb:
+                l = l * (1.0 + self.l0_perturb * np.random.default_rng(12345).uniform(-1.0, 1.0, l.shape))
         else:
             # commented-out alternative of the reference (DGSQP.py:313-319): caller-supplied duals
             l = np.array(l_ws, dtype=np.float64).copy()

@@ -22,7 +22,7 @@ class QPFailure(Exception):
     pass
 
 
-def solve_qp_gi(H, q, G, g, max_iter=None, feas_tol=FEAS_TOL, stats=None):
+def solve_qp_gi(H, q, G, g, max_iter=None, feas_tol=FEAS_TOL, stats=None, polish=True):
     n, m = H.shape[0], G.shape[0]
     if max_iter is None:
         max_iter = 10 * (n + m)
@@ -115,6 +115,21 @@ def solve_qp_gi(H, q, G, g, max_iter=None, feas_tol=FEAS_TOL, stats=None):
             lam_act = np.delete(lam_act, ldrop)
             iq -= 1
             n_drop += 1
+    # Polish.  The iteration starts at the unconstrained minimiser x0 = -H^-1 q and moves by x += t z; for an
+    # ill-conditioned H (reg = 0 games: eigenvalues at the 1e-10 floor) x0 is ~1e10 |q| along the near-null directions and
+    # the steps cancel it, leaving errors of 1e-5..1e-3 in x and 1e-2 in lam.  The KKT point of the final active set W is
+    # therefore re-evaluated from the final factors in a form where the large terms never meet: with J = [J1 J2],
+    # J'N_W = [R; 0] and c = J'q,   x = J1 R^-T g_W - J2 c2,   lam_W = R^-1 (R^-T g_W + c1)   (1e-10 / 1e-8 against an
+    # extended-precision KKT solve).  It is the role OSQP's polish (reduced KKT system of the active set + iterative
+    # refinement) plays in the reference (DGSQP.py:186, polish=True); the CUDA path applies the same formula (gi_polish).
+    if polish:
+        c = J.T @ q
+        if iq:
+            tp = sla.solve_triangular(R[:iq, :iq], g[act], trans="T", lower=False)
+            x = J[:, :iq] @ tp - J[:, iq:] @ c[iq:]
+            lam_act = sla.solve_triangular(R[:iq, :iq], tp + c[:iq], lower=False)
+        else:
+            x = -J @ c
     lam = np.zeros(m)
     if iq:
         lam[act] = lam_act

@@ -45,7 +45,8 @@ ph = solver.last_phase_cycles(B).astype(np.float64)
 tot = ph.sum()
 print("phase shares (of CTA cycles) and mean kcycles per instance:")
 for k, name in enumerate(_abi.PHASES):
-    print(f"  {name:12s} {100*ph[:,k].sum()/tot:6.2f} %   {ph[:,k].mean()/1e3:10.1f} kcyc")
+    if ph[:, k].sum() > 0 or k < 13:
+        print(f"  {name:12s} {100*ph[:,k].sum()/tot:6.2f} %   {ph[:,k].mean()/1e3:10.1f} kcyc   per QP {ph[:,k].sum()/max(qp.sum(),1)/1e3:8.1f} kcyc")
 print(f"  total mean {ph.sum(axis=1).mean()/1e6:.2f} Mcyc per instance; per full eval hess {ph[:,2].sum()/max(d[:,0].sum(),1)/1e3:.1f} kcyc; "
       f"per QP tridiag {ph[:,3].sum()/max(qp.sum(),1)/1e3:.1f} eig {ph[:,4].sum()/max(qp.sum(),1)/1e3:.1f} chol {ph[:,5].sum()/max(qp.sum(),1)/1e3:.1f} "
       f"trinv {ph[:,6].sum()/max(qp.sum(),1)/1e3:.1f} GI {ph[:,7].sum()/max(qp.sum(),1)/1e3:.1f} (per GI it {ph[:,7].sum()/max(d[:,2].sum(),1)/1e3:.2f}) kcyc; "

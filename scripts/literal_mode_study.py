@@ -32,6 +32,9 @@ VARIANTS = {
     "d1": dict(qp_method="osqp"),
     "d2": dict(mu_vio_thresh=0.0),
     "d3": dict(dual_init_method="scipy"),
+    # chaos floor: the PRODUCT mode against itself with the dual initialisation perturbed by one ulp / by 1e-12 relative
+    "ulp": dict(l0_perturb=2.2e-16),
+    "eps1e-12": dict(l0_perturb=1e-12),
     "all_rho25": dict(qp_method="osqp", mu_vio_thresh=0.0, dual_init_method="scipy", osqp_kw=dict(adaptive_rho_interval=25)),
     "all_rho100": dict(qp_method="osqp", mu_vio_thresh=0.0, dual_init_method="scipy", osqp_kw=dict(adaptive_rho_interval=100)),
 }

@@ -12,7 +12,9 @@ import pathlib
 import sys
 import time
 
-import numpy as np
+for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_k] = "1"       # before numpy is imported: one BLAS thread per worker process
+import numpy as np  # noqa: E402
 
 ROOT = pathlib.Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))

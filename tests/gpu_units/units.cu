@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256, 1) units_kernel(const GameDesc* Gp, const
     DG_FOR(t, n * n) A.H[(size_t)inst * n * n + t] = X.W.B.matA[(t / n) * D.ld + (t % n)];
     c.sync();
     int it = 0, na = 0;
-    int st = qp_solve_gi<SM>(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na);
+    int st = qp_solve_gi<SM>(c, D, X.W.E, X.W.E.q, X.W.Q, X.W.B, &it, &na, 0);
     DG_FOR(t, n) A.du[(size_t)inst * n + t] = X.W.Q.xq[t];
     DG_FOR(t, m) A.lam[(size_t)inst * m + t] = X.W.Q.lam[t];
     c.sync();

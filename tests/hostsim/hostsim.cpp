@@ -99,7 +99,7 @@ int hs_qp(void* hp, double* H, const double* q, double* du, double* lam, int* it
   int na = 0;
   for (int i = 0; i < h->D.n; ++i) memcpy(h->W.B.matA + (size_t)i * h->D.ld, H + (size_t)i * h->D.n, sizeof(double) * h->D.n);
   std::vector<double> qc(q, q + h->D.n);      // q may alias workspace the solver reuses
-  int st = qp_solve_gi<false>(c, h->D, h->W.E, qc.data(), h->W.Q, h->W.B, iters, &na);
+  int st = qp_solve_gi<false>(c, h->D, h->W.E, qc.data(), h->W.Q, h->W.B, iters, &na, 0);
   memcpy(du, h->W.Q.xq, sizeof(double) * h->D.n);
   memcpy(lam, h->W.Q.lam, sizeof(double) * h->D.m);
   return st;
@@ -117,7 +117,7 @@ void hs_solve(void* hp, const double* x0, const double* u_ws, const double* l_ws
   HsHandle* h = (HsHandle*)hp; Cta c;
   SolveCtx X; X.G = &h->G; X.P = &h->P; X.D = h->D; X.W = h->W; X.x0 = x0; X.up_in = u_prev;
   SolveOut O; O.u = u; O.l = l; O.x = x; O.cost = cost; O.cond = cond; O.num_iters = num_iters; O.status = status;
-  O.qp_solves = qp_solves; O.diag = diag; O.l_init = l_init;
+  O.qp_solves = qp_solves; O.diag = diag; O.l_init = l_init; O.iter_log = nullptr; O.iter_cap = 0;
   if (h->P.policy == 2) sqp_solve_v2<false>(c, X, u_ws, l_ws, O);
   else sqp_solve_v1<false>(c, X, u_ws, l_ws, O);
 }

@@ -14,9 +14,9 @@ HERE = pathlib.Path(__file__).resolve().parent / "hostsim"
 _libs = {}
 
 
-def build(asan=False, merge=False, guard=False, warm=False):
+def build(asan=False, merge=False, guard=False):
     out = HERE / ("libhostsim" + ("_merge" if merge else "") + ("_asan" if asan else "") + ("_guard" if guard else "")
-                  + ("_warm" if warm else "") + ".so")
+                  + ".so")
     srcs = [HERE / "hostsim.cpp"] + sorted((HERE.parents[1] / "dgsqp_b200" / "csrc").glob("*.cuh")) \
         + sorted((HERE.parents[1] / "dgsqp_b200" / "csrc").glob("*.h"))
     if out.exists() and all(out.stat().st_mtime >= s.stat().st_mtime for s in srcs):
@@ -24,18 +24,16 @@ def build(asan=False, merge=False, guard=False, warm=False):
     flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if asan else ["-O2"]
     if merge:
         flags = flags + ["-DDG_GAME_MERGE=1"]
-    if warm:
-        flags = flags + ["-DDG_QP_WARM_START=1"]   # experimental active-set warm start (compiled out of the product)
     if guard:
         flags = flags + ["-DDG_PLAN_GUARD=16"]      # canary gaps behind every buffer of the memory plan (hs_guard_check)
     subprocess.check_call(["g++", *flags, "-shared", "-fPIC", "-std=c++17", "-o", str(out), str(HERE / "hostsim.cpp")])
     return out
 
 
-def load(asan=False, merge=False, guard=False, warm=False):
-    if (asan, merge, guard, warm) in _libs:
-        return _libs[(asan, merge, guard, warm)]
-    lib = C.CDLL(str(build(asan, merge, guard, warm)))
+def load(asan=False, merge=False, guard=False):
+    if (asan, merge, guard) in _libs:
+        return _libs[(asan, merge, guard)]
+    lib = C.CDLL(str(build(asan, merge, guard)))
     gs = MergeGameStruct if merge else RacingGameStruct
     lib.hs_create.restype = C.c_void_p
     lib.hs_create.argtypes = [C.POINTER(gs), C.POINTER(ParamsStruct)]
@@ -49,7 +47,7 @@ def load(asan=False, merge=False, guard=False, warm=False):
     lib.hs_lsqr.restype = C.c_int
     lib.hs_guard_check.restype = C.c_int
     lib.hs_guard_check.argtypes = [C.c_void_p]
-    _libs[(asan, merge, guard, warm)] = lib
+    _libs[(asan, merge, guard)] = lib
     return lib
 
 
@@ -58,15 +56,15 @@ def _p(a):
 
 
 class HostSim:
-    def __init__(self, game, params, asan=False, guard=False, warm=False):
-        self.lib = load(asan, merge=isinstance(game, MergeGame), guard=guard, warm=warm)
+    def __init__(self, game, params, asan=False, guard=False, qp_warm=True, mu_vio_thresh=1e-10):
+        self.lib = load(asan, merge=isinstance(game, MergeGame), guard=guard)
         self.game = game
         gs = game.to_struct()
         if isinstance(params, DGSQPV2Params):
-            ps = params_v2_to_struct(params)
+            ps = params_v2_to_struct(params, mu_vio_thresh=mu_vio_thresh, qp_warm_start=qp_warm)
             self.h = C.c_void_p(self.lib.hs_create_v2(C.byref(gs), C.byref(ps)))
         else:
-            ps = params_to_struct(params)
+            ps = params_to_struct(params, mu_vio_thresh=mu_vio_thresh, qp_warm_start=qp_warm)
             self.h = C.c_void_p(self.lib.hs_create(C.byref(gs), C.byref(ps)))
         assert self.h.value, "hs_create failed"
         dims = np.zeros(4, dtype=np.int32)
