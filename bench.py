@@ -43,6 +43,8 @@ UNIT = "solves/s"
 CURVE_THETAS = (45.0, 75.0, 90.0)          # scripts/DGSQP_ALGAMES_monte_carlo_curve.py:134-146
 CURVE_NS = (10, 15, 20, 25)
 DEFAULT_BATCH = dict(chicane=10000, curve=12000, agents3=4000, agents4=2000, merge=10000)
+MU_VIO = 1e-10                             # deterministic penalty-weight switch: the setting of the oracle and
+                                           # of every parity fixture; the class default 0 is the literal DGSQP.py:560 rule
 CPU_ARM_BUDGET_S = 200.0                   # wall budget of the whole `--impl reference` run
 CPU_BASELINE_BUDGET_S = 20.0               # wall budget of the cpu_baseline leg inside the GPU arm
 
@@ -83,7 +85,8 @@ def workload_config(workload, cells, batch, total):
                horizon=(g.N if len(cells) == 1 else [int(n) for n in CURVE_NS]),
                n=(g.n if len(cells) == 1 else [c["game"].n for c in cells[:len(CURVE_NS)]]),
                m=(g.m if len(cells) == 1 else [c["game"].m for c in cells[:len(CURVE_NS)]]),
-               solver=f"DGSQP v1 (DGSQPParams: reg={p.reg:g}, nonmono_ls, {p.sqp_iters} SQP iters, tol {p.p_tol:g})",
+               solver=f"DGSQP v1 (DGSQPParams: reg={p.reg:g}, nonmono_ls, {p.sqp_iters} SQP iters, tol {p.p_tol:g}; "
+                      f"mu_vio_thresh={MU_VIO:g}, exact polished QP)",
                l2_policy="256 MiB buffer written between timed steps (L2 flush)",
                sampler_seed=(1 if workload in ("curve", "merge") else 0))
     if len(cells) > 1:
@@ -333,7 +336,7 @@ def main():
     for c in cells:
         x0, u_ws = c["sampler"](c["game"], c["B"], rank)         # each rank owns its shard of the global batch
         c["x0"], c["u_ws"] = x0, u_ws
-        c["solver"] = dg.DGSQP(c["game"], c["params"], print_method=None, device=local_rank)
+        c["solver"] = dg.DGSQP(c["game"], c["params"], print_method=None, device=local_rank, mu_vio_thresh=MU_VIO)
         c["x0_d"], c["u_d"] = torch.from_numpy(x0).to(dev), torch.from_numpy(u_ws).to(dev)
         c["out"] = c["solver"].alloc_outputs(c["B"], dev)
 

@@ -39,8 +39,22 @@ class BatchResult:
         return self.status <= 1
 
 
+MU_VIO_REFERENCE = 0.0        # `thresh` of DGSQP._get_mu (DGSQP.py:560): the literal reference rule, the class default
+MU_VIO_DETERMINISTIC = 1e-10  # the penalty-weight switch no longer reacts to +-1 ulp at active linear rows
+
+
 class DGSQP:
-    def __init__(self, game: RacingGame, params: DGSQPParams = None, print_method=print, device: int = 0):
+    """``DGSQP(game, params)``.  ``game`` is one of the records of :mod:`dgsqp_b200.games` (the literals the reference
+    scripts feed CasADi); :func:`dgsqp_b200.frontend.game_from_reference_args` builds it from the reference's own
+    constructor arguments ``(joint_dynamics, costs, agent_constraints, shared_constraints, bounds)`` (DGSQP.py:26-34) when
+    they describe one of the supported game families.
+
+    ``mu_vio_thresh``: 0 (default) is the reference's rule; ``MU_VIO_DETERMINISTIC`` is the setting every parity fixture
+    was generated with.  ``qp_warm_start``: each QP of an instance starts from the active set of its
+    previous QP (same solution, fewer active-set iterations); False = cold start like the reference (DGSQP.py:240-241)."""
+
+    def __init__(self, game: RacingGame, params: DGSQPParams = None, print_method=print, device: int = 0,
+                 mu_vio_thresh: float = MU_VIO_REFERENCE, qp_warm_start: bool = True):
         if params is None:
             params = DGSQPParams()
         self.v2 = isinstance(params, DGSQPV2Params)      # step policy of DGSQP_v2.py instead of DGSQP.py
@@ -65,11 +79,14 @@ class DGSQP:
         self._lib = _abi.load()
         gs = game.to_struct()
         self._h = C.c_void_p()
+        self.mu_vio_thresh, self.qp_warm_start = float(mu_vio_thresh), bool(qp_warm_start)
+        self.save_iter_data = bool(getattr(params, "save_iter_data", False))
+        kw = dict(mu_vio_thresh=self.mu_vio_thresh, qp_warm_start=self.qp_warm_start, iter_log=self.save_iter_data)
         if self.v2:
-            ps = params_v2_to_struct(params)
+            ps = params_v2_to_struct(params, **kw)
             create = self._lib.dgsqp_create_merge_v2 if self.merge else self._lib.dgsqp_create_v2
         else:
-            ps = params_to_struct(params)
+            ps = params_to_struct(params, **kw)
             create = self._lib.dgsqp_create_merge if self.merge else self._lib.dgsqp_create
         _abi.check(create(C.byref(gs), C.byref(ps), int(device), C.byref(self._h)))
         dims = (C.c_int32 * 4)()
@@ -130,8 +147,11 @@ class DGSQP:
         self.print_method(f'Solve time: {dur:.2f}')
         self.print_method(str(res.cost[0]))
         cond = dict(p_feas=float(res.cond[0, 0]), comp=float(res.cond[0, 1]), stat=float(res.cond[0, 2]))
+        if self.v2 and msg == "time_limit":
+            msg = "time_limit_exceeded"                # the v2 class's string (DGSQP_v2.py:412)
+        iter_data = self.last_iter_data(1)[0] if self.save_iter_data else []
         return dict(time=dur, num_iters=int(res.num_iters[0]), status=bool(res.status[0] <= 1), cost=res.cost[0],
-                    cond=cond, iter_data=[], msg=msg, init=dict(u=self.u_ws.copy(), l=None),
+                    cond=cond, iter_data=iter_data, msg=msg, init=dict(u=self.u_ws.copy(), l=None),
                     qp_solves=int(res.qp_solves[0]))
 
     def step(self, states: List[VehicleState], parameters: np.ndarray = np.array([])):
@@ -231,10 +251,16 @@ class DGSQP:
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
         v = lambda t: C.c_void_p(t.data_ptr())
-        lw = v(l_ws.contiguous()) if l_ws is not None else None
+        for name, t, width in (("l_ws", l_ws, g.m), ("u_prev", u_prev, g.n_u)):
+            if t is not None and not (t.is_cuda and t.dtype == torch.float64 and tuple(t.shape) == (B, width) and t.device == dev):
+                raise RuntimeError(f"{name} must be a float64 CUDA tensor of shape (B,{width}) on {dev}")
+        # contiguous copies stay referenced by the result until the caller drops it (the kernel may still be queued)
+        l_ws = l_ws.contiguous() if l_ws is not None else None
+        u_prev = u_prev.contiguous() if u_prev is not None else None
+        lw = v(l_ws) if l_ws is not None else None
         if u_prev is not None and not sync:
             raise RuntimeError("u_prev needs the synchronous device call")
-        upv = v(u_prev.contiguous()) if u_prev is not None else None
+        upv = v(u_prev) if u_prev is not None else None
         t0 = time.perf_counter()
         if sync and u_prev is not None:
             _abi.check(self._lib.dgsqp_solve_batch_up(self._h, B, v(x0), v(u_ws), lw, upv, v(u), v(l), v(x), v(cost),
@@ -245,7 +271,9 @@ class DGSQP:
         else:
             _abi.check(self._lib.dgsqp_solve_batch_async(self._h, B, v(x0), v(u_ws), lw, v(u), v(l), v(x), v(cost),
                                                          v(cond), v(it), v(st), v(qp), C.c_void_p(stream)))
-        return BatchResult(u, l, x, cost, cond, it, st, qp, time.perf_counter() - t0)
+        res = BatchResult(u, l, x, cost, cond, it, st, qp, time.perf_counter() - t0)
+        res._inputs = (x0, u_ws, l_ws, u_prev)          # keeps the device buffers of an asynchronous launch alive
+        return res
 
     def alloc_outputs(self, B, dev):
         import torch
@@ -270,6 +298,23 @@ class DGSQP:
         _abi.check(self._lib.dgsqp_batch_stats(self.device, int(res.status.shape[0]), v(res.status), v(res.num_iters),
                                                v(res.qp_solves), v(res.cond), out.ctypes.data_as(C.c_void_p),
                                                C.c_void_p(stream)))
+        return out
+
+    def last_iter_data(self, B):
+        """Per-iteration records of the last solve_batch (needs ``params.save_iter_data``): for each of the first B instances
+        the list the reference keeps as ``iter_data`` (DGSQP.py:445-452; v2: the IterationData fields of the same name,
+        DGSQP_v2.py:31-52) -- ``cond`` (p_feas, comp, stat at the start of the iteration), ``qp_solves`` and ``it_time``
+        of every completed iteration.  Iterates (``u_sol``, ``l_sol``) are not kept on the device."""
+        if not self.save_iter_data:
+            raise RuntimeError("params.save_iter_data is False: no per-iteration records were kept")
+        cap = self._lib.dgsqp_iter_log_capacity(self._h)
+        buf = np.zeros((B, cap, 5))
+        _abi.check(self._lib.dgsqp_last_iter_data(self._h, B, buf.ctypes.data_as(C.c_void_p)))
+        out = []
+        for b in range(B):
+            rows = buf[b][buf[b, :, 3] > 0]
+            out.append([dict(cond=dict(p_feas=float(r[0]), comp=float(r[1]), stat=float(r[2])), qp_solves=int(r[3]),
+                             it_time=float(r[4])) for r in rows])
         return out
 
     def last_diag(self, B):

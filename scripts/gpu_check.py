@@ -12,7 +12,7 @@ nchk = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 nbig = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 game, params = dg.chicane_game(), dg.chicane_params()
 x0, u_ws = sample_head_to_head(game, max(nchk, nbig), seed=0)
-solver = dg.DGSQP(game, params, print_method=None)
+solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
 t = time.time(); res = solver.solve_batch(x0[:nchk], u_ws[:nchk]); print("gpu solve", nchk, "instances:", time.time() - t, "s")
 hs = HostSim(game, params)
 same = 0; worst = 0.0

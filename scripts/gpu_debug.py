@@ -9,7 +9,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 limit = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 game, params = dg.chicane_game(), dg.chicane_params()
 x0, u_ws = sample_head_to_head(game, B, seed=0)
-solver = dg.DGSQP(game, params, print_method=None)
+solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
 if limit:
     solver.set_smem_limit(limit)
 print("plan", solver.memory_plan())

@@ -13,7 +13,7 @@ x0, u_ws = sample_head_to_head(game, nchk, seed=0)
 hs = HostSim(game, params)
 H = [hs.solve(x0[i], u_ws[i]) for i in range(nchk)]
 hst = np.array([h["status"] for h in H]); hit = np.array([h["num_iters"] for h in H]); hqp = np.array([h["qp_solves"] for h in H])
-solver = dg.DGSQP(game, params, print_method=None)
+solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
 # same dual initialisation for both sides (isolates the LSQR chaos)
 l0 = np.stack([h["l_init"] for h in H])
 H2 = [hs.solve(x0[i], u_ws[i], l0[i]) for i in range(nchk)]

@@ -5,7 +5,7 @@ sys.path.insert(0, str(ROOT))
 import numpy as np
 import dgsqp_b200 as dg
 d = dict(np.load(ROOT / "tests/golden/chicane_N25_seed0_stats.npz").items())
-res = dg.DGSQP(dg.chicane_game(), dg.chicane_params(), print_method=None).solve_batch(d["x0"], d["u_ws"])
+res = dg.DGSQP(dg.chicane_game(), dg.chicane_params(), print_method=None, mu_vio_thresh=1e-10).solve_batch(d["x0"], d["u_ws"])
 same = (res.status == d["status"]) & (res.num_iters == d["num_iters"])
 print(f"identical (status, iters): {int(same.sum())}/1000; identical status: {int((res.status == d['status']).sum())}")
 for code, name in ((0, "conv_abs_tol"), (1, "conv_rel_tol")):

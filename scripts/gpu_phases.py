@@ -28,7 +28,7 @@ elif os.environ.get("DG_WORKLOAD", "").startswith("curve"):
 else:
     game, params = dg.chicane_game(), dg.chicane_params()
     x0, u_ws = sample_head_to_head(game, B, seed=0)
-solver = dg.DGSQP(game, params, print_method=None)
+solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
 if threads or ctas:
     solver.configure(ctas, threads)
 dev = torch.device("cuda:0")

@@ -8,7 +8,7 @@ from dgsqp_b200.montecarlo import sample_head_to_head
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 game, params = dg.chicane_game(), dg.chicane_params()
 x0, u_ws = sample_head_to_head(game, nb, seed=0)
-solver = dg.DGSQP(game, params, print_method=None)
+solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
 bits = lambda a: np.ascontiguousarray(a).view(np.int64)
 os.environ["DGSQP_POISON"] = "0"
 r0 = solver.solve_batch(x0, u_ws)

@@ -10,6 +10,6 @@ iters = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 game, params = dg.chicane_game(), dg.chicane_params()
 params.sqp_iters = iters
 x0, u_ws = sample_head_to_head(game, max(ids) + 1, seed=0)
-solver = dg.DGSQP(game, params, print_method=None)
+solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
 r = solver.solve_batch(x0[ids], u_ws[ids])
 print("status", r.status, "iters", r.num_iters, "qp", r.qp_solves)

@@ -10,7 +10,7 @@ nb = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 threads = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 game, params = dg.chicane_game(), dg.chicane_params()
 x0, u_ws = sample_head_to_head(game, nb, seed=0)
-solver = dg.DGSQP(game, params, print_method=None)
+solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
 if threads: solver.configure(0, threads)
 print("plan", solver.memory_plan())
 fields = ("u", "l", "x", "cost", "cond", "num_iters", "status", "qp_solves")

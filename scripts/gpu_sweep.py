@@ -24,7 +24,7 @@ ref = None
 configs = [(256, 1, 0), (256, 1, 110), (128, 1, 0), (128, 2, 110), (128, 2, 80), (64, 2, 110), (64, 4, 56), (64, 3, 75),
            (96, 2, 110), (192, 1, 0), (128, 1, 110), (64, 1, 0)]
 for threads, ctas, cap_kb in configs:
-    solver = dg.DGSQP(game, params, print_method=None)
+    solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
     try:
         if cap_kb:
             solver.set_smem_limit(cap_kb * 1024)

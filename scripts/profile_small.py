@@ -14,7 +14,7 @@ if os.environ.get("DG_WORKLOAD") == "merge":
 else:
     game, params = dg.chicane_game(), dg.chicane_params()
     x0, u_ws = sample_head_to_head(game, B, seed=0)
-solver = dg.DGSQP(game, params, print_method=None)
+solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
 dev = torch.device("cuda:0")
 r = solver.solve_batch(torch.from_numpy(x0).to(dev), torch.from_numpy(u_ws).to(dev))
 torch.cuda.synchronize()

@@ -60,27 +60,29 @@ def _golden(name):
     return np.load(GOLDEN / f"{name}.npz"), json.loads((GOLDEN / f"{name}.json").read_text())
 
 
-@pytest.mark.parametrize("name,mk,tol,min_same", [
-    ("chicane_N25_seed0", lambda: (dg.chicane_game(), dg.chicane_params()), 1e-6, 0.9),
-    ("curve45_N15_seed1", lambda: (dg.curve_game(45.0, 15), dg.curve_params(15)), 1e-4, 0.9),
-    ("agents3_N15_seed0", lambda: (dg.agents_game(3, 90.0, 15), dg.agents_params(15)), 1e-6, 0.9)])
-def test_solve_vs_golden_shared_dual_init(name, mk, tol, min_same):
-    """Same instances, same dual initialisation as the oracle run: identical status and iteration count,
-    and equilibria (u, x, l) within tolerance on the instances that converge by the KKT test."""
+@pytest.mark.parametrize("name,mk,tol,max_diff", [
+    ("chicane_N25_seed0", lambda: (dg.chicane_game(), dg.chicane_params()), 1e-6, 1),
+    ("curve45_N15_seed1", lambda: (dg.curve_game(45.0, 15), dg.curve_params(15)), 1e-6, 1),
+    ("agents3_N15_seed0", lambda: (dg.agents_game(3, 90.0, 15), dg.agents_params(15)), 1e-6, 0)])
+def test_solve_vs_golden_shared_dual_init(name, mk, tol, max_diff):
+    """Same instances, same dual initialisation as the oracle run: identical status and iteration count (at most
+    `max_diff` instances of the fixture may differ: 47/48, 24/24, 16/16 with the host build of the kernel source), and
+    equilibria -- inputs, states, MULTIPLIERS, costs -- within 1e-6 relative on the instances that converge by the KKT test
+    (measured 1e-11 or better: both sides polish the QP's KKT point, qp_gi.cuh gi_polish / oracle/qp.py)."""
     game, params = mk()
     data, meta = _golden(name)
-    solver = dg.DGSQP(game, params, print_method=None)
+    solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
     res = solver.solve_batch(data["x0"], data["u_ws"], data["l_init"])
     B = data["x0"].shape[0]
     same = np.array([res.msg[i] == meta["msg"][i] and int(res.num_iters[i]) == meta["num_iters"][i] for i in range(B)])
-    assert same.mean() >= min_same, f"identical (status, iters): {same.sum()}/{B}"
+    assert same.sum() >= B - max_diff, f"identical (status, iters): {same.sum()}/{B}"
     checked = 0
     for i in np.where(same)[0]:
         if meta["msg"][i] != "conv_abs_tol":
             continue
         checked += 1
         assert _rel(res.u[i], data["u"][i]) < tol and _rel(res.x[i], data["x"][i]) < tol
-        assert _rel(res.l[i], data["l"][i]) < 10 * tol
+        assert _rel(res.l[i], data["l"][i]) < tol
         assert _rel(res.cost[i], data["cost"][i]) < tol
         assert int(res.qp_solves[i]) == meta["qp_solves"][i]
     assert checked >= 3
@@ -90,13 +92,14 @@ def test_solve_vs_golden_own_lsqr():
     """End to end with the on-device (reorthogonalised) LSQR dual initialisation."""
     game, params = dg.chicane_game(), dg.chicane_params()
     data, meta = _golden("chicane_N25_seed0")
-    res = dg.DGSQP(game, params, print_method=None).solve_batch(data["x0"], data["u_ws"])
+    res = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10).solve_batch(data["x0"], data["u_ws"])
     B = data["x0"].shape[0]
     same = np.array([res.msg[i] == meta["msg"][i] and int(res.num_iters[i]) == meta["num_iters"][i] for i in range(B)])
-    assert same.mean() >= 0.9, f"identical (status, iters): {same.sum()}/{B}"
+    assert same.sum() >= B - 2, f"identical (status, iters): {same.sum()}/{B}"
     for i in np.where(same)[0]:
         if meta["msg"][i] == "conv_abs_tol":
             assert _rel(res.u[i], data["u"][i]) < 1e-6 and _rel(res.x[i], data["x"][i]) < 1e-6
+            assert _rel(res.l[i], data["l"][i]) < 1e-6
 
 
 def test_live_oracle_small():
@@ -110,13 +113,13 @@ def test_live_oracle_small():
     oracle = OracleDGSQP(RacingGame(chicane_track(), M=2, N=N))
     refs = [oracle.solve(x0[i], u_ws[i]) for i in range(6)]
     l0 = np.stack([r["init"]["l"] for r in refs])
-    res = dg.DGSQP(game, params, print_method=None).solve_batch(x0, u_ws, l0)
+    res = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10).solve_batch(x0, u_ws, l0)
     ok = 0
     for i, r in enumerate(refs):
         if res.msg[i] == r["msg"] and int(res.num_iters[i]) == r["num_iters"]:
             ok += 1
             if r["msg"] == "conv_abs_tol":
-                assert _rel(res.u[i], r["u"]) < 1e-6 and _rel(res.l[i], r["l"]) < 1e-5
+                assert _rel(res.u[i], r["u"]) < 1e-6 and _rel(res.l[i], r["l"]) < 1e-6
     assert ok >= 5
 
 
@@ -125,7 +128,7 @@ def test_live_oracle_small():
 def big_batch():
     game, params = dg.chicane_game(), dg.chicane_params()
     x0, u_ws = sample_head_to_head(game, 10000, seed=0)
-    solver = dg.DGSQP(game, params, print_method=None)
+    solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
     return game, params, solver, x0, u_ws, solver.solve_batch(x0, u_ws)
 
 
@@ -181,7 +184,7 @@ def test_device_path_equals_host_path(big_batch):
 # ------------------------------------------------------------------ reference surface and edge cases
 def test_solver_class_surface():
     game, params = dg.chicane_game(N=10), dg.chicane_params(N=10)
-    solver = dg.DGSQP(game, params, print_method=None)
+    solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
     assert (solver.N, solver.M, solver.n_u, solver.n_q) == (10, 2, 4, 12) and sum(solver.n_c) == game.m
     x0, u_ws = sample_head_to_head(game, 1, seed=5)
     states = []
@@ -214,7 +217,7 @@ def test_solver_class_surface():
 
 def test_edge_batches():
     game, params = dg.chicane_game(N=10), dg.chicane_params(N=10)
-    solver = dg.DGSQP(game, params, print_method=None)
+    solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
     empty = solver.solve_batch(np.zeros((0, 12)), np.zeros((0, game.n)))
     assert empty.u.shape == (0, game.n) and empty.status.shape == (0,)
     x0, u_ws = sample_head_to_head(game, 3, seed=1)
@@ -237,7 +240,7 @@ def test_multi_agent_games_run_and_satisfy_kkt(M):
     N = 25
     game, params = dg.agents_game(M=M, N=N), dg.agents_params(N)
     x0, u_ws = sample_agents(game, 64, seed=0)
-    res = dg.DGSQP(game, params, print_method=None).solve_batch(x0, u_ws)
+    res = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10).solve_batch(x0, u_ws)
     conv = res.status == 0
     assert conv.sum() >= 8
     assert np.all(res.cond[conv] < 1e-3)
@@ -257,15 +260,15 @@ def test_v2_solve_vs_golden():
     and equilibria within 1e-6 relative."""
     data, meta = _golden("chicane_v2_N15_seed0")
     game = dg.chicane_game(N=15)
-    solver = dg.DGSQP(game, dg.DGSQPV2Params(N=15, **meta["solver_kw"]), print_method=None)
+    solver = dg.DGSQP(game, dg.DGSQPV2Params(N=15, **meta["solver_kw"]), print_method=None, mu_vio_thresh=1e-10)
     B = data["x0"].shape[0]
     for l0 in (data["l_init"], None):
         res = solver.solve_batch(data["x0"], data["u_ws"], l0)
         same = np.array([res.msg[i] == meta["msg"][i] and int(res.num_iters[i]) == meta["num_iters"][i] for i in range(B)])
-        assert same.mean() >= 0.9, f"identical (status, iters): {same.sum()}/{B}"
+        assert same.sum() >= B - 1, f"identical (status, iters): {same.sum()}/{B}"
         for i in np.where(same)[0]:
             assert _rel(res.u[i], data["u"][i]) < 1e-6 and _rel(res.x[i], data["x"][i]) < 1e-6
-            assert _rel(res.l[i], data["l"][i]) < 1e-5
+            assert _rel(res.l[i], data["l"][i]) < 1e-6
             assert int(res.qp_solves[i]) == meta["qp_solves"][i]
     again = solver.solve_batch(data["x0"], data["u_ws"])
     bits = lambda a: np.ascontiguousarray(a).view(np.int64)
@@ -279,7 +282,7 @@ def test_v2_batch_kkt_and_limits():
     game = dg.chicane_game(N=N)
     params = dg.DGSQPV2Params(N=N, reg=1e-3, p_tol=1e-3, d_tol=1e-3, sqp_iters=40)
     x0, u_ws = sample_head_to_head(game, 512, seed=2)
-    solver = dg.DGSQP(game, params, print_method=None)
+    solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
     res = solver.solve_batch(x0, u_ws)
     conv = res.status == 0
     assert conv.mean() > 0.3 and set(np.unique(res.status)) <= {0, 1, 2, 3, 4}
@@ -288,23 +291,24 @@ def test_v2_batch_kkt_and_limits():
     d = solver.last_diag(512)
     assert np.all(d[res.status == 2, 6] == params.sqp_iters) and np.all(d[:, 6] <= params.sqp_iters)
     with pytest.raises(ValueError):
-        dg.DGSQP(game, dg.DGSQPV2Params(N=N, merit_function="sum_obj"), print_method=None)
+        dg.DGSQP(game, dg.DGSQPV2Params(N=N, merit_function="sum_obj"), print_method=None, mu_vio_thresh=1e-10)
     with pytest.raises(ValueError):
-        dg.DGSQP(game, dg.DGSQPV2Params(N=N, merit_decrease_condition="wolfe"), print_method=None)
+        dg.DGSQP(game, dg.DGSQPV2Params(N=N, merit_decrease_condition="wolfe"), print_method=None, mu_vio_thresh=1e-10)
 
 
 # ------------------------------------------------------------------ merge scenario (BASELINE config 5)
 def test_merge_vs_golden():
     """Merge game (three unicycles, RK3, lane half-planes) on device against the oracle's golden results
     (scripts/DGSQP_merge_monte_carlo.py: seed 1, zero warm start, reg = 0): identical status / iterations / QP counts
-    on every instance, trajectories and costs within 1e-6.  reg = 0 leaves eigenvalues of the QP Hessian at the 1e-10
-    floor (condition ~1e11), so inputs agree to cond * eps ~ 1e-5 and multipliers to 1e-4 (tests/test_merge.py)."""
+    on every instance; trajectories, costs, inputs and multipliers within 1e-6 (measured 3e-8 / 5e-8: reg = 0 leaves
+    eigenvalues of the QP Hessian at the 1e-10 floor, condition ~1e11, and only the polished KKT point -- gi_polish -- is
+    reproducible there; the un-polished active-set iterate agreed to 1e-5 in u and 1e-4 in l)."""
     from dgsqp_b200.montecarlo import sample_merge
     data, meta = _golden("merge_N20_seed1")
     game, params = dg.merge_game(), dg.merge_params()
     x0, u_ws = sample_merge(game, 32, seed=1)
     assert np.array_equal(x0, data["x0"]) and not u_ws.any()
-    solver = dg.DGSQP(game, params, print_method=None)
+    solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
     B = x0.shape[0]
     for l0 in (data["l_init"], None):
         res = solver.solve_batch(x0, u_ws, l0)
@@ -316,7 +320,7 @@ def test_merge_vs_golden():
         for i in np.where(same)[0]:
             assert int(res.qp_solves[i]) == meta["qp_solves"][i]
             assert _rel(res.x[i], data["x"][i]) < 1e-6 and _rel(res.cost[i], data["cost"][i]) < 1e-6
-            assert _rel(res.u[i], data["u"][i]) < 1e-5 and _rel(res.l[i], data["l"][i]) < 1e-4
+            assert _rel(res.u[i], data["u"][i]) < 1e-6 and _rel(res.l[i], data["l"][i]) < 1e-6
     # n = 120: the two n x n work matrices (232 KB) do not fit in shared memory, the pool and the sensitivities do;
     # with a small cap everything moves to the global workspace -- same answer
     plan = solver.memory_plan()
@@ -337,7 +341,7 @@ def test_merge_batch_properties():
     game, params = dg.merge_game(), dg.merge_params()
     B = 4096
     x0, u_ws = sample_merge(game, B, seed=1)
-    solver = dg.DGSQP(game, params, print_method=None)
+    solver = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10)
     res = solver.solve_batch(x0, u_ws)
     assert set(np.unique(res.status)) <= {0, 1, 2, 3, 4}
     conv = res.status == 0
@@ -374,7 +378,7 @@ def test_small_horizon_games_eigen_scratch():
     N = 10
     game, params = dg.merge_game(N=N), dg.merge_params(N)
     x0, u_ws = sample_merge(game, 6, seed=1)
-    res = dg.DGSQP(game, params, print_method=None).solve_batch(x0, u_ws)
+    res = dg.DGSQP(game, params, print_method=None, mu_vio_thresh=1e-10).solve_batch(x0, u_ws)
     orc = OracleDGSQP(MergeGame(N=N), reg=0.0)
     for i in range(6):
         r = orc.solve(x0[i], u_ws[i])
@@ -396,7 +400,7 @@ def test_v2_sum_obj_merit_live_oracle():
     for kw in (dict(reg=1e-3, reg_decay=0.9, nms=False, sqp_iters=30, merit_decrease=0.3, merit_function="sum_obj_l1"),
                dict(reg=1e-1, reg_decay=0.8, nms_frequency=2, sqp_iters=40, merit_function="sum_obj_l1")):
         for game, og, (x0, u_ws) in cases:
-            res = dg.DGSQP(game, dg.DGSQPV2Params(N=N, **kw), print_method=None).solve_batch(x0, u_ws)
+            res = dg.DGSQP(game, dg.DGSQPV2Params(N=N, **kw), print_method=None, mu_vio_thresh=1e-10).solve_batch(x0, u_ws)
             sol = OracleDGSQPV2(og, **kw)
             for i in range(x0.shape[0]):
                 r = sol.solve(x0[i], u_ws[i])
@@ -424,22 +428,24 @@ def test_device_statistics_match_host_statistics(big_batch):
 
 def test_large_sample_parity_1000():
     """The CUDA path on the first 1000 instances of the bench batch against the oracle's stored results
-    (tests/golden/chicane_N25_seed0_stats.npz; 47 CPU-minutes of oracle time): identical (status, iterations) on at
-    least 97.5 % (measured: 98.9 % on the GPU and with the host build of the same source), KKT-converged equilibria
-    within 1e-6 relative."""
+    (tests/golden/chicane_N25_seed0_stats.npz): identical (status, iterations) on at least 99 % -- the bar BASELINE.json
+    states (host build of the kernel source: 995 cold start / 997 warm start) -- and KKT-converged equilibria within
+    1e-6 relative (measured: max 2e-7, median 1e-15)."""
     d = dict(np.load(GOLDEN / "chicane_N25_seed0_stats.npz").items())
-    res = dg.DGSQP(dg.chicane_game(), dg.chicane_params(), print_method=None).solve_batch(d["x0"], d["u_ws"])
+    res = dg.DGSQP(dg.chicane_game(), dg.chicane_params(), print_method=None, mu_vio_thresh=1e-10).solve_batch(d["x0"], d["u_ws"])
     same = (res.status == d["status"]) & (res.num_iters == d["num_iters"])
     print(f"identical (status, iters): {int(same.sum())}/1000; identical status: {int((res.status == d['status']).sum())}")
-    assert same.mean() >= 0.975 and (res.status == d["status"]).mean() >= 0.98
-    # KKT-converged instances on the same path (status, iterations AND QP count; measured: 541 of the 542 identical
-    # conv_abs_tol instances, u to 2.3e-8 -- the one with a different watchdog path, 48 vs 52 QPs, differs by 3.8e-6)
+    assert same.mean() >= 0.99 and (res.status == d["status"]).mean() >= 0.99
+    # every instance that converged by the KKT test on the same path: inputs and costs to 1e-6, same QP count
     kkt0 = same & (d["status"] == 0)
-    kkt = kkt0 & (res.qp_solves == d["qp_solves"])
-    assert kkt0.sum() > 500 and kkt.sum() >= kkt0.sum() - 3
-    err = np.abs(res.u[kkt] - d["u"][kkt]).max(axis=1) / np.maximum(1.0, np.abs(d["u"][kkt]).max(axis=1))
-    assert err.max() < 1e-6
-    cerr = np.abs(res.cost[kkt] - d["cost"][kkt]).max(axis=1) / np.maximum(1.0, np.abs(d["cost"][kkt]).max(axis=1))
-    assert cerr.max() < 1e-6
+    assert kkt0.sum() > 500 and (res.qp_solves[kkt0] == d["qp_solves"][kkt0]).sum() >= kkt0.sum() - 1
     err0 = np.abs(res.u[kkt0] - d["u"][kkt0]).max(axis=1) / np.maximum(1.0, np.abs(d["u"][kkt0]).max(axis=1))
-    assert err0.max() < 1e-4
+    assert err0.max() < 1e-6
+    cerr = np.abs(res.cost[kkt0] - d["cost"][kkt0]).max(axis=1) / np.maximum(1.0, np.abs(d["cost"][kkt0]).max(axis=1))
+    assert cerr.max() < 1e-6
+    # conv_rel_tol is a stagnation test, not a KKT test (DGSQP.py:454-462): such instances stop at non-stationary points
+    # where the iteration is not contractive; they are counted in `same` above and reported, not compared point-wise
+    rel = same & (d["status"] == 1)
+    err1 = np.abs(res.u[rel] - d["u"][rel]).max(axis=1) / np.maximum(1.0, np.abs(d["u"][rel]).max(axis=1))
+    print(f"conv_rel_tol: {int(rel.sum())} identical, u within 1e-6 on {int((err1 < 1e-6).sum())}, max {err1.max():.1e}")
+    assert (err1 < 1e-6).mean() >= 0.95

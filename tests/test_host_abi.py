@@ -59,7 +59,7 @@ def test_create_fails_loudly_without_gpu():
     assert rc == -2 and not h.value
     assert b"no CPU fallback" in lib.dgsqp_last_error()
     with pytest.raises(_abi.DgsqpLibraryError):
-        dg.DGSQP(dg.chicane_game(), dg.chicane_params(), print_method=None)
+        dg.DGSQP(dg.chicane_game(), dg.chicane_params(), print_method=None, mu_vio_thresh=1e-10)
 
 
 def test_invalid_arguments_rejected():

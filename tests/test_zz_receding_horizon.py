@@ -16,7 +16,7 @@ def test_v2_u_prev_and_step_sequence():
     N = 10
     kw = dict(reg=1e-2, reg_decay=0.8, nms_frequency=2, sqp_iters=40, p_tol=1e-4, d_tol=1e-4)
     game, og = dg.chicane_game(N=N), RacingGame(chicane_track(), M=2, N=N)
-    solver, sol = dg.DGSQP(game, dg.DGSQPV2Params(N=N, **kw), print_method=None), OracleDGSQPV2(og, **kw)
+    solver, sol = dg.DGSQP(game, dg.DGSQPV2Params(N=N, **kw), print_method=None, mu_vio_thresh=1e-10), OracleDGSQPV2(og, **kw)
     x0, u_ws = sample_head_to_head(game, 6, seed=4)
     rng = np.random.default_rng(0)
     up = np.column_stack([rng.uniform(-1.5, 1.5, 6), rng.uniform(-0.3, 0.3, 6), rng.uniform(-1.5, 1.5, 6), rng.uniform(-0.3, 0.3, 6)])
