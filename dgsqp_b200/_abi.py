@@ -14,7 +14,8 @@ NDIAG = 8   # DGSQP_NDIAG
 PHASES = ["lin_full", "adj_full", "hessian", "pd_tridiag", "pd_eig", "cholesky", "tri_inverse", "active_set", "lsqr",
           "lin_grad", "adj_grad", "merit", "other",
           # sub-phases, non-zero only in the profiling build (-DDG_FINE_PHASES, scripts/build_prof.sh)
-          "pd_sym", "pd_eigval", "pd_invit", "pd_back", "gi_slack", "gi_dz", "gi_step", "gi_add", "gi_drop", "qp_x0", "qp_warm"]
+          "pd_sym", "pd_eigval", "pd_invit", "pd_back", "gi_slack", "gi_dz", "gi_step", "gi_add", "gi_drop", "qp_x0", "qp_warm",
+          "ws_d", "ws_qr", "ws_apply", "ws_mult"]
 
 STATUS_MSG = {0: "conv_abs_tol", 1: "conv_rel_tol", 2: "max_it", 3: "diverged", 4: "qp_fail", 5: "time_limit"}
 

@@ -19,6 +19,7 @@ enum { PH_LIN_FULL = 0, PH_ADJ_FULL, PH_HESS, PH_PD_TRIDIAG, PH_PD_EIG, PH_CHOL,
        // sub-phases, only counted by the profiling build (-DDG_FINE_PHASES: c.lapf); in the product build their time
        // stays in the coarse phase around them (pd_eig / active_set / tri_inverse)
        PH_PD_SYM, PH_PD_EIGVAL, PH_PD_INVIT, PH_PD_BACK, PH_GI_SLACK, PH_GI_DZ, PH_GI_STEP, PH_GI_ADD, PH_GI_DROP, PH_QP_X0, PH_QP_WARM,
+       PH_WS_D, PH_WS_QR, PH_WS_APPLY, PH_WS_MULT,       // stages of the warm start (the rest of it stays in qp_warm)
        DG_NPHASE };
 
 #ifdef DG_HOSTSIM
@@ -47,6 +48,8 @@ struct Cta {
   // smallest value, ties -> smallest index; every thread gets the winner
   inline void argmin(double v, int idx, double& ov, int& oi) { ov = v; oi = idx; }
   inline double warp_sum(double v) { return v; }
+  template <int N> inline void warp_sum_n(double (&)[N]) {}
+  inline void warp_argmin(double&, int&) {}
   inline void syncwarp() {}
   inline void sum2(double& a, double& b) {}
   inline void sum3(double& a, double& b, double& d) {}
@@ -99,6 +102,24 @@ struct Cta {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+  }
+  // N independent warp sums, butterfly stage by stage (the N shuffles of a stage are in flight together)
+  template <int N>
+  __device__ __forceinline__ void warp_sum_n(double (&v)[N]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int t = 0; t < N; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t], o);
+    }
+  }
+  // smallest value over the warp, ties -> smallest index; every lane gets the winner
+  __device__ __forceinline__ void warp_argmin(double& v, int& idx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (v2 < v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
+    }
   }
   // Block reductions use two alternating scratch buffers, so one barrier per reduction suffices: a thread
   // can only reach the next reduction that reuses a buffer after passing the barrier of the one in between.

@@ -394,6 +394,56 @@ DG_DEVN void game_G_row(Cta& c, const Dims& D_, const EvalBuf& E_, int r, double
   c.sync();
 }
 
+// Rows of G with a single entry +-1 (input bounds): true, and the entry as (input index << 1 | negative) in t1 (t2 = -1);
+// false for the rows that read the sensitivities.  Same entries as game_G_row.
+DG_DEV bool game_G_sparse(const Dims& D, int r, int& t1, int& t2) {
+  int k, kind, a, b;
+  decode_row(D, r, k, kind, a, b);
+  t1 = t2 = -1;
+  if (kind == K_INUB) { t1 = (a * D.twoN + 2 * k + b) << 1; return true; }
+  if (kind == K_INLB) { t1 = ((a * D.twoN + 2 * k + b) << 1) | 1; return true; }
+  return false;
+}
+
+// Rows ids[0..cnt) of G, transposed: out[t * ldo + c] = G[ids[c]][t], t < n (one warp per row, lanes along the inputs; same
+// entries as game_G_row).  No barrier: the caller synchronises.  Used by the blocked warm start of the QP (qp_gi.cuh).
+template <bool SM>
+DG_DEVN void game_G_cols(Cta& c, const Dims& D_, const EvalBuf& E_, const int* ids, int cnt, double* out, int ldo) {
+  const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_; const GameDesc& G = *E.G;
+  for (int col = c.warp(); col < cnt; col += c.nwarps()) {
+    int k, kind, a, b;
+    decode_row(D, ids[col], k, kind, a, b);
+    double n0 = 0.0, n1 = 0.0;
+    if (kind == K_LANE) lane_normal(G.lane[a][b], E.x[k * D.nq + a * DG_NQA], n0, n1);
+    for (int t = c.lane(); t < D.n; t += c.wsz) {
+      int ta = t / D.twoN, j = t - ta * D.twoN, kj = j >> 1, cc = j & 1;
+      double val = 0.0;
+      if (kind == K_COLL) {
+        if ((ta == a || ta == b) && kj < k) {
+          double dx = E.x[k * D.nq + a * DG_NQA] - E.x[k * D.nq + b * DG_NQA];
+          double dy = E.x[k * D.nq + a * DG_NQA + 1] - E.x[k * D.nq + b * DG_NQA + 1];
+          const double* Sk = E.S + sens_off(D, ta, k, 0) + j;
+          double sg = ta == a ? -2.0 : 2.0;
+          val = sg * (dx * Sk[0] + dy * Sk[2 * k]);
+        }
+      } else if (kind == K_LANE) {
+        if (ta == a && kj < k) {
+          const double* Sk = E.S + sens_off(D, ta, k, 0) + j;
+          val = n0 * Sk[0] + n1 * Sk[2 * k];
+        }
+      } else if (kind == K_INUB) { if (ta == a && kj == k && cc == b) val = 1.0; }
+      else if (kind == K_INLB) { if (ta == a && kj == k && cc == b) val = -1.0; }
+      else {
+        if (ta == a && kj < k) {
+          double sv = E.S[sens_off(D, ta, k, 2) + j];
+          val = kind == K_STUB ? sv : -sv;
+        }
+      }
+      out[t * ldo + col] = val;
+    }
+  }
+}
+
 // stage / terminal state cost of agent f: (k == N ? term_scale : 1) * 1/2 (q^f - goal^f)' diag(w_q) (q^f - goal^f)
 DG_DEV double cost_lx(const GameDesc& G, const Dims& D, const double* x, int f, int k, int idx) {
   int blk = idx / DG_NQA, comp = idx - blk * DG_NQA;

@@ -426,6 +426,61 @@ DG_DEVN void game_G_row(Cta& c, const Dims& D_, const EvalBuf& E_, int r, double
   c.sync();
 }
 
+// Rows of G with one or two entries +-1 (input bounds, rate limits): true, and the entries as (input index << 1 | negative)
+// in t1 / t2 (-1 = none); false for the rows that read the sensitivities.  Same entries as game_G_row.
+DG_DEV bool game_G_sparse(const Dims& D, int r, int& t1, int& t2) {
+  int k, kind, a, b;
+  decode_row(D, r, k, kind, a, b);
+  t1 = t2 = -1;
+  if (kind == K_INUB) { t1 = uidx(D, a, k, b) << 1; return true; }
+  if (kind == K_INLB) { t1 = (uidx(D, a, k, b) << 1) | 1; return true; }
+  if (kind == K_RATE) {
+    const int neg = (b & 1) == 0 ? 0 : 1;
+    t1 = (uidx(D, a, k, b >> 1) << 1) | neg;
+    if (k >= 1) t2 = (uidx(D, a, k - 1, b >> 1) << 1) | (neg ^ 1);
+    return true;
+  }
+  return false;
+}
+
+// Rows ids[0..cnt) of G, transposed: out[t * ldo + c] = G[ids[c]][t], t < n (one warp per row, lanes along the inputs; same
+// entries as game_G_row).  No barrier: the caller synchronises.  Used by the blocked warm start of the QP (qp_gi.cuh).
+template <bool SM>
+DG_DEVN void game_G_cols(Cta& c, const Dims& D_, const EvalBuf& E_, const int* ids, int cnt, double* out, int ldo) {
+  const EvalBuf E = E_; DG_SH_EVAL(E); const Dims D = D_;
+  for (int col = c.warp(); col < cnt; col += c.nwarps()) {
+    int k, kind, a, b;
+    decode_row(D, ids[col], k, kind, a, b);
+    for (int t = c.lane(); t < D.n; t += c.wsz) {
+      int ta = t / D.twoN, j = t - ta * D.twoN, kj = j >> 1, cc = j & 1;
+      double val = 0.0;
+      if (kind == K_COLL) {
+        if ((ta == a || ta == b) && kj < k) {
+          double dx = E.x[k * D.nq + a * DG_NQA] - E.x[k * D.nq + b * DG_NQA];
+          double dy = E.x[k * D.nq + a * DG_NQA + 1] - E.x[k * D.nq + b * DG_NQA + 1];
+          const double* Sk = E.S + sens_off(D, ta, k, 0) + j;
+          double sg = ta == a ? -2.0 : 2.0;
+          val = sg * (dx * Sk[0] + dy * Sk[2 * k]);
+        }
+      } else if (kind == K_RATE) {
+        if (ta == a && cc == (b >> 1)) {
+          double sg = (b & 1) == 0 ? 1.0 : -1.0;
+          if (kj == k) val = sg;
+          else if (kj == k - 1) val = -sg;
+        }
+      } else if (kind == K_INUB) { if (ta == a && kj == k && cc == b) val = 1.0; }
+      else if (kind == K_INLB) { if (ta == a && kj == k && cc == b) val = -1.0; }
+      else {
+        if (ta == a && kj < k) {
+          double sv = E.S[sens_off(D, ta, k, 2) + j];
+          val = kind == K_STUB ? sv : -sv;
+        }
+      }
+      out[t * ldo + col] = val;
+    }
+  }
+}
+
 // terminal-cost gradient entries of agent f wrt joint x_N:  -c_prog*s_f + sum_b c_comp*atan(s_b - s_f)
 DG_DEV double term_grad(const GameDesc& G, const Dims& D, const double* xN, int f, int idx) {
   int blk = idx / DG_NQA, comp = idx - blk * DG_NQA;
