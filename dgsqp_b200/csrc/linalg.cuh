@@ -291,6 +291,210 @@ DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
 #undef DG_PS
 }
 
+// ---- register-resident tridiagonalisation on 2D tiles (256-thread CTAs, n <= 16*T <= 128) ----------------------------
+// The column-per-thread form above pulls every entry of the Householder vectors through shared memory once per THREAD
+// (three broadcasts of ~n/2 doubles per thread and step: ~2500 shared-memory wavefronts per step at n = 100 -- the
+// shared-memory pipe, not the FP64 pipe, bounds it; ncu: 58 % LSU utilisation inside the phase).  Here the threads form a
+// 16 x 16 grid and thread (ti, tj) keeps the cyclic tile  A[ti + 16 ra][tj + 16 cb], ra, cb < T,  of the full symmetric
+// matrix in registers, so a step needs only the 2T entries of each vector that belong to the thread's rows and columns.
+// Step k (off = k + 1), two barriers:
+//   scalars (beta, tau, scale) from the 16 partial norms the holders of column off left, by every thread
+//   v for the thread's rows and columns from the raw column x (zero on dead indices: no masks)
+//   partial products sum_cb a[ra][cb] v_cb, reduced over the 16 lanes of the thread row with a reduce-scatter butterfly
+//   (8 double shuffles), p = tau A v into shared memory; v'Av per warp                               -> barrier
+//   A -= v c' + p v'  with  c = p - 2 hk v  (= v w' + w v', w = p - hk v, without a second vector exchange)
+//   the holders of column off + 1 publish it (raw) with their partial norms                           -> barrier
+// Dead tile rows / columns (all indices <= k) are skipped by a CTA-uniform switch on off >> 4; what remains of the dead
+// entries only collects values that are multiplied by zeros of v.  Same outputs as sym_tridiag.
+// Scratch: 424 doubles of B.part.
+DG_DEV void tile_reduce_scatter(double (&q)[8], int l16) {
+  // sum over the 16 lanes of a half warp; lane l16 ends with the total of entry (l16 >> 1) & 7 in q[0]
+  {
+    const bool b = (l16 >> 3) & 1;
+    double snd[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) snd[i] = b ? q[i] : q[i + 4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const double r = __shfl_xor_sync(0xffffffffu, snd[i], 8); q[i] = (b ? q[i + 4] : q[i]) + r; }
+  }
+  {
+    const bool b = (l16 >> 2) & 1;
+    double snd[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) snd[i] = b ? q[i] : q[i + 2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const double r = __shfl_xor_sync(0xffffffffu, snd[i], 4); q[i] = (b ? q[i + 2] : q[i]) + r; }
+  }
+  {
+    const bool b = (l16 >> 1) & 1;
+    const double snd = b ? q[0] : q[1];
+    const double r = __shfl_xor_sync(0xffffffffu, snd, 2);
+    q[0] = (b ? q[1] : q[0]) + r;
+  }
+  q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+}
+
+// Householder scalars of the column published in xs / pn (alpha = xs[off], |x[off+1:]|^2 from the 16 partial norms):
+// beta = -sign(alpha) |x|, tau = (beta - alpha) / beta, scale = 1 / (alpha - beta), formed from one reciprocal square root
+// and one reciprocal instead of a square root and two divisions (the chain sits between two barriers of every step).
+struct TileHh { double beta, tau, scale; };
+DG_DEV TileHh tile_householder(const double* DG_RESTRICT xs, const double* DG_RESTRICT pn, int off) {
+  const double2* DG_RESTRICT p2 = reinterpret_cast<const double2*>(pn);
+  const double2 p0 = p2[0], p1 = p2[1], p2_ = p2[2], p3 = p2[3], p4 = p2[4], p5 = p2[5], p6 = p2[6], p7 = p2[7];
+  const double xn2 = (((p0.x + p0.y) + (p1.x + p1.y)) + ((p2_.x + p2_.y) + (p3.x + p3.y))) + (((p4.x + p4.y) + (p5.x + p5.y)) + ((p6.x + p6.y) + (p7.x + p7.y)));
+  const double alpha = xs[off];
+  TileHh h; h.beta = alpha; h.tau = 0.0; h.scale = 0.0;
+  if (xn2 > 0.0) {
+    const double s2 = fma(alpha, alpha, xn2);
+    const double rn = rsqrt(s2);                                   // 1 / |x|
+    const double nrm = s2 * rn;
+    h.beta = -copysign(nrm, alpha);
+    h.tau = (alpha - h.beta) * copysign(rn, alpha);                // (beta - alpha) / beta,  1 / beta = -sign(alpha) / |x|
+    h.scale = __drcp_rn(alpha - h.beta);
+  }
+  return h;
+}
+
+template <int T, int S, bool SM>
+DG_DEV void tridiag_tile_step(Cta& c, int n, int k, int ld, double (&a)[T][T], double* DG_RESTRICT W, const LinBuf& B,
+                              double* DG_RESTRICT xs, double* DG_RESTRICT pn, double* DG_RESTRICT pb, double* DG_RESTRICT hp,
+                              TileHh& hh) {
+  const int tj = c.tid() & 15, ti = c.tid() >> 4, off = k + 1;
+  const double tauk = hh.tau, scale = hh.scale;
+  double vr[T], vc[T];
+#pragma unroll
+  for (int r = S; r < T; ++r) { const int j = ti + 16 * r; vr[r] = j == off ? 1.0 : xs[j] * scale; }
+#pragma unroll
+  for (int r = S; r < T; ++r) { const int i = tj + 16 * r; vc[r] = i == off ? 1.0 : xs[i] * scale; }
+  if (tj == (k & 15)) {
+#pragma unroll
+    for (int r = S; r < T; ++r) { const int j = ti + 16 * r; if (j > off && j < n) W[j * ld + k] = vr[r]; }   // keep the reflector
+  }
+  // partial products and v'Av
+  double q[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) q[r] = 0.0;
+  double vav = 0.0;
+#pragma unroll
+  for (int r = S; r < T; ++r) {
+    double acc = 0.0;
+#pragma unroll
+    for (int cb = S; cb < T; ++cb) acc = fma(a[r][cb], vc[cb], acc);
+    q[r] = acc;
+    vav = fma(vr[r], acc, vav);
+  }
+  tile_reduce_scatter(q, tj);
+  vav = c.warp_sum(vav);
+  {
+    const int idx = (tj >> 1) & 7;
+    if ((tj & 1) == 0 && idx < T) pb[ti + 16 * idx] = tauk * q[0];
+    if (c.lane() == 0) hp[c.warp()] = vav;
+  }
+  c.sync();
+  double hk;
+  {
+    const double2* DG_RESTRICT h2 = reinterpret_cast<const double2*>(hp);
+    const double2 h0 = h2[0], h1 = h2[1], h2_ = h2[2], h3 = h2[3];
+    hk = 0.5 * tauk * tauk * (((h0.x + h0.y) + (h1.x + h1.y)) + ((h2_.x + h2_.y) + (h3.x + h3.y)));
+  }
+  // A -= v c' + p v': first the tile column that contains column off, whose holders publish it (raw, with their partial
+  // norms) for the next step
+  double pr[T], cc[T];
+#pragma unroll
+  for (int r = S; r < T; ++r) pr[r] = pb[ti + 16 * r];
+#pragma unroll
+  for (int cb = S; cb < T; ++cb) cc[cb] = fma(-2.0 * hk, vc[cb], pb[tj + 16 * cb]);
+#pragma unroll
+  for (int r = S; r < T; ++r) a[r][S] = fma(-vr[r], cc[S], fma(-pr[r], vc[S], a[r][S]));
+  if (tj == (off & 15)) {
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < T; ++r) {
+      const int j = ti + 16 * r;
+      double val = 0.0;
+      if (r >= S) {
+        const double av = a[r][S];
+        if (j == off) B.dg[off] = av;
+        if (j > off && j < n) val = av;
+      }
+      xs[j] = val;
+      if (j >= off + 2) nrm = fma(val, val, nrm);
+    }
+    pn[ti] = nrm;
+  }
+  c.sync();
+  // the scalars of the next step (a chain of dependent special-function and FP64 operations) beside the rest of the update
+  if (off + 1 < n) {
+    hh = tile_householder(xs, pn, off + 1);
+    if (c.tid() == 0) { B.od[off] = hh.beta; B.od2[off] = hh.beta * hh.beta; B.tau[off] = hh.tau; }
+  }
+#pragma unroll
+  for (int r = S; r < T; ++r)
+#pragma unroll
+    for (int cb = S + 1; cb < T; ++cb) a[r][cb] = fma(-vr[r], cc[cb], fma(-pr[r], vc[cb], a[r][cb]));
+}
+
+#define DG_TILE_CASE(m) case m: if constexpr (m < T) tridiag_tile_step<T, m, SM>(c, n, k, ld, a, W, B, xs, pn, pb, hp, hh); break;
+template <int T, bool SM>
+DG_DEVN void sym_tridiag_tiles(Cta& c, int n, const LinBuf& B_) {
+  static_assert(T >= 1 && T <= 8, "tiles of at most 8 x 8 entries per thread");
+  const LinBuf B = B_; DG_SH_LIN_T(B);
+  double* DG_RESTRICT W = B.matA;
+  const int ld = B.ld;
+  const int tj = c.tid() & 15, ti = c.tid() >> 4;
+  double* DG_RESTRICT xs = B.part;                                // [128] raw column of the step
+  double* DG_RESTRICT pn = B.part + 128;                          // [16]  partial norms of its holders
+  double* DG_RESTRICT pb = B.part + 144;                          // [128] p = tau A v
+  double* DG_RESTRICT hp = B.part + 272;                          // [8]   v'Av per warp
+  double a[T][T];
+#pragma unroll
+  for (int r = 0; r < T; ++r)
+#pragma unroll
+    for (int cb = 0; cb < T; ++cb) {
+      const int j = ti + 16 * r, i = tj + 16 * cb;
+      a[r][cb] = (j < n && i < n) ? W[j * ld + i] : 0.0;
+    }
+  DG_FOR(t, 128) { xs[t] = 0.0; pb[t] = 0.0; }
+  c.sync();
+  if (tj == 0) {
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < T; ++r) {
+      const int j = ti + 16 * r;
+      if (j < n) {
+        const double av = a[r][0];
+        if (j == 0) B.dg[0] = av;
+        else { xs[j] = av; if (j >= 2) nrm = fma(av, av, nrm); }
+      }
+    }
+    pn[ti] = nrm;
+  }
+  c.sync();
+  TileHh hh = tile_householder(xs, pn, 1);
+  if (c.tid() == 0) { B.od[0] = hh.beta; B.od2[0] = hh.beta * hh.beta; B.tau[0] = hh.tau; }
+  for (int k = 0; k + 1 < n; ++k) {
+    switch ((k + 1) >> 4) { DG_TILE_CASE(0) DG_TILE_CASE(1) DG_TILE_CASE(2) DG_TILE_CASE(3) DG_TILE_CASE(4) DG_TILE_CASE(5) DG_TILE_CASE(6) DG_TILE_CASE(7) default: break; }
+  }
+  if (c.tid() == 0) { B.od[n - 1] = 0.0; B.od2[n - 1] = 0.0; }
+  c.sync();
+}
+#undef DG_TILE_CASE
+
+template <bool SM>
+DG_DEV bool sym_tridiag_tiles_dispatch(Cta& c, int n, const LinBuf& B) {
+  if (c.nt() != 256 || n < 33 || n > 128) return false;
+  const int T = (n + 15) >> 4;
+  switch (T) {
+    case 3: sym_tridiag_tiles<3, SM>(c, n, B); break;
+    case 4: sym_tridiag_tiles<4, SM>(c, n, B); break;
+    case 5: sym_tridiag_tiles<5, SM>(c, n, B); break;
+    case 6: sym_tridiag_tiles<6, SM>(c, n, B); break;
+    case 7: sym_tridiag_tiles<7, SM>(c, n, B); break;
+    default: sym_tridiag_tiles<8, SM>(c, n, B); break;
+  }
+  return true;
+}
+
 // picks the instantiation whose scratch fits: 4*RMAX <= 3n and n <= 2*RMAX
 template <bool SM>
 DG_DEV bool sym_tridiag_regs_dispatch(Cta& c, int n, const LinBuf& B) {
@@ -348,8 +552,9 @@ DG_DEV int sturm_count(int n, const double* DG_RESTRICT dg, const double* DG_RES
 // One thread walks the whole chain, so the recurrences are arranged to keep as little as possible on it: pivots are
 // stored as reciprocals (the back substitution multiplies), the running entries of y stay in registers (no
 // store -> load round trip through shared memory per row) and |y|^2 is accumulated beside the chain.
-DG_DEV double tridiag_shift_solve(int n, const double* dg, const double* od, double lam, double tiny,
-                                  double* fw, double* y, int st, bool refactor) {
+DG_DEV double tridiag_shift_solve(int n, const double* DG_RESTRICT dg, const double* DG_RESTRICT od, double lam, double tiny,
+                                  double* DG_RESTRICT fw, double* DG_RESTRICT y, int st, bool refactor) {
+  // (fw and y are disjoint: the loads of the factors can run ahead of the stores into y)
   double* ra = fw; double* b1 = fw + n * st; double* b2 = fw + 2 * n * st; double* ml = fw + 3 * n * st; double* sw = fw + 4 * n * st;
   const double rtiny = 1.0 / tiny;
   if (refactor) {
@@ -436,6 +641,44 @@ DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, doubl
   c.sync();
 }
 
+#ifndef DG_HOSTSIM
+// Back-transformation of the eigenvectors of the tridiagonal matrix, y = H_0 H_1 ... H_{n-3} z: one warp per vector, the
+// vector in REGISTERS (lane l holds the entries l, l+32, ..), the reflector tails (column k of W below row k+1) fetched
+// one step ahead of the dependent chain  dot -> warp sum -> update.  Z: vector-major, n entries per vector.
+template <int RPL>
+DG_DEV void backtransform_regs(Cta& c, int n, int ld, const double* DG_RESTRICT W, const double* DG_RESTRICT tau,
+                               double* DG_RESTRICT Z, int nvec) {
+  for (int jv = c.warp(); jv < nvec; jv += c.nwarps()) {
+    double* DG_RESTRICT z = Z + (size_t)jv * n;
+    double zr[RPL], v[RPL], vn[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) { const int j = c.lane() + 32 * r; zr[r] = j < n ? z[j] : 0.0; }
+    // reflector k: v_j = 0 (j <= k), 1 (j == k+1), W[j][k] (j > k+1)
+    int k = n - 3;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) { const int j = c.lane() + 32 * r; vn[r] = (j > k + 1 && j < n) ? W[j * ld + k] : (j == k + 1 ? 1.0 : 0.0); }
+    for (; k >= 0; --k) {
+      const double tk = tau[k];
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) v[r] = vn[r];
+      if (k > 0) {
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) { const int j = c.lane() + 32 * r; vn[r] = (j > k && j < n) ? W[j * ld + k - 1] : (j == k ? 1.0 : 0.0); }
+      }
+      if (tk == 0.0) continue;
+      double pp = 0.0;
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) pp = fma(v[r], zr[r], pp);
+      pp = c.warp_sum(pp) * tk;
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) zr[r] = fma(-pp, v[r], zr[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) { const int j = c.lane() + 32 * r; if (j < n) z[j] = zr[r]; }
+  }
+}
+#endif
+
 // matA <- nearestPD(Qraw) + reg*I  (n x n, leading dimension B.ld).  Qraw is row-major n x n (global memory, read
 // twice).  matB is scratch.  Returns the number of negative eigenvalues (uniform across threads).
 template <bool SM>
@@ -457,7 +700,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
     c.sync();
     c.lapf(PH_PD_SYM);
 #ifndef DG_HOSTSIM
-    if (!sym_tridiag_regs_dispatch<SM>(c, n, B))
+    if (!sym_tridiag_tiles_dispatch<SM>(c, n, B) && !sym_tridiag_regs_dispatch<SM>(c, n, B))
 #endif
     sym_tridiag<SM>(c, n, B);
     c.lap(PH_PD_TRIDIAG);
@@ -531,6 +774,12 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
       }
       c.lapf(PH_PD_INVIT);
       // back-transform y = H_0 H_1 ... H_{n-2} z (last reflector first): one warp per eigenvector, no CTA barrier inside
+#ifndef DG_HOSTSIM
+      if (n <= 64) backtransform_regs<2>(c, n, ld, Hm, B.tau, Z, nneg);
+      else if (n <= 128) backtransform_regs<4>(c, n, ld, Hm, B.tau, Z, nneg);
+      else if (n <= 256) backtransform_regs<8>(c, n, ld, Hm, B.tau, Z, nneg);
+      else
+#endif
       for (int jv = c.warp(); jv < nneg; jv += c.nwarps()) {
         double* DG_RESTRICT z = Z + (size_t)jv * n;
         for (int k = n - 3; k >= 0; --k) {
@@ -706,7 +955,7 @@ DG_DEVN bool cholesky_regs(Cta& c, int n, const LinBuf& B_) {
     const double d = rb[DG_PS(k)];
     if (!(d > 0.0)) return false;
     const double inv = DG_RSQRT(d);
-    if (own && col_ok && i >= k) W[i * ld + k] = rowv * inv;
+    if (own && col_ok && i >= k) { W[i * ld + k] = rowv * inv; W[k * ld + i] = rowv * inv; }   // L and, mirrored, L' (tri_inverse_regs walks rows)
     const double nci = col_ok ? -(rb[DG_PS(i)] * inv) * inv : 0.0;
     const double* DG_RESTRICT xg = rb + g * XS;
     DG_TRI_SWITCH(seg, (chol_sweep<RMAX, CB>(a, xg, nci)))
@@ -724,6 +973,77 @@ DG_DEV bool cholesky_regs_dispatch(Cta& c, int n, const LinBuf& B, bool& ok) {
   if (n >= 43 && n <= 64) { ok = cholesky_regs<32, SM>(c, n, B); return true; }
   if (n >= 70 && n <= 104) { ok = cholesky_regs<52, SM>(c, n, B); return true; }
   if (n >= 105 && n <= 128) { ok = cholesky_regs<64, SM>(c, n, B); return true; }
+  return false;
+}
+#endif
+
+#ifndef DG_HOSTSIM
+// ---- register-resident triangular inverse (256-thread CTAs, n <= 2*RMAX <= 128; pairs with cholesky_regs) ----------------
+// Y = L^-1 column by column: lanes (2c, 2c+1) of a warp own column c, the residual r of L y = e_c lives in their
+// registers in 4-row chunks that alternate between the two lanes (local index r <-> row 8 (r>>2) + 4 g + (r&3)).
+// Step k (the same k in every thread; columns c > k just carry zeros, which also zero-fills the upper triangle the
+// active-set solver expects):  y_k = r_k / L_kk is formed by the lane that holds row k and handed to its neighbour with
+// one shuffle, then r_j -= L[j][k] y_k over the thread's live chunks.  Column k of L is read as ROW k of the mirror L'
+// that cholesky_regs leaves in the upper triangle: the four rows of a chunk are contiguous, every lane of a parity reads
+// the same address (broadcast), 128-bit loads on even k.  No CTA barrier inside the sweep: the warps never exchange data.
+// The blocked shared-memory version this replaces (tri_inverse) costs 108 kcycles at n = 100.
+template <int RMAX, int CB>
+DG_DEV void trinv_sweep_vec(double (&a)[RMAX], const double* DG_RESTRICT row, int g, int n, double nx) {
+#pragma unroll
+  for (int cb = CB; cb < RMAX; cb += 4) {
+    if (2 * cb + 4 * g < n) {
+      const double2 x01 = *reinterpret_cast<const double2*>(row + 2 * cb), x23 = *reinterpret_cast<const double2*>(row + 2 * cb + 2);
+      a[cb + 0] = fma(x01.x, nx, a[cb + 0]); a[cb + 1] = fma(x01.y, nx, a[cb + 1]);
+      a[cb + 2] = fma(x23.x, nx, a[cb + 2]); a[cb + 3] = fma(x23.y, nx, a[cb + 3]);
+    }
+  }
+}
+template <int RMAX, int CB>
+DG_DEV void trinv_sweep_scl(double (&a)[RMAX], const double* DG_RESTRICT row, int g, int n, double nx) {
+#pragma unroll
+  for (int cb = CB; cb < RMAX; cb += 4) {
+    if (2 * cb + 4 * g < n) {
+      const double x0 = row[2 * cb], x1 = row[2 * cb + 1], x2 = row[2 * cb + 2], x3 = row[2 * cb + 3];
+      a[cb + 0] = fma(x0, nx, a[cb + 0]); a[cb + 1] = fma(x1, nx, a[cb + 1]);
+      a[cb + 2] = fma(x2, nx, a[cb + 2]); a[cb + 3] = fma(x3, nx, a[cb + 3]);
+    }
+  }
+}
+template <int RMAX, bool SM>
+DG_DEVN void tri_inverse_regs(Cta& c, int n, const LinBuf& B_) {
+  static_assert(RMAX % 4 == 0 && RMAX <= 64, "RMAX: multiple of the 4-row chunk, at most 64 rows per thread");
+  const LinBuf B = B_; DG_SH_LIN_T(B);
+  const double* DG_RESTRICT W = B.matA;
+  double* DG_RESTRICT Y = B.matB;
+  double* DG_RESTRICT rdiag = B.part;
+  const int ld = B.ld;
+  const int col = c.tid() >> 1, g = c.tid() & 1;
+  DG_FOR(k, n) rdiag[k] = 1.0 / W[k * ld + k];
+  double a[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) a[r] = (8 * (r >> 2) + 4 * g + (r & 3)) == col ? 1.0 : 0.0;
+  c.sync();
+  for (int k = 0; k < n; ++k) {
+    const int seg = k >> 3;                                        // CTA-uniform chunk offset CB = 4*seg
+    const bool own = g == ((k >> 2) & 1);
+    double rk = 0.0;
+    DG_TRI_SWITCH(seg, rk = tri_peel<RMAX, CB>(a, k & 3))
+    double x = own ? rk * rdiag[k] : 0.0;
+    const double other = __shfl_xor_sync(0xffffffffu, x, 1);
+    x = own ? x : other;
+    if (own && col < n) Y[k * ld + col] = x;
+    const double* DG_RESTRICT row = W + k * ld + 4 * g;
+    if (k & 1) { DG_TRI_SWITCH(seg, (trinv_sweep_scl<RMAX, CB>(a, row, g, n, -x))) }
+    else { DG_TRI_SWITCH(seg, (trinv_sweep_vec<RMAX, CB>(a, row, g, n, -x))) }
+  }
+}
+template <bool SM>
+DG_DEV bool tri_inverse_regs_dispatch(Cta& c, int n, const LinBuf& B) {
+  if (c.nt() != 256) return false;
+  if (n >= 27 && n <= 40) { tri_inverse_regs<20, SM>(c, n, B); return true; }
+  if (n >= 43 && n <= 64) { tri_inverse_regs<32, SM>(c, n, B); return true; }
+  if (n >= 70 && n <= 104) { tri_inverse_regs<52, SM>(c, n, B); return true; }
+  if (n >= 105 && n <= 128) { tri_inverse_regs<64, SM>(c, n, B); return true; }
   return false;
 }
 #endif

@@ -551,15 +551,20 @@ DG_DEVN bool qp_factor(Cta& c, const Dims& D_, const double* DG_RESTRICT qv, con
   const QpBuf Q = Q_; DG_SH_QP(Q); const LinBuf B = B_; DG_SH_LIN(B); const Dims D = D_;
   const int n = D.n, m = D.m, ld = B.ld;
   double* DG_RESTRICT Y = B.matB;
+  bool regs = false;
   {
     bool ok = false;
 #ifndef DG_HOSTSIM
-    if (!cholesky_regs_dispatch<SM>(c, n, B, ok))
+    regs = cholesky_regs_dispatch<SM>(c, n, B, ok);
+    if (!regs)
 #endif
     ok = cholesky_lower<SM>(c, n, ld, B.matA, B.sp, B.part);
     if (!ok) return false;
   }
   c.lap(PH_CHOL);
+#ifndef DG_HOSTSIM
+  if (!(regs && tri_inverse_regs_dispatch<SM>(c, n, B)))       // (the register form reads the mirror L' cholesky_regs leaves)
+#endif
   tri_inverse<SM>(c, n, ld, B.matA, Y, B.sp, B.part);
   c.sync();
   c.lapf(PH_TRINV);
