@@ -965,6 +965,205 @@ DG_DEVN bool cholesky_regs(Cta& c, int n, const LinBuf& B_) {
   return true;
 }
 
+// ---- Cholesky and triangular inverse on 2D register tiles (256-thread CTAs, n <= 16*T <= 128) -------------------------
+// Same 16 x 16 thread grid and cyclic tiles as sym_tridiag_tiles: the column-per-thread forms above move ~n/2 doubles
+// per THREAD and step through shared memory (the LSU, not the FP64 pipe, bounds them); a tile needs the T entries of the
+// step's column that belong to its rows and the T that belong to its columns.
+// Cholesky, iteration k (one barrier): the raw column k (published by its holders in the previous iteration) gives
+// 1/sqrt(d) and l = x/sqrt(d) for the thread's rows and columns; beside that dependent chain the rank-1 update of step
+// k - 1 is finished (all tile columns but the one done early); then the tile column that contains column k + 1 is updated,
+// its holders publish column k + 1, barrier.  L is written column by column into W (lower triangle).
+template <int T, int S, bool SM>
+DG_DEV bool chol_tile_iter(Cta& c, int n, int k, int ld, double (&a)[T][T], double* DG_RESTRICT W, double* DG_RESTRICT xs2,
+                           double (&lrp)[T], double (&lcp)[T]) {
+  const int tj = c.tid() & 15, ti = c.tid() >> 4;
+  const double* DG_RESTRICT xs = xs2 + (k & 1) * 128;
+  double* DG_RESTRICT xn = xs2 + ((k & 1) ^ 1) * 128;
+  const double d = xs[k];
+  double xr[T], xc[T];
+#pragma unroll
+  for (int r = S; r < T; ++r) { xr[r] = xs[ti + 16 * r]; xc[r] = xs[tj + 16 * r]; }
+  // finish step k - 1 beside the reciprocal square root
+#pragma unroll
+  for (int r = S; r < T; ++r)
+#pragma unroll
+    for (int cb = S + 1; cb < T; ++cb) a[r][cb] = fma(-lrp[r], lcp[cb], a[r][cb]);
+  if (!(d > 0.0)) return false;
+  const double inv = DG_RSQRT(d);
+#pragma unroll
+  for (int r = S; r < T; ++r) { lrp[r] = xr[r] * inv; lcp[r] = xc[r] * inv; }
+  if (tj == (k & 15)) {
+#pragma unroll
+    for (int r = S; r < T; ++r) { const int j = ti + 16 * r; if (j >= k && j < n) W[j * ld + k] = lrp[r]; }
+  }
+  if (k + 1 < n) {
+    const bool same = ((k + 1) >> 4) == S;
+    if (same) {
+#pragma unroll
+      for (int r = S; r < T; ++r) a[r][S] = fma(-lrp[r], lcp[S], a[r][S]);
+    } else if constexpr (S + 1 < T) {
+#pragma unroll
+      for (int r = S; r < T; ++r) a[r][S + 1] = fma(-lrp[r], lcp[S + 1], a[r][S + 1]);
+    }
+    if (tj == ((k + 1) & 15)) {
+#pragma unroll
+      for (int r = 0; r < T; ++r) {
+        const int j = ti + 16 * r;
+        double val = 0.0;
+        if (r >= S && j > k && j < n) {
+          if constexpr (S + 1 < T) val = same ? a[r][S] : a[r][S + 1];
+          else val = a[r][S];
+        }
+        xn[j] = val;
+      }
+    }
+  }
+  c.sync();
+  return true;
+}
+#define DG_CHT_CASE(m) case m: if constexpr (m < T) ok = chol_tile_iter<T, m, SM>(c, n, k, ld, a, W, xs2, lrp, lcp); break;
+template <int T, bool SM>
+DG_DEVN bool cholesky_tiles(Cta& c, int n, const LinBuf& B_) {
+  const LinBuf B = B_; DG_SH_LIN_T(B);
+  double* DG_RESTRICT W = B.matA;
+  const int ld = B.ld;
+  const int tj = c.tid() & 15, ti = c.tid() >> 4;
+  double* DG_RESTRICT xs2 = B.part;                               // two buffers of 128: raw column of the iteration
+  double a[T][T], lrp[T], lcp[T];
+#pragma unroll
+  for (int r = 0; r < T; ++r) {
+    lrp[r] = 0.0; lcp[r] = 0.0;
+#pragma unroll
+    for (int cb = 0; cb < T; ++cb) {
+      const int j = ti + 16 * r, i = tj + 16 * cb;
+      a[r][cb] = (j < n && i < n) ? W[j * ld + i] : 0.0;
+    }
+  }
+  DG_FOR(t, 256) xs2[t] = 0.0;
+  c.sync();
+  if (tj == 0) {
+#pragma unroll
+    for (int r = 0; r < T; ++r) { const int j = ti + 16 * r; if (j < n) xs2[j] = a[r][0]; }
+  }
+  c.sync();
+  bool ok = true;
+  for (int k = 0; k < n && ok; ++k) {
+    switch (k >> 4) { DG_CHT_CASE(0) DG_CHT_CASE(1) DG_CHT_CASE(2) DG_CHT_CASE(3) DG_CHT_CASE(4) DG_CHT_CASE(5) DG_CHT_CASE(6) DG_CHT_CASE(7) default: break; }
+  }
+  c.sync();
+  return ok;
+}
+#undef DG_CHT_CASE
+
+// Triangular inverse Y = L^-1 on tiles: the tiles start as the identity and carry  e_i - sum_{j<k} L[i][j] Y[j][:] ; iteration
+// k reads the final row k of Y (published by its holders in the previous iteration) and column k of L (straight from W,
+// broadcast inside a thread row), finishes the update of step k - 1 beside those loads, updates the tile row that contains
+// row k + 1, whose holders scale it by 1/L[k+1][k+1], publish it and store it as row k + 1 of Y.  One barrier per iteration.
+template <int T, int S, bool SM>
+DG_DEV void trinv_tile_iter(Cta& c, int n, int k, int ld, double (&a)[T][T], const double* DG_RESTRICT W, double* DG_RESTRICT Y,
+                            double* DG_RESTRICT xr2, const double* DG_RESTRICT rdiag, double (&mp)[T], double (&yp)[T]) {
+  const int tj = c.tid() & 15, ti = c.tid() >> 4;
+  const double* DG_RESTRICT xrow = xr2 + (k & 1) * 128;
+  double* DG_RESTRICT xnext = xr2 + ((k & 1) ^ 1) * 128;
+  double m[T], yk[T];
+#pragma unroll
+  for (int r = S; r < T; ++r) { const int i = ti + 16 * r; m[r] = (i > k && i < n) ? W[i * ld + k] : 0.0; }
+#pragma unroll
+  for (int cb = 0; cb <= S; ++cb) yk[cb] = xrow[tj + 16 * cb];
+  // finish step k - 1: tile rows above the one done early
+#pragma unroll
+  for (int r = S + 1; r < T; ++r)
+#pragma unroll
+    for (int cb = 0; cb <= S; ++cb) a[r][cb] = fma(-mp[r], yp[cb], a[r][cb]);
+  if (k + 1 < n) {
+    const bool same = ((k + 1) >> 4) == S;
+    const double rd = rdiag[k + 1];
+    if (same) {
+#pragma unroll
+      for (int cb = 0; cb <= S; ++cb) a[S][cb] = fma(-m[S], yk[cb], a[S][cb]);
+    } else if constexpr (S + 1 < T) {
+#pragma unroll
+      for (int cb = 0; cb <= S; ++cb) a[S + 1][cb] = fma(-m[S + 1], yk[cb], a[S + 1][cb]);
+    }
+    if (ti == ((k + 1) & 15)) {
+#pragma unroll
+      for (int cb = 0; cb < T; ++cb) {
+        const int i = tj + 16 * cb;
+        double val = 0.0;
+        if (cb <= S + 1 && i <= k + 1) {
+          if constexpr (S + 1 < T) val = (same ? a[S][cb] : a[S + 1][cb]) * rd;
+          else val = a[S][cb] * rd;
+        }
+        xnext[i] = val;
+        if (i < n) Y[(k + 1) * ld + i] = val;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = S; r < T; ++r) mp[r] = m[r];
+#pragma unroll
+  for (int cb = 0; cb <= S; ++cb) yp[cb] = yk[cb];
+  c.sync();
+}
+#define DG_TIT_CASE(m) case m: if constexpr (m < T) trinv_tile_iter<T, m, SM>(c, n, k, ld, a, W, Y, xr2, rdiag, mp, yp); break;
+template <int T, bool SM>
+DG_DEVN void tri_inverse_tiles(Cta& c, int n, const LinBuf& B_) {
+  const LinBuf B = B_; DG_SH_LIN_T(B);
+  const double* DG_RESTRICT W = B.matA;
+  double* DG_RESTRICT Y = B.matB;
+  const int ld = B.ld;
+  const int tj = c.tid() & 15, ti = c.tid() >> 4;
+  double* DG_RESTRICT xr2 = B.part;                               // two buffers of 128: final row k of Y
+  double* DG_RESTRICT rdiag = B.part + 256;                       // 1 / L[k][k]
+  double a[T][T], mp[T], yp[T];
+#pragma unroll
+  for (int r = 0; r < T; ++r) {
+    mp[r] = 0.0; yp[r] = 0.0;
+#pragma unroll
+    for (int cb = 0; cb < T; ++cb) a[r][cb] = (ti + 16 * r == tj + 16 * cb) ? 1.0 : 0.0;
+  }
+  DG_FOR(t, 256) xr2[t] = 0.0;
+  DG_FOR(t, n) rdiag[t] = 1.0 / W[t * ld + t];
+  c.sync();
+  if (ti == 0) {
+    // row 0 of Y: (1 / L00, 0, ..)
+#pragma unroll
+    for (int cb = 0; cb < T; ++cb) { const int i = tj + 16 * cb; const double val = i == 0 ? rdiag[0] : 0.0; if (i < 128) xr2[i] = val; if (i < n) Y[i] = val; }
+  }
+  c.sync();
+  for (int k = 0; k < n; ++k) {
+    switch (k >> 4) { DG_TIT_CASE(0) DG_TIT_CASE(1) DG_TIT_CASE(2) DG_TIT_CASE(3) DG_TIT_CASE(4) DG_TIT_CASE(5) DG_TIT_CASE(6) DG_TIT_CASE(7) default: break; }
+  }
+}
+#undef DG_TIT_CASE
+
+template <bool SM>
+DG_DEV bool cholesky_tiles_dispatch(Cta& c, int n, const LinBuf& B, bool& ok) {
+  if (c.nt() != 256 || n < 33 || n > 128) return false;
+  switch ((n + 15) >> 4) {
+    case 3: ok = cholesky_tiles<3, SM>(c, n, B); break;
+    case 4: ok = cholesky_tiles<4, SM>(c, n, B); break;
+    case 5: ok = cholesky_tiles<5, SM>(c, n, B); break;
+    case 6: ok = cholesky_tiles<6, SM>(c, n, B); break;
+    case 7: ok = cholesky_tiles<7, SM>(c, n, B); break;
+    default: ok = cholesky_tiles<8, SM>(c, n, B); break;
+  }
+  return true;
+}
+template <bool SM>
+DG_DEV bool tri_inverse_tiles_dispatch(Cta& c, int n, const LinBuf& B) {
+  if (c.nt() != 256 || n < 33 || n > 128) return false;
+  switch ((n + 15) >> 4) {
+    case 3: tri_inverse_tiles<3, SM>(c, n, B); break;
+    case 4: tri_inverse_tiles<4, SM>(c, n, B); break;
+    case 5: tri_inverse_tiles<5, SM>(c, n, B); break;
+    case 6: tri_inverse_tiles<6, SM>(c, n, B); break;
+    case 7: tri_inverse_tiles<7, SM>(c, n, B); break;
+    default: tri_inverse_tiles<8, SM>(c, n, B); break;
+  }
+  return true;
+}
+
 // picks the instantiation whose scratch fits; false = not applicable (the caller runs cholesky_lower)
 template <bool SM>
 DG_DEV bool cholesky_regs_dispatch(Cta& c, int n, const LinBuf& B, bool& ok) {

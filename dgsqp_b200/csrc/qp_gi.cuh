@@ -555,7 +555,8 @@ DG_DEVN bool qp_factor(Cta& c, const Dims& D_, const double* DG_RESTRICT qv, con
   {
     bool ok = false;
 #ifndef DG_HOSTSIM
-    regs = cholesky_regs_dispatch<SM>(c, n, B, ok);
+    if (!cholesky_tiles_dispatch<SM>(c, n, B, ok)) regs = cholesky_regs_dispatch<SM>(c, n, B, ok);
+    else regs = true;
     if (!regs)
 #endif
     ok = cholesky_lower<SM>(c, n, ld, B.matA, B.sp, B.part);
@@ -563,7 +564,8 @@ DG_DEVN bool qp_factor(Cta& c, const Dims& D_, const double* DG_RESTRICT qv, con
   }
   c.lap(PH_CHOL);
 #ifndef DG_HOSTSIM
-  if (!(regs && tri_inverse_regs_dispatch<SM>(c, n, B)))       // (the register form reads the mirror L' cholesky_regs leaves)
+  // (tri_inverse_regs reads the mirror L' that cholesky_regs leaves in the upper triangle; the tile forms need only L)
+  if (!tri_inverse_tiles_dispatch<SM>(c, n, B) && !(regs && tri_inverse_regs_dispatch<SM>(c, n, B)))
 #endif
   tri_inverse<SM>(c, n, ld, B.matA, Y, B.sp, B.part);
   c.sync();
