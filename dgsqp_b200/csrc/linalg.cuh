@@ -60,8 +60,10 @@ struct LinBuf {
 // to tridiagonal form; reflector k is stored in W[k+2.., k] (v[0] = 1 implicit) with tau[k].
 // Both O(len^2) parts of a step -- p = tau A22 v and A22 -= v w' + w v' -- are spread over the whole CTA with the 2D
 // decomposition (thread = column, column groups interleave the rows).  Four barriers per step.
+// kstop < n - 1: only the steps k < kstop are taken (dg, od, tau, reflectors of those columns; the trailing matrix is left
+// updated in W for a register-resident continuation, see nearest_pd).
 template <bool SM>
-DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_) {
+DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_, int kstop) {
   // local copies: the tables live in shared memory and would otherwise be re-read after every store
   const LinBuf B = B_; DG_SH_LIN_T(B);
   double* DG_RESTRICT W = B.matA;
@@ -73,7 +75,7 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_) {
   double nrm = 0.0;
   for (int i = c.tid() + 2; i < n; i += c.nt()) { double xv = W[i * ld]; nrm += xv * xv; }
   double xn2 = c.sum(nrm);
-  for (int k = 0; k + 1 < n; ++k) {
+  for (int k = 0; k + 1 < n && k < kstop; ++k) {
     const int len = n - k - 1;            // x = W[k+1.., k]
     const int off = k + 1;
     const double alpha = W[off * ld + k];
@@ -93,13 +95,32 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_) {
     }
     const Split2 sp = split2(c, len);
     const double* DG_RESTRICT vc = W + off * ld + k;            // x_j = vc[j*ld]
+    if constexpr (!SM) {
+      // W may live in the L2-resident workspace: the column goes through shared memory once (pv is free until v is formed)
+      DG_FOR(i, len) pv[i] = vc[i * ld];
+      c.sync();
+    }
     // partial products  sum_{j>=1, j = g (mod G)} A22[j][i] x_j   (the j = 0 term has v_0 = 1 and no scale)
     for (int i = sp.i0; i < len; i += sp.istep) {
       const double* DG_RESTRICT col = W + off * ld + off + i;
       double a0 = 0.0, a1 = 0.0;
       int j = sp.g == 0 ? sp.G : sp.g;
-      for (; j + sp.G < len; j += 2 * sp.G) { a0 += col[j * ld] * vc[j * ld]; a1 += col[(j + sp.G) * ld] * vc[(j + sp.G) * ld]; }
-      if (j < len) a0 += col[j * ld] * vc[j * ld];
+      if constexpr (!SM) {
+        // L2 latency bound: eight loads in flight per thread
+        double a2 = 0.0, a3 = 0.0;
+        for (; j + 7 * sp.G < len; j += 8 * sp.G) {
+          double y[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) y[u] = col[(j + u * sp.G) * ld];
+          a0 += y[0] * pv[j] + y[4] * pv[j + 4 * sp.G]; a1 += y[1] * pv[j + sp.G] + y[5] * pv[j + 5 * sp.G];
+          a2 += y[2] * pv[j + 2 * sp.G] + y[6] * pv[j + 6 * sp.G]; a3 += y[3] * pv[j + 3 * sp.G] + y[7] * pv[j + 7 * sp.G];
+        }
+        for (; j < len; j += sp.G) a0 += col[j * ld] * pv[j];
+        a0 += a2; a1 += a3;
+      } else {
+        for (; j + sp.G < len; j += 2 * sp.G) { a0 += col[j * ld] * vc[j * ld]; a1 += col[(j + sp.G) * ld] * vc[(j + sp.G) * ld]; }
+        if (j < len) a0 += col[j * ld] * vc[j * ld];
+      }
       part[sp.g * sp.istep + i] = a0 + a1;
     }
     c.sync();
@@ -109,7 +130,8 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_) {
         double acc = part[i];
         for (int g = 1; g < sp.G; ++g) acc += part[g * sp.istep + i];
         const double pi = (W[off * ld + off + i] + scale * acc) * tauk;
-        const double vi = i == 0 ? 1.0 : vc[i * ld] * scale;
+        const double xi = SM ? vc[i * ld] : pv[i];
+        const double vi = i == 0 ? 1.0 : xi * scale;
         pv[i] = vi; wv[i] = pi;
         pdot += pi * vi;
       }
@@ -127,7 +149,23 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_) {
     for (int j = sp.i0; j < len; j += sp.istep) {
       const double vj = pv[j], wj = wv[j];
       double* DG_RESTRICT col = W + off * ld + off + j;
-      for (int i = sp.g; i < len; i += sp.G) {
+      int i = sp.g;
+      if constexpr (!SM) {
+        // eight independent read-modify-writes per step
+        for (; i + 7 * sp.G < len; i += 8 * sp.G) {
+          double y[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) y[u] = col[(i + u * sp.G) * ld];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int iu = i + u * sp.G;
+            const double cv = y[u] - (pv[iu] * wj + wv[iu] * vj);
+            col[iu * ld] = cv;
+            if (iu == 0 && j >= 2) nrm += cv * cv;
+          }
+        }
+      }
+      for (; i < len; i += sp.G) {
         const double cv = col[i * ld] - (pv[i] * wj + wv[i] * vj);
         col[i * ld] = cv;
         if (i == 0 && j >= 2) nrm += cv * cv;
@@ -135,7 +173,7 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_) {
     }
     xn2 = c.sum(nrm);
   }
-  if (c.tid() == 0) { B.dg[n - 1] = W[(n - 1) * ld + (n - 1)]; B.od[n - 1] = 0.0; B.od2[n - 1] = 0.0; }
+  if (c.tid() == 0 && kstop >= n - 1) { B.dg[n - 1] = W[(n - 1) * ld + (n - 1)]; B.od[n - 1] = 0.0; B.od2[n - 1] = 0.0; }
   c.sync();
 }
 
@@ -700,9 +738,17 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
     c.sync();
     c.lapf(PH_PD_SYM);
 #ifndef DG_HOSTSIM
-    if (!sym_tridiag_tiles_dispatch<SM>(c, n, B) && !sym_tridiag_regs_dispatch<SM>(c, n, B))
+    if (c.nt() == 256 && n > 128 && n <= 256) {
+      // larger games (3-4 agents): the generic steps until the trailing matrix fits the register tiles, then the tile form
+      // on the trailing 128 x 128 block (same algorithm continued: shifted views of W, dg, od, tau)
+      const int base = n - 128;
+      sym_tridiag<SM>(c, n, B, base);
+      LinBuf Bt = B;
+      Bt.matA = B.matA + (size_t)base * ld + base; Bt.dg = B.dg + base; Bt.od = B.od + base; Bt.od2 = B.od2 + base; Bt.tau = B.tau + base;
+      sym_tridiag_tiles<8, SM>(c, 128, Bt);
+    } else if (!sym_tridiag_tiles_dispatch<SM>(c, n, B) && !sym_tridiag_regs_dispatch<SM>(c, n, B))
 #endif
-    sym_tridiag<SM>(c, n, B);
+    sym_tridiag<SM>(c, n, B, n);
     c.lap(PH_PD_TRIDIAG);
     double tn = 0.0;
     DG_FOR(i, n) {

@@ -44,17 +44,42 @@ MU_VIO_DETERMINISTIC = 1e-10  # the penalty-weight switch no longe
 
 
 class DGSQP:
-    """``DGSQP(game, params)``.  ``game`` is one of the records of :mod:`dgsqp_b200.games` (the literals the reference
-    scripts feed CasADi); :func:`dgsqp_b200.frontend.game_from_reference_args` builds it from the reference's own
-    constructor arguments ``(joint_dynamics, costs, agent_constraints, shared_constraints, bounds)`` (DGSQP.py:26-34) when
-    they describe one of the supported game families.
+    """``DGSQP(game, params)`` or, like the reference (DGSQP.py:25-33), ``DGSQP(joint_dynamics, costs, agent_constraints,
+    shared_constraints, bounds, params)``.  ``game`` is one of the records of :mod:`dgsqp_b200.games` (the literals the
+    reference scripts feed CasADi); the six-argument form is routed through
+    :func:`dgsqp_b200.frontend.game_from_reference_args`, which identifies that record from plain-Python cost / constraint
+    callables and raises ``NotImplementedError`` for anything outside the supported game family.
 
     ``mu_vio_thresh``: 0 (default) is the reference's rule; ``MU_VIO_DETERMINISTIC`` is the setting every parity fixture
     was generated with.  ``qp_warm_start``: each QP of an instance starts from the active set of its
     previous QP (same solution, fewer active-set iterations); False = cold start like the reference (DGSQP.py:240-241)."""
 
-    def __init__(self, game: RacingGame, params: DGSQPParams = None, print_method=print, device: int = 0,
-                 mu_vio_thresh: float = MU_VIO_REFERENCE, qp_warm_start: bool = True):
+    def __init__(self, game, *args, **kw):
+        from .dynamics import CasadiDecoupledMultiAgentDynamicsModel
+        if isinstance(game, CasadiDecoupledMultiAgentDynamicsModel):
+            # the reference's own form (DGSQP.py:25-33):
+            #   DGSQP(joint_dynamics, costs, agent_constraints, shared_constraints, bounds, params=..., print_method=...)
+            from .frontend import game_from_reference_args
+            names = ["costs", "agent_constraints", "shared_constraints", "bounds", "params", "print_method"]
+            ref = dict(zip(names, args))
+            for k in names:
+                if k in kw:
+                    ref[k] = kw.pop(k)
+            missing = [k for k in names[:4] if k not in ref]
+            if missing:
+                raise TypeError("DGSQP(joint_dynamics, costs, agent_constraints, shared_constraints, bounds, params): missing "
+                                + ", ".join(missing))
+            for k in ("xy_plot", "use_mx"):          # accepted and ignored like a head-less run of the reference
+                kw.pop(k, None)
+            params = ref.get("params") or DGSQPParams()
+            record = game_from_reference_args(game, ref["costs"], ref["agent_constraints"], ref["shared_constraints"],
+                                              ref["bounds"], params)
+            self._init(record, params, ref.get("print_method", print), **kw)
+        else:
+            self._init(game, *args, **kw)
+
+    def _init(self, game: RacingGame, params: DGSQPParams = None, print_method=print, device: int = 0,
+              mu_vio_thresh: float = MU_VIO_REFERENCE, qp_warm_start: bool = True):
         if params is None:
             params = DGSQPParams()
         self.v2 = isinstance(params, DGSQPV2Params)      # step policy of DGSQP_v2.py instead of DGSQP.py

@@ -128,15 +128,19 @@ def test_solve_matches_golden(chicane_full):
 # tolerance: the curve configuration runs with reg = 0 (DGSQP_ALGAMES_monte_carlo_curve.py:161), so the projected
 # Hessian keeps eigenvalues of 1e-10 (cond ~1e11) and the QP step amplifies the 1e-13 differences between
 # LAPACK's eigh and the device eigen-solver; 1e-6 is kept for the regularised games.
-@pytest.mark.parametrize("name,mk,tol", [
-    ("curve45_N15_seed1", lambda: (dg.curve_game(45.0, 15), dg.curve_params(15)), 1e-4),
-    ("agents3_N15_seed0", lambda: (dg.agents_game(3, 90.0, 15), dg.agents_params(15)), 1e-6)])
-def test_solve_other_games_match_golden(name, mk, tol):
+@pytest.mark.parametrize("name,mk,tol,limit", [
+    ("curve45_N15_seed1", lambda: (dg.curve_game(45.0, 15), dg.curve_params(15)), 1e-4, None),
+    ("agents3_N15_seed0", lambda: (dg.agents_game(3, 90.0, 15), dg.agents_params(15)), 1e-6, None),
+    # round-2 fixtures (tests/golden/make_golden_r2.py): the N = 25 curves and four agents at N = 25 (n = 200)
+    ("curve75_N25_seed1", lambda: (dg.curve_game(75.0, 25), dg.curve_params(25)), 1e-6, None),
+    ("curve90_N25_seed1", lambda: (dg.curve_game(90.0, 25), dg.curve_params(25)), 1e-6, None),
+    ("agents4_N25_seed0", lambda: (dg.agents_game(4, 90.0, 25), dg.agents_params(25)), 1e-6, 4)])
+def test_solve_other_games_match_golden(name, mk, tol, limit):
     game, params = mk()
     hs = HostSim(game, params)
     data = np.load(GOLDEN / f"{name}.npz")
     meta = json.loads((GOLDEN / f"{name}.json").read_text())
-    B = data["x0"].shape[0]
+    B = data["x0"].shape[0] if limit is None else limit
     same = 0
     for i in range(B):
         r = hs.solve(data["x0"][i], data["u_ws"][i], data["l_init"][i])
