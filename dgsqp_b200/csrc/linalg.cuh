@@ -473,8 +473,9 @@ DG_DEV void tridiag_tile_step(Cta& c, int n, int k, int ld, double (&a)[T][T], d
 }
 
 #define DG_TILE_CASE(m) case m: if constexpr (m < T) tridiag_tile_step<T, m, SM>(c, n, k, ld, a, W, B, xs, pn, pb, hp, hh); break;
+// Qraw != null: the tiles are loaded as sym(Qraw) = (Qraw + Qraw')/2 straight from the row-major n x n matrix (no pass through W).
 template <int T, bool SM>
-DG_DEVN void sym_tridiag_tiles(Cta& c, int n, const LinBuf& B_) {
+DG_DEVN void sym_tridiag_tiles(Cta& c, int n, const LinBuf& B_, const double* DG_RESTRICT Qraw) {
   static_assert(T >= 1 && T <= 8, "tiles of at most 8 x 8 entries per thread");
   const LinBuf B = B_; DG_SH_LIN_T(B);
   double* DG_RESTRICT W = B.matA;
@@ -490,7 +491,7 @@ DG_DEVN void sym_tridiag_tiles(Cta& c, int n, const LinBuf& B_) {
 #pragma unroll
     for (int cb = 0; cb < T; ++cb) {
       const int j = ti + 16 * r, i = tj + 16 * cb;
-      a[r][cb] = (j < n && i < n) ? W[j * ld + i] : 0.0;
+      a[r][cb] = (j < n && i < n) ? (Qraw ? 0.5 * (Qraw[j * n + i] + Qraw[i * n + j]) : W[j * ld + i]) : 0.0;
     }
   DG_FOR(t, 128) { xs[t] = 0.0; pb[t] = 0.0; }
   c.sync();
@@ -518,17 +519,18 @@ DG_DEVN void sym_tridiag_tiles(Cta& c, int n, const LinBuf& B_) {
 }
 #undef DG_TILE_CASE
 
+DG_DEV bool sym_tridiag_tiles_applies(const Cta& c, int n) { return c.nt() == 256 && n >= 33 && n <= 128; }
 template <bool SM>
-DG_DEV bool sym_tridiag_tiles_dispatch(Cta& c, int n, const LinBuf& B) {
-  if (c.nt() != 256 || n < 33 || n > 128) return false;
+DG_DEV bool sym_tridiag_tiles_dispatch(Cta& c, int n, const LinBuf& B, const double* DG_RESTRICT Qraw) {
+  if (!sym_tridiag_tiles_applies(c, n)) return false;
   const int T = (n + 15) >> 4;
   switch (T) {
-    case 3: sym_tridiag_tiles<3, SM>(c, n, B); break;
-    case 4: sym_tridiag_tiles<4, SM>(c, n, B); break;
-    case 5: sym_tridiag_tiles<5, SM>(c, n, B); break;
-    case 6: sym_tridiag_tiles<6, SM>(c, n, B); break;
-    case 7: sym_tridiag_tiles<7, SM>(c, n, B); break;
-    default: sym_tridiag_tiles<8, SM>(c, n, B); break;
+    case 3: sym_tridiag_tiles<3, SM>(c, n, B, Qraw); break;
+    case 4: sym_tridiag_tiles<4, SM>(c, n, B, Qraw); break;
+    case 5: sym_tridiag_tiles<5, SM>(c, n, B, Qraw); break;
+    case 6: sym_tridiag_tiles<6, SM>(c, n, B, Qraw); break;
+    case 7: sym_tridiag_tiles<7, SM>(c, n, B, Qraw); break;
+    default: sym_tridiag_tiles<8, SM>(c, n, B, Qraw); break;
   }
   return true;
 }
@@ -730,12 +732,17 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
   int nneg = 0;
   const double* Zall = nullptr;
   if (conv_approx) {
-    // symmetric part into W
-    DG_FOR(t, n * n) {
-      int i = t / n, j = t - i * n;
-      Hm[i * ld + j] = 0.5 * (Qraw[i * n + j] + Qraw[j * n + i]);
+    // symmetric part into W (the register-tile tridiagonalisation loads it from Qraw itself)
+#ifndef DG_HOSTSIM
+    if (!sym_tridiag_tiles_applies(c, n))
+#endif
+    {
+      DG_FOR(t, n * n) {
+        int i = t / n, j = t - i * n;
+        Hm[i * ld + j] = 0.5 * (Qraw[i * n + j] + Qraw[j * n + i]);
+      }
+      c.sync();
     }
-    c.sync();
     c.lapf(PH_PD_SYM);
 #ifndef DG_HOSTSIM
     if (c.nt() == 256 && n > 128 && n <= 256) {
@@ -745,8 +752,8 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
       sym_tridiag<SM>(c, n, B, base);
       LinBuf Bt = B;
       Bt.matA = B.matA + (size_t)base * ld + base; Bt.dg = B.dg + base; Bt.od = B.od + base; Bt.od2 = B.od2 + base; Bt.tau = B.tau + base;
-      sym_tridiag_tiles<8, SM>(c, 128, Bt);
-    } else if (!sym_tridiag_tiles_dispatch<SM>(c, n, B) && !sym_tridiag_regs_dispatch<SM>(c, n, B))
+      sym_tridiag_tiles<8, SM>(c, 128, Bt, nullptr);
+    } else if (!sym_tridiag_tiles_dispatch<SM>(c, n, B, Qraw) && !sym_tridiag_regs_dispatch<SM>(c, n, B))
 #endif
     sym_tridiag<SM>(c, n, B, n);
     c.lap(PH_PD_TRIDIAG);
@@ -846,12 +853,27 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
     }
   }
   // H = sym(Q) + sum_j (floor - lam_j) y_j y_j' + reg I   (the reflectors in matA are dead now)
-  DG_FOR(t, n * n) {
-    int i = t / n, j = t - i * n;
-    double acc = 0.5 * (Qraw[i * n + j] + Qraw[j * n + i]);
-    for (int jv = 0; jv < nneg; ++jv) acc += (floor_val - B.lam[jv]) * Zall[(size_t)jv * n + i] * Zall[(size_t)jv * n + j];
-    if (i == j) acc += reg;
-    Hm[i * ld + j] = acc;
+  // (Qraw is streamed from L2: the loads of four entries are issued before the first is used)
+  for (int t0 = c.tid(); t0 < n * n; t0 += 4 * c.nt()) {
+    double q1[4], q2[4];
+    int ii[4], jj[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * c.nt();
+      ii[u] = t / n; jj[u] = t - ii[u] * n;
+      const bool in = t < n * n;
+      q1[u] = in ? Qraw[ii[u] * n + jj[u]] : 0.0; q2[u] = in ? Qraw[jj[u] * n + ii[u]] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (t0 + u * c.nt() < n * n) {
+        const int i = ii[u], j = jj[u];
+        double acc = 0.5 * (q1[u] + q2[u]);
+        for (int jv = 0; jv < nneg; ++jv) acc += (floor_val - B.lam[jv]) * Zall[(size_t)jv * n + i] * Zall[(size_t)jv * n + j];
+        if (i == j) acc += reg;
+        Hm[i * ld + j] = acc;
+      }
+    }
   }
   c.sync();
   c.lap(PH_PD_EIG);
