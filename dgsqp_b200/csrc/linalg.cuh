@@ -784,6 +784,10 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
         bool cluster = false;
         for (int jj = 1; jj < kc; ++jj)
           if (fabs(B.lam[j0 + jj] - B.lam[j0 + jj - 1]) <= 1e-3 * tnorm) cluster = true;
+        // a cluster may straddle the chunk boundary: the vectors the previous chunks finished (vector-major in Z) take part
+        // in the Gram-Schmidt of this chunk
+        const bool cross = j0 > 0 && fabs(B.lam[j0] - B.lam[j0 - 1]) <= 1e-3 * tnorm;
+        cluster = cluster || cross;
         for (int itn = 0; itn < DG_EIG_INVIT; ++itn) {
           DG_FOR(jj, kc) {
             double* z = Zt + jj;
@@ -796,9 +800,19 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
           c.sync();
           if (cluster) {
             if (c.warp() == 0) {                   // modified Gram-Schmidt inside clusters, lanes along the vectors
-              for (int jj = 1; jj < kc; ++jj) {
+              for (int jj = cross ? 0 : 1; jj < kc; ++jj) {
                 double* z = Zt + jj;
                 bool changed = false;
+                for (int ip = j0 - 1; cross && ip >= 0; --ip) {      // finished vectors of earlier chunks (eigenvalues ascend)
+                  if (fabs(B.lam[j0 + jj] - B.lam[ip]) > 1e-3 * tnorm) break;
+                  const double* zp = Z + (size_t)ip * n;
+                  double dt = 0.0;
+                  for (int i = c.lane(); i < n; i += c.wsz) dt += zp[i] * z[i * CH];
+                  dt = c.warp_sum(dt);
+                  for (int i = c.lane(); i < n; i += c.wsz) z[i * CH] -= dt * zp[i];
+                  c.syncwarp();
+                  changed = true;
+                }
                 for (int ii = 0; ii < jj; ++ii) {
                   if (fabs(B.lam[j0 + jj] - B.lam[j0 + ii]) > 1e-3 * tnorm) continue;
                   const double* zi = Zt + ii;

@@ -189,6 +189,34 @@ class DGSQP:
             self.set_warm_start(np.vstack((self.u_pred[1:], self.u_pred[-1])))
         return info
 
+    def step_batch(self, x0, u_ws=None, u_prev=None):
+        """Receding-horizon step of B independent games at once: the batched form of ``step`` (DGSQP.py:283-297,
+        DGSQP_v2.py:301-328) for closed-loop Monte-Carlo runs (many races advanced in lock-step).
+
+        ``x0`` [B, n_q]; ``u_ws`` [B, n] agent-major warm start (default: the shifted solutions this solver kept from the
+        previous call, zeros on the first); ``u_prev`` [B, n_u] previous inputs (v2 policy; default: what the previous
+        call applied).  Returns ``(u0, result)`` -- ``u0`` [B, n_u] the first-stage inputs to apply, ``result`` the
+        :class:`BatchResult` -- and keeps, per instance, ``u_prev = u0`` and the warm start shifted by one stage with the
+        last stage repeated, except where the solve diverged / failed its QP (the previous warm start stays, like the
+        reference)."""
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        B = x0.shape[0]
+        st = getattr(self, "_batch_state", None)
+        if st is None or st["u_ws"].shape[0] != B:
+            st = self._batch_state = dict(u_ws=np.zeros((B, self.game.n)), u_prev=np.zeros((B, self.n_u)))
+        if u_ws is not None:
+            st["u_ws"] = np.ascontiguousarray(u_ws, dtype=np.float64).copy()
+        if u_prev is not None:
+            st["u_prev"] = np.ascontiguousarray(u_prev, dtype=np.float64).copy()
+        res = self.solve_batch(x0, st["u_ws"], u_prev=st["u_prev"] if self.v2 else None)
+        u_sm = self.agent_to_stage_major(res.u)                     # [B, N, n_u]
+        u0 = np.ascontiguousarray(u_sm[:, 0])
+        st["u_prev"] = u0.copy()
+        ok = ~np.isin(res.status, (3, 4))                           # 'diverged', 'qp_fail' keep the old warm start
+        shifted = self.stage_to_agent_major(np.concatenate((u_sm[:, 1:], u_sm[:, -1:]), axis=1))
+        st["u_ws"][ok] = shifted[ok]
+        return u0, res
+
     def get_prediction(self) -> List[VehiclePrediction]:
         return self.state_input_predictions
 

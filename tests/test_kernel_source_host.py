@@ -81,6 +81,23 @@ def test_nearest_pd_many_negative_eigenvalues_and_clusters(chicane_full):
     assert nn0 == 0
 
 
+def test_nearest_pd_cluster_across_inverse_iteration_chunks(chicane_full):
+    """A degenerate cluster of negative eigenvalues that straddles the boundary between two inverse-iteration chunks
+    (16 vectors each): its vectors must be orthogonalised against the ones the previous chunk finished."""
+    og, game, params = chicane_full
+    hs = HostSim(game, params)
+    rng = np.random.default_rng(11)
+    n = og.n
+    U, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    s = np.concatenate([-np.linspace(10.0, 4.0, 14), [-2.0, -2.0, -2.0 - 1e-12, -2.0 + 1e-12, -2.0], [-1.0, -0.5],
+                        rng.uniform(0.1, 5, n - 21)])
+    Q = (U * s) @ U.T
+    H2, nneg = hs.nearest_pd(Q)
+    assert nneg == 21
+    assert np.abs(H2 - (nearest_pd(Q) + 1e-3 * np.eye(n))).max() < 1e-9
+    assert np.linalg.eigvalsh(H2).min() > 0.9e-3
+
+
 def test_lsqr_dual_init(chicane_full):
     """Dual initialisation: same recurrences / stopping rules as scipy.sparse.linalg.lsqr with reorthogonalised
     Golub-Kahan vectors.  Kernel source == oracle to rounding, iteration for iteration; the literal SciPy call

@@ -49,3 +49,30 @@ def test_v2_u_prev_and_step_sequence():
         shifted = solver.stage_to_agent_major(np.vstack((u1[1:], u1[-1]))[None])[0]
         r2 = sol.solve(x0[0], shifted, u_prev=u1[0])
         assert info2["msg"] == r2["msg"] and info2["num_iters"] == r2["num_iters"]
+
+
+def test_step_batch_closed_loop_matches_single_steps():
+    """step_batch: B races advanced in lock-step.  Two closed-loop steps of 5 instances -- the states moved
+    by the bicycle model of the host sampler between the steps -- give, per instance, exactly what the single-instance
+    step() sequence of the reference-shaped class gives (same applied inputs, status, iterations)."""
+    N = 10
+    kw = dict(reg=1e-2, reg_decay=0.8, nms_frequency=2, sqp_iters=40, p_tol=1e-4, d_tol=1e-4)
+    game = dg.chicane_game(N=N)
+    x0, u_ws = sample_head_to_head(game, 5, seed=9)
+    batch = dg.DGSQP(game, dg.DGSQPV2Params(N=N, **kw), print_method=None, mu_vio_thresh=1e-10)
+    u0a, ra = batch.step_batch(x0, u_ws=u_ws)
+    x1 = ra.x.reshape(5, N + 1, game.n_q)[:, 1]                    # the solver's own roll-out: state after applying u0
+    u0b, rb = batch.step_batch(x1)
+    assert u0a.shape == (5, game.n_u) and np.array_equal(u0a, batch.agent_to_stage_major(ra.u)[:, 0])
+    for i in range(5):
+        single = dg.DGSQP(game, dg.DGSQPV2Params(N=N, **kw), print_method=None, mu_vio_thresh=1e-10)
+        single.set_warm_start(single.agent_to_stage_major(u_ws[i:i + 1])[0])
+        for step, (xs, u0, res) in enumerate(((x0, u0a, ra), (x1, u0b, rb))):
+            states = []
+            for a in range(2):
+                s = dg.VehicleState(t=0.0)
+                s.x.x, s.x.y, s.v.v_long, s.p.e_psi, s.p.s, s.p.x_tran = xs[i, 6 * a:6 * a + 6]
+                states.append(s)
+            info = single.step(states)
+            assert info["msg"] == res.msg[i] and info["num_iters"] == int(res.num_iters[i]), (i, step)
+            assert np.array_equal(single.u_pred[0], u0[i]), (i, step)
