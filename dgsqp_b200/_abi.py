@@ -68,7 +68,7 @@ class ParamsV2Struct(C.Structure):
 
 
 EXPORTS = ["dgsqp_create", "dgsqp_create_v2", "dgsqp_create_merge", "dgsqp_create_merge_v2", "dgsqp_destroy", "dgsqp_dims", "dgsqp_solve_batch", "dgsqp_solve_batch_up", "dgsqp_solve_batch_async",
-           "dgsqp_batch_stats", "dgsqp_pid_rollout", "dgsqp_last_diag", "dgsqp_iter_log_capacity", "dgsqp_last_iter_data", "dgsqp_phase_count", "dgsqp_last_phase_cycles", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_memory_plan", "dgsqp_set_smem_limit", "dgsqp_last_error", "dgsqp_version"]
+           "dgsqp_batch_stats", "dgsqp_last_stats", "dgsqp_pid_rollout", "dgsqp_last_diag", "dgsqp_iter_log_capacity", "dgsqp_last_iter_data", "dgsqp_phase_count", "dgsqp_last_phase_cycles", "dgsqp_measure_fp64_peak", "dgsqp_kernel_launches", "dgsqp_configure", "dgsqp_memory_plan", "dgsqp_set_smem_limit", "dgsqp_last_error", "dgsqp_version"]
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "libdgsqp_b200.so"
 _lib = None
@@ -113,6 +113,8 @@ def load():
     lib.dgsqp_pid_rollout.restype = C.c_int
     lib.dgsqp_batch_stats.argtypes = [C.c_int, C.c_int32, vp, vp, vp, vp, vp, vp]
     lib.dgsqp_batch_stats.restype = C.c_int
+    lib.dgsqp_last_stats.argtypes = [vp, vp]
+    lib.dgsqp_last_stats.restype = C.c_int
     lib.dgsqp_last_diag.argtypes = [vp, C.c_int32, vp]
     lib.dgsqp_last_diag.restype = C.c_int
     lib.dgsqp_iter_log_capacity.argtypes = [vp]

@@ -19,6 +19,7 @@ struct dgsqp_handle_vtbl {
   int (*last_phase_cycles)(dgsqp_handle*, int32_t, int64_t*);
   int (*iter_log_capacity)(const dgsqp_handle*);
   int (*last_iter_data)(dgsqp_handle*, int32_t, double*);
+  int (*last_stats)(dgsqp_handle*, double*);
 };
 struct dgsqp_handle { const dgsqp_handle_vtbl* vt = nullptr; };
 

@@ -249,6 +249,11 @@ int dgsqp_last_iter_data(dgsqp_handle* h, int32_t B, double* out) {
 
 int dgsqp_phase_count(void) { return DG_NPHASE; }
 
+int dgsqp_last_stats(dgsqp_handle* h, double* out16) {
+  if (!h) return dg_set_err(DGSQP_EINVAL, "NULL handle");
+  return h->vt->last_stats(h, out16);
+}
+
 int dgsqp_last_phase_cycles(dgsqp_handle* h, int32_t B, int64_t* cycles) {
   if (!h || !cycles) return dg_set_err(DGSQP_EINVAL, "NULL argument");
   return h->vt->last_phase_cycles(h, B, cycles);

@@ -17,7 +17,12 @@
 #include "cta.cuh"
 
 #define DG_EIG_CHUNK 16     // eigenvectors computed concurrently by inverse iteration
-#define DG_EIG_INVIT 3      // inverse-iteration sweeps per eigenvector (shifts are accurate to ~1 ulp of |T|)
+#ifndef DG_EIG_INVIT
+#define DG_EIG_INVIT 2      // inverse-iteration sweeps per eigenvector (shifts are accurate to ~1 ulp of |T|: H agrees with
+                            // eigh to 3e-15 relative with 2 as with 3 sweeps, 1.4e-14 with one; tests/test_kernel_source_host.py)
+#endif
+#define DG_EIG_SMALL 2       // eigenvectors whose inverse-iteration scratch fits the small shared-memory block LinBuf::eig_s
+                            // (merge game: 11.5 KB beside the 212 KB of the split placement)
 #define DG_CHOL_NB 8        // Cholesky panel width
 #ifndef DG_MAX_THREADS
 #define DG_MAX_THREADS 256
@@ -39,6 +44,7 @@ struct LinBuf {
   double* wv;     // n
   double* sp;     // n*DG_CHOL_NB  Cholesky panel (aliases the seven vectors above)
   double* part;   // max(DG_PART_SZ, 2n)  partial sums of the 2D-decomposed products, scratch vectors
+  double* eig_s;  // 6*n*DG_EIG_SMALL or null: shared-memory scratch of the inverse iteration when matB lives in the L2 workspace
 };
 
 #ifdef DG_NO_SH_LIN
@@ -639,6 +645,16 @@ DG_DEV double tridiag_shift_solve(int n, const double* DG_RESTRICT dg, const dou
   return nr;
 }
 
+// One inverse-iteration sweep of one eigenvector (thread-serial): start vector on the first sweep, solve, normalise.
+DG_DEV void invit_sweep(int n, const double* DG_RESTRICT dg, const double* DG_RESTRICT od, double lam, double tiny,
+                        double* DG_RESTRICT fw, double* DG_RESTRICT z, int st, bool first, int seed) {
+  if (first)
+    for (int i = 0; i < n; ++i) z[i * st] = 1.0 + 0.37 * (double)(((i + 1) * 7919 + seed * 104729) % 97) / 97.0;
+  double nr = tridiag_shift_solve(n, dg, od, lam, tiny, fw, z, st, first);
+  nr = DG_RSQRT(nr);
+  for (int i = 0; i < n; ++i) z[i * st] *= nr;
+}
+
 // Negative eigenvalues of the tridiagonal matrix into B.lam[0..nneg): Sturm-count multisection.  All
 // eigenvalues are refined together: each round spends the CTA's nt probes evenly over the brackets.
 // lo/hi: nneg doubles each; first: nneg ints of scratch.
@@ -775,6 +791,10 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
       double* Zs = Zt + n * CH;
       const long cap = ((long)n * ld - (Zs - scr)) / n;    // eigenvectors that fit behind the scratch
       double* Z = nneg <= cap ? Zs : B.Zg;
+      // matB in the L2 workspace (split / global placement): the serial chains of the inverse iteration would walk L2; the
+      // usual one to three vectors run in a small shared-memory block instead, interleaved with stride nneg
+      int st = CH;
+      if (B.eig_s && nneg <= DG_EIG_SMALL) { st = nneg; itw = B.eig_s; Zt = itw + 5 * n * st; }
       negative_eigenvalues<SM>(c, n, B, nneg, tnorm, pivmin, B.pv, B.wv, cnts);
       c.lapf(PH_PD_EIGVAL);
       // --- eigenvectors in chunks: inverse iteration (thread per vector), Gram-Schmidt inside clusters
@@ -790,12 +810,9 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
         cluster = cluster || cross;
         for (int itn = 0; itn < DG_EIG_INVIT; ++itn) {
           DG_FOR(jj, kc) {
-            double* z = Zt + jj;
-            if (itn == 0)
-              for (int i = 0; i < n; ++i) z[i * CH] = 1.0 + 0.37 * (double)(((i + 1) * 7919 + (j0 + jj) * 104729) % 97) / 97.0;
-            double nr = tridiag_shift_solve(n, B.dg, B.od, B.lam[j0 + jj], tiny, itw + jj, z, CH, itn == 0);
-            nr = DG_RSQRT(nr);
-            for (int i = 0; i < n; ++i) z[i * CH] *= nr;
+            // (the stride is a compile-time constant on the common path: the serial chains index six arrays with it)
+            if (st == CH) invit_sweep(n, B.dg, B.od, B.lam[j0 + jj], tiny, itw + jj, Zt + jj, CH, itn == 0, j0 + jj);
+            else invit_sweep(n, B.dg, B.od, B.lam[j0 + jj], tiny, itw + jj, Zt + jj, st, itn == 0, j0 + jj);
           }
           c.sync();
           if (cluster) {
@@ -807,9 +824,9 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
                   if (fabs(B.lam[j0 + jj] - B.lam[ip]) > 1e-3 * tnorm) break;
                   const double* zp = Z + (size_t)ip * n;
                   double dt = 0.0;
-                  for (int i = c.lane(); i < n; i += c.wsz) dt += zp[i] * z[i * CH];
+                  for (int i = c.lane(); i < n; i += c.wsz) dt += zp[i] * z[i * st];
                   dt = c.warp_sum(dt);
-                  for (int i = c.lane(); i < n; i += c.wsz) z[i * CH] -= dt * zp[i];
+                  for (int i = c.lane(); i < n; i += c.wsz) z[i * st] -= dt * zp[i];
                   c.syncwarp();
                   changed = true;
                 }
@@ -817,17 +834,17 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
                   if (fabs(B.lam[j0 + jj] - B.lam[j0 + ii]) > 1e-3 * tnorm) continue;
                   const double* zi = Zt + ii;
                   double dt = 0.0;
-                  for (int i = c.lane(); i < n; i += c.wsz) dt += zi[i * CH] * z[i * CH];
+                  for (int i = c.lane(); i < n; i += c.wsz) dt += zi[i * st] * z[i * st];
                   dt = c.warp_sum(dt);
-                  for (int i = c.lane(); i < n; i += c.wsz) z[i * CH] -= dt * zi[i * CH];
+                  for (int i = c.lane(); i < n; i += c.wsz) z[i * st] -= dt * zi[i * st];
                   c.syncwarp();
                   changed = true;
                 }
                 if (changed) {
                   double nr = 0.0;
-                  for (int i = c.lane(); i < n; i += c.wsz) nr += z[i * CH] * z[i * CH];
+                  for (int i = c.lane(); i < n; i += c.wsz) nr += z[i * st] * z[i * st];
                   nr = 1.0 / sqrt(c.warp_sum(nr));
-                  for (int i = c.lane(); i < n; i += c.wsz) z[i * CH] *= nr;
+                  for (int i = c.lane(); i < n; i += c.wsz) z[i * st] *= nr;
                   c.syncwarp();
                 }
               }
@@ -836,7 +853,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
           }
         }
         // de-interleave the chunk into the vector-major store
-        for (int e = c.tid(); e < kc * n; e += c.nt()) { int jj = e / n, i = e - jj * n; Z[(size_t)(j0 + jj) * n + i] = Zt[i * CH + jj]; }
+        for (int e = c.tid(); e < kc * n; e += c.nt()) { int jj = e / n, i = e - jj * n; Z[(size_t)(j0 + jj) * n + i] = Zt[i * st + jj]; }
         c.sync();
       }
       c.lapf(PH_PD_INVIT);

@@ -139,6 +139,9 @@ DG_HD MemPlan plan_memory(const Dims& D, double* gbase, double* sbase, size_t sb
   PLACE(W.S.u, n); PLACE(W.S.du, n); PLACE(W.S.l, m); PLACE(W.S.dl, m); PLACE(W.Q.lam, m);
   PLACE(W.S.u_c, n); PLACE(W.S.l_c, m); PLACE(W.S.s, m); PLACE(W.S.ds, m); PLACE(W.S.Gdu, m);
   PLACE(W.S.tn, n); PLACE(W.S.tn2, n);
+  // ---- small shared-memory scratch of the inverse iteration when matB is not shared-memory resident (linalg.cuh: eig_s)
+  W.B.eig_s = nullptr;
+  if (!P.mats_in_smem && so + rnd(6 * n * DG_EIG_SMALL) + DG_GPAD <= sbudget) STAKE(W.B.eig_s, 6 * n * DG_EIG_SMALL);
   // ---- global only
   GTAKE(W.E.Q, n * n); GTAKE(W.B.Zg, n * n);
   { double* t; GTAKE(t, (m + 1) / 2 + 1); W.E.rowtab = (int*)t; }

@@ -353,6 +353,13 @@ class DGSQP:
                                                C.c_void_p(stream)))
         return out
 
+    def last_stats(self) -> np.ndarray:
+        """The same 16-entry statistics vector for the LAST ``solve_batch`` of this solver, accumulated by the solve kernel
+        itself in its epilogue (``dgsqp_last_stats``): no second pass over the outputs, no extra launch."""
+        out = np.zeros(16)
+        _abi.check(self._lib.dgsqp_last_stats(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def last_iter_data(self, B):
         """Per-iteration records of the last solve_batch (needs ``params.save_iter_data``): for each of the first B instances
         the list the reference keeps as ``iter_data`` (DGSQP.py:445-452; v2: the IterationData fields of the same name,

@@ -214,6 +214,12 @@ int dgsqp_pid_rollout(const dgsqp_racing_game* game, const double* key_pts, int 
 int dgsqp_batch_stats(int device, int32_t B, const int32_t* status, const int32_t* num_iters, const int32_t* qp_solves,
                       const double* cond, double* out16, void* stream);
 
+/* The same 16 statistics for the LAST solve_batch[_async] on this handle, accumulated by the solve kernel itself as its
+ * instances finish (one atomic per entry and instance in the kernel's epilogue: no second pass over the outputs, no extra
+ * launch).  Waits for that launch; out16 is a HOST array.  Counts and iteration sums are integer-valued doubles, so the
+ * result does not depend on the order in which the instances finish. */
+int dgsqp_last_stats(dgsqp_handle* h, double* out16);
+
 /* Per-instance work counters of the LAST solve_batch on this handle (device->host copy), DGSQP_NDIAG = 8 ints each:
  * full evaluations, gradient-only evaluations, QP active-set iterations, max #negative eigenvalues of a Hessian,
  * QPs whose Hessian was indefinite, sum of #negative eigenvalues, sum of final active-set sizes, line-search trials. */

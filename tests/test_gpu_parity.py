@@ -499,6 +499,17 @@ def test_device_statistics_match_host_statistics(big_batch):
     assert np.array_equal(solver.batch_stats(res)[:13], shard_stats(res.status, res.num_iters, res.qp_solves, res.cond)[:13])
 
 
+def test_fused_statistics_equal_host_statistics(big_batch):
+    """the statistics the solve kernel accumulates in its epilogue (dgsqp_last_stats) equal the host
+    reduction of the returned arrays entry for entry (counts and iteration sums are exact; the maxima bitwise)."""
+    from dgsqp_b200.sharding import shard_stats
+    game, params, solver, x0, u_ws, res = big_batch
+    again = solver.solve_batch(x0[:3000], u_ws[:3000])
+    fused = solver.last_stats()
+    host = shard_stats(again.status, again.num_iters, again.qp_solves, again.cond)
+    assert fused[0] == 3000 and np.array_equal(fused[:15], host[:15])
+
+
 def test_large_sample_parity_1000():
     """The CUDA path on the first 1000 instances of the bench batch against the oracle's stored results
     (tests/golden/chicane_N25_seed0_stats.npz): identical (status, iterations) on at least 99 % -- the bar BASELINE.json
