@@ -794,7 +794,9 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
       // matB in the L2 workspace (split / global placement): the serial chains of the inverse iteration would walk L2; the
       // usual one to three vectors run in a small shared-memory block instead, interleaved with stride nneg
       int st = CH;
-      if (B.eig_s && nneg <= DG_EIG_SMALL) { st = nneg; itw = B.eig_s; Zt = itw + 5 * n * st; }
+      if constexpr (!SM) {                 // (SM = true: matB is shared memory already, and the pointers keep their address space)
+        if (B.eig_s && nneg <= DG_EIG_SMALL) { st = nneg; itw = B.eig_s; Zt = itw + 5 * n * st; }
+      }
       negative_eigenvalues<SM>(c, n, B, nneg, tnorm, pivmin, B.pv, B.wv, cnts);
       c.lapf(PH_PD_EIGVAL);
       // --- eigenvectors in chunks: inverse iteration (thread per vector), Gram-Schmidt inside clusters
@@ -811,7 +813,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
         for (int itn = 0; itn < DG_EIG_INVIT; ++itn) {
           DG_FOR(jj, kc) {
             // (the stride is a compile-time constant on the common path: the serial chains index six arrays with it)
-            if (st == CH) invit_sweep(n, B.dg, B.od, B.lam[j0 + jj], tiny, itw + jj, Zt + jj, CH, itn == 0, j0 + jj);
+            if (SM || st == CH) invit_sweep(n, B.dg, B.od, B.lam[j0 + jj], tiny, itw + jj, Zt + jj, CH, itn == 0, j0 + jj);
             else invit_sweep(n, B.dg, B.od, B.lam[j0 + jj], tiny, itw + jj, Zt + jj, st, itn == 0, j0 + jj);
           }
           c.sync();
