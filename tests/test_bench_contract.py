@@ -31,12 +31,34 @@ def _check_line(d, reference=False):
     assert d["warmup"] >= 3
 
 
+def _last_line(name):
+    return json.loads((ROOT / "profiles" / name).read_text().strip().splitlines()[-1])
+
+
 def test_committed_bench_lines_follow_the_contract():
     for name in ("r1_s15_bench.json", "r1_s13_bench_merge.json"):
         _check_line(json.loads((ROOT / "profiles" / name).read_text()))
     _check_line(json.loads((ROOT / "profiles" / "r1_s13_bench_ref.json").read_text()), reference=True)
     two = json.loads((ROOT / "profiles" / "r1_s12_bench_2gpu.json").read_text().strip().splitlines()[-1])
     assert two["n_gpus"] == 2 and two["config"]["instances_per_gpu"] == 2960
+
+
+def test_round2_bench_lines_follow_the_contract():
+    """The round-2 lines of every BASELINE workload: contract keys, the reference arm on the SAME config as the GPU arm
+    (same_config was false), measured DRAM traffic for the two profiled workloads, single-instance latency."""
+    head = _last_line("r2_final_bench.json")
+    _check_line(head)
+    ref = _last_line("r2_final_bench_ref.json")
+    _check_line(ref, reference=True)
+    assert ref["config"] == head["config"] and ref["metric"] == head["metric"] and ref["unit"] == head["unit"]
+    assert head["roofline"]["traffic"] is not None and head["single_instance"]["gpu_ms_median"] > 0
+    assert head["cpu_baseline"]["value"] > 5.0          # the BLAS-thread defect of round 1 gave 0.35
+    for wl in ("merge", "curve", "agents3", "agents4"):
+        d = _last_line(f"r2_final_bench_{wl}.json")
+        _check_line(d)
+        assert d["config"]["workload"].startswith(wl[:5]) or wl.startswith("agents")
+    two = _last_line("r2_final_bench_2gpu.json")
+    assert two["n_gpus"] == 2 and 1.9 < two["value"] / head["value"] < 2.1
 
 
 def test_bench_defaults_and_arguments():
