@@ -46,15 +46,15 @@ def test_committed_bench_lines_follow_the_contract():
 def test_round2_bench_lines_follow_the_contract():
     """The round-2 lines of every BASELINE workload: contract keys, the reference arm on the SAME config as the GPU arm
     (same_config was false), measured DRAM traffic for the two profiled workloads, single-instance latency."""
-    head = _last_line("r2_final_bench.json")
+    head = _last_line("r2_close_bench.json")
     _check_line(head)
-    ref = _last_line("r2_final_bench_ref.json")
+    ref = _last_line("r2_close_bench_ref.json")
     _check_line(ref, reference=True)
     assert ref["config"] == head["config"] and ref["metric"] == head["metric"] and ref["unit"] == head["unit"]
     assert head["roofline"]["traffic"] is not None and head["single_instance"]["gpu_ms_median"] > 0
     assert head["cpu_baseline"]["value"] > 5.0          # the BLAS-thread defect of round 1 gave 0.35
     for wl in ("merge", "curve", "agents3", "agents4"):
-        d = _last_line(f"r2_final_bench_{wl}.json")
+        d = _last_line(f"r2_close_bench_{wl}.json" if wl != "agents4" else "r2_final_bench_agents4.json")
         _check_line(d)
         assert d["config"]["workload"].startswith(wl[:5]) or wl.startswith("agents")
     two = _last_line("r2_final_bench_2gpu.json")
