@@ -184,157 +184,6 @@ DG_DEVN void sym_tridiag(Cta& c, int n, const LinBuf& B_, int kstop) {
 }
 
 #ifndef DG_HOSTSIM
-// ---- register-resident tridiagonalisation (256-thread CTAs, n <= 2*RMAX <= 128) --------------------------------
-// Thread (i = tid & 127, g = tid >> 7) owns column i of the rows j = g, g+2, ... in a[r] (j = g + 2r): the trailing
-// matrix never touches shared memory.  The Householder vector / the rank-2 vectors are broadcast from shared
-// memory in a parity-split layout (element j at (j&1)*RMAX + (j>>1)) so that a thread fetches two of its rows'
-// coefficients per 128-bit load.  The live part of a thread's rows starts at r_first = ceil((off - g) / 2), which
-// moves by one 4-row chunk every 8 steps: the three register sweeps of a step (peel, products, update) are
-// compiled once per chunk offset CB and selected by ONE CTA-uniform switch on (k+1)>>3, so the sweeps themselves
-// are branch-free straight-line code (per-chunk guards cost more than the arithmetic they skipped).
-// Rows that are already eliminated and padding rows (j >= n) need no masks: their entries of x are kept at zero, so
-// they add nothing to the products, and whatever the update writes into their registers is never used.
-template <int RMAX, int CB>
-DG_DEV void tri_sweep_products(const double (&a)[RMAX], const double* DG_RESTRICT xg, double& acc) {
-  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll
-  for (int cb = CB; cb < RMAX; cb += 4) {
-    const double2 x01 = *reinterpret_cast<const double2*>(xg + cb);
-    const double2 x23 = *reinterpret_cast<const double2*>(xg + cb + 2);
-    acc0 += a[cb + 0] * x01.x; acc1 += a[cb + 1] * x01.y; acc2 += a[cb + 2] * x23.x; acc3 += a[cb + 3] * x23.y;
-  }
-  acc = (acc0 + acc1) + (acc2 + acc3);
-}
-template <int RMAX, int CB>
-DG_DEV void tri_sweep_update(double (&a)[RMAX], const double* DG_RESTRICT pg, const double* DG_RESTRICT wg, double vi, double wi) {
-  const double nvi = -vi, nwi = -wi;
-#pragma unroll
-  for (int cb = CB; cb < RMAX; cb += 4) {
-    const double2 v01 = *reinterpret_cast<const double2*>(pg + cb), v23 = *reinterpret_cast<const double2*>(pg + cb + 2);
-    const double2 w01 = *reinterpret_cast<const double2*>(wg + cb), w23 = *reinterpret_cast<const double2*>(wg + cb + 2);
-    // two fused multiply-adds per entry (nvi = -v_i, nwi = -w_i)
-    a[cb + 0] = fma(v01.x, nwi, fma(w01.x, nvi, a[cb + 0])); a[cb + 1] = fma(v01.y, nwi, fma(w01.y, nvi, a[cb + 1]));
-    a[cb + 2] = fma(v23.x, nwi, fma(w23.x, nvi, a[cb + 2])); a[cb + 3] = fma(v23.y, nwi, fma(w23.y, nvi, a[cb + 3]));
-  }
-}
-// a[CB + d], d in 0..4 (the row `off` of this thread's parity sits at r_first, within 4 rows of the chunk offset)
-template <int RMAX, int CB>
-DG_DEV double tri_peel(const double (&a)[RMAX], int d) {
-  double v = a[CB];
-#pragma unroll
-  for (int q = 1; q <= 4; ++q) if (CB + q < RMAX) v = d == q ? a[CB + q < RMAX ? CB + q : 0] : v;
-  return v;
-}
-#define DG_TRI_CASE(m, ...) case m: if constexpr (4 * m < RMAX) { constexpr int CB = 4 * m; __VA_ARGS__; } break;
-#define DG_TRI_SWITCH(seg, ...) switch (seg) { \
-  DG_TRI_CASE(0, __VA_ARGS__) DG_TRI_CASE(1, __VA_ARGS__) DG_TRI_CASE(2, __VA_ARGS__) DG_TRI_CASE(3, __VA_ARGS__) DG_TRI_CASE(4, __VA_ARGS__) DG_TRI_CASE(5, __VA_ARGS__) \
-  DG_TRI_CASE(6, __VA_ARGS__) DG_TRI_CASE(7, __VA_ARGS__) DG_TRI_CASE(8, __VA_ARGS__) DG_TRI_CASE(9, __VA_ARGS__) DG_TRI_CASE(10, __VA_ARGS__) DG_TRI_CASE(11, __VA_ARGS__) \
-  DG_TRI_CASE(12, __VA_ARGS__) DG_TRI_CASE(13, __VA_ARGS__) DG_TRI_CASE(14, __VA_ARGS__) DG_TRI_CASE(15, __VA_ARGS__) default: break; }
-
-// Per step k (off = k+1):
-//   row off is peeled out of the registers                                          [needed twice below]
-//   partial products  sum_j A[j][i] x_j  with the raw column x; the j = off term is corrected to
-//   u_off = alpha - beta  (u = v / scale)                                           -> barrier
-//   p = tau*scale*(sum), v, p.v (block sum), w = p - hk v                           -> barrier
-//   A -= v w' + w v' in registers; the next column = updated row off = row - (w + w_off v) needs no second peel
-//   block sum of the next column norm.
-// Same outputs as sym_tridiag: dg, od, od2, tau and the reflectors in W[k+2.., k].
-// Needs 4*RMAX <= 3n doubles behind B.pv (pv .. pv+3n is one region) and 256 + 2*RMAX <= DG_PART_SZ.
-template <int RMAX, bool SM>
-DG_DEVN void sym_tridiag_regs(Cta& c, int n, const LinBuf& B_) {
-  static_assert(RMAX % 4 == 0 && RMAX <= 64, "RMAX: multiple of the 4-row chunk, at most 64 rows per thread");
-  const LinBuf B = B_; DG_SH_LIN_T(B);
-  double* DG_RESTRICT W = B.matA;
-  const int ld = B.ld;
-  const int i = c.tid() & 127, g = c.tid() >> 7;
-  constexpr int XS = RMAX;                                        // stride of the parity-split layout
-  constexpr int VS = 2 * XS;                                      // doubles per parity-split vector incl. zero padding
-  double* DG_RESTRICT part = B.part;                              // [2][128] partial products
-  double* DG_RESTRICT xs = B.part + 256;                          // x  (parity-split)
-  double* DG_RESTRICT pv = B.pv;                                  // v  (parity-split)
-  double* DG_RESTRICT wv = B.pv + VS;                             // w  (parity-split)
-#define DG_PS(j) ((((j) & 1) * XS) + ((j) >> 1))
-  const int r_end = (n - g + 1) >> 1;                             // rows owned: j = g + 2r < n
-  const bool col_ok = i < n;
-  double a[RMAX];
-#pragma unroll
-  for (int r = 0; r < RMAX; ++r) a[r] = 0.0;
-  if (col_ok) {
-#pragma unroll
-    for (int r = 0; r < RMAX; ++r) if (r < r_end) a[r] = W[(g + 2 * r) * ld + i];
-  }
-  DG_FOR(t, VS) { xs[t] = 0.0; pv[t] = 0.0; wv[t] = 0.0; }
-  c.sync();
-  // row 0 -> x, |x[1:]|^2, first diagonal entry
-  double nrm = 0.0;
-  if (g == 0 && col_ok) {
-    if (i >= 1) xs[DG_PS(i)] = a[0];
-    if (i >= 2) nrm = a[0] * a[0];
-    if (i == 0) B.dg[0] = a[0];
-  }
-  double xn2 = c.sum(nrm);
-  const double* DG_RESTRICT xg = xs + g * XS;
-  const double* DG_RESTRICT pg = pv + g * XS;
-  const double* DG_RESTRICT wg = wv + g * XS;
-  for (int k = 0; k + 1 < n; ++k) {
-    const int off = k + 1;
-    const int seg = off >> 3;                                     // CTA-uniform chunk offset CB = 4*seg <= r_first
-    const double alpha = xs[DG_PS(off)];
-    double tauk = 0.0, beta = alpha, scale = 0.0;
-    if (xn2 > 0.0) {
-      beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-      tauk = (beta - alpha) / beta;
-      scale = 1.0 / (alpha - beta);
-    }
-    if (c.tid() == 0) { B.od[k] = beta; B.od2[k] = beta * beta; B.tau[k] = tauk; }
-    const int r_first = (off - g + 1) >> 1;                       // first owned row with j >= off
-    const bool own_off = g == (off & 1);                          // this thread's group holds row off, at r_first
-    // peel row off (pre-update) out of the registers
-    double rowv = 0.0;
-    DG_TRI_SWITCH(seg, rowv = tri_peel<RMAX, CB>(a, r_first - CB))
-    double vi = 0.0, wi = 0.0, woff = 0.0;
-    if (tauk != 0.0) {
-      double acc = 0.0;
-      DG_TRI_SWITCH(seg, (tri_sweep_products<RMAX, CB>(a, xg, acc)))
-      if (own_off) acc -= rowv * beta;                             // u_off = alpha - beta instead of alpha
-      part[g * 128 + i] = acc;
-      c.sync();
-      double pdot = 0.0, pi = 0.0;
-      if (c.tid() == 0) xs[DG_PS(off)] = 0.0;                       // alpha has been consumed: dead entries of x must read as 0
-      if (g == 0 && col_ok && i >= off) {
-        pi = (part[i] + part[128 + i]) * (tauk * scale);
-        vi = i == off ? 1.0 : xs[DG_PS(i)] * scale;
-        pv[DG_PS(i)] = vi;
-        pdot = pi * vi;
-      }
-      const double hk = 0.5 * tauk * c.sum(pdot);
-      if (g == 0 && col_ok && i >= off) {
-        wv[DG_PS(i)] = pi - hk * vi;
-        if (i > off) W[i * ld + k] = vi;                           // keep the reflector
-      }
-      c.sync();
-      if (col_ok) { vi = pv[DG_PS(i)]; wi = wv[DG_PS(i)]; }
-      woff = wv[DG_PS(off)];
-      DG_TRI_SWITCH(seg, (tri_sweep_update<RMAX, CB>(a, pg, wg, vi, wi)))
-    } else c.sync();                                               // (rare) nothing to annihilate: order the x reads before the writes below
-    // next column = updated row off  (v_off = 1)
-    nrm = 0.0;
-    if (tauk == 0.0 && c.tid() == 0) xs[DG_PS(off)] = 0.0;
-    if (own_off && col_ok && i >= off) {
-      const double xnew = tauk != 0.0 ? rowv - (wi + woff * vi) : rowv;
-      if (i == off) B.dg[off] = xnew;
-      else {
-        xs[DG_PS(i)] = xnew;
-        if (i >= off + 2) nrm = xnew * xnew;
-      }
-    }
-    xn2 = c.sum(nrm);
-  }
-  if (c.tid() == 0) { B.od[n - 1] = 0.0; B.od2[n - 1] = 0.0; }
-  c.sync();
-#undef DG_PS
-}
-
 // ---- register-resident tridiagonalisation on 2D tiles (256-thread CTAs, n <= 16*T <= 128) ----------------------------
 // The column-per-thread form above pulls every entry of the Householder vectors through shared memory once per THREAD
 // (three broadcasts of ~n/2 doubles per thread and step: ~2500 shared-memory wavefronts per step at n = 100 -- the
@@ -541,16 +390,6 @@ DG_DEV bool sym_tridiag_tiles_dispatch(Cta& c, int n, const LinBuf& B, const dou
   return true;
 }
 
-// picks the instantiation whose scratch fits: 4*RMAX <= 3n and n <= 2*RMAX
-template <bool SM>
-DG_DEV bool sym_tridiag_regs_dispatch(Cta& c, int n, const LinBuf& B) {
-  if (c.nt() != 256) return false;
-  if (n >= 27 && n <= 40) { sym_tridiag_regs<20, SM>(c, n, B); return true; }
-  if (n >= 43 && n <= 64) { sym_tridiag_regs<32, SM>(c, n, B); return true; }
-  if (n >= 70 && n <= 104) { sym_tridiag_regs<52, SM>(c, n, B); return true; }
-  if (n >= 105 && n <= 128) { sym_tridiag_regs<64, SM>(c, n, B); return true; }
-  return false;
-}
 #endif
 
 // number of eigenvalues of tridiag(dg, od) that are < x   (od2 = od^2).
@@ -769,7 +608,7 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
       LinBuf Bt = B;
       Bt.matA = B.matA + (size_t)base * ld + base; Bt.dg = B.dg + base; Bt.od = B.od + base; Bt.od2 = B.od2 + base; Bt.tau = B.tau + base;
       sym_tridiag_tiles<8, SM>(c, 128, Bt, nullptr);
-    } else if (!sym_tridiag_tiles_dispatch<SM>(c, n, B, Qraw) && !sym_tridiag_regs_dispatch<SM>(c, n, B))
+    } else if (!sym_tridiag_tiles_dispatch<SM>(c, n, B, Qraw))
 #endif
     sym_tridiag<SM>(c, n, B, n);
     c.lap(PH_PD_TRIDIAG);
@@ -1002,70 +841,6 @@ DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, doubl
 }
 
 #ifndef DG_HOSTSIM
-// ---- register-resident Cholesky (256-thread CTAs, n <= 2*RMAX <= 128) ------------------------------------------------
-// Same thread mapping as sym_tridiag_regs: thread (i = tid & 127, g = tid >> 7) keeps column i of the rows j = g, g+2, ..
-// of the (full, symmetric) trailing matrix in a[r].  Right-looking step k:
-//   row k (= column k) is peeled out of the registers of the parity-(k&1) threads and published in a parity-split buffer
-//                                                                                                   -> ONE barrier
-//   every thread reads the pivot d = A[k][k] (non-positive: not PD), the owners store L[i][k] = A[k][i] / sqrt(d),
-//   A[j][i] -= A[k][j] * (A[k][i] / d) over the thread's rows: one FMA per entry, the row broadcast with 128-bit loads.
-// The row buffers alternate between steps, so a thread that runs ahead never overwrites a row that is still being read.
-// Rows <= k are dead: whole 4-row chunks of them are skipped by the CTA-uniform switch of the tridiagonalisation, what
-// remains of them only collects values nobody reads.  The blocked shared-memory version this replaces (cholesky_lower)
-// spends four barriers and a one-warp 8x8 factorisation per panel: 196 kcycles at n = 100 against ~2 n^3/3 / 64 = 10.
-// Needs 4*RMAX doubles in B.part.
-template <int RMAX, int CB>
-DG_DEV void chol_sweep(double (&a)[RMAX], const double* DG_RESTRICT xg, double nci) {
-#pragma unroll
-  for (int cb = CB; cb < RMAX; cb += 4) {
-    const double2 x01 = *reinterpret_cast<const double2*>(xg + cb), x23 = *reinterpret_cast<const double2*>(xg + cb + 2);
-    a[cb + 0] = fma(x01.x, nci, a[cb + 0]); a[cb + 1] = fma(x01.y, nci, a[cb + 1]);
-    a[cb + 2] = fma(x23.x, nci, a[cb + 2]); a[cb + 3] = fma(x23.y, nci, a[cb + 3]);
-  }
-}
-template <int RMAX, bool SM>
-DG_DEVN bool cholesky_regs(Cta& c, int n, const LinBuf& B_) {
-  static_assert(RMAX % 4 == 0 && RMAX <= 64, "RMAX: multiple of the 4-row chunk, at most 64 rows per thread");
-  const LinBuf B = B_; DG_SH_LIN_T(B);
-  double* DG_RESTRICT W = B.matA;
-  const int ld = B.ld;
-  const int i = c.tid() & 127, g = c.tid() >> 7;
-  constexpr int XS = RMAX;
-#define DG_PS(j) ((((j) & 1) * XS) + ((j) >> 1))
-  double* DG_RESTRICT buf = B.part;                               // two parity-split row buffers of 2*XS doubles
-  const int r_end = (n - g + 1) >> 1;
-  const bool col_ok = i < n;
-  double a[RMAX];
-#pragma unroll
-  for (int r = 0; r < RMAX; ++r) a[r] = 0.0;
-  if (col_ok) {
-#pragma unroll
-    for (int r = 0; r < RMAX; ++r) if (r < r_end) a[r] = W[(g + 2 * r) * ld + i];
-  }
-  DG_FOR(t, 4 * XS) buf[t] = 0.0;
-  c.sync();
-  for (int k = 0; k < n; ++k) {
-    const int seg = k >> 3;                                        // CTA-uniform chunk offset CB = 4*seg <= first live row
-    const bool own = g == (k & 1);
-    const int r_k = (k - g) >> 1;                                  // owners: row k sits at r_k, within 4 rows of CB
-    double rowv = 0.0;
-    DG_TRI_SWITCH(seg, rowv = tri_peel<RMAX, CB>(a, own ? r_k - CB : 0))
-    double* DG_RESTRICT rb = buf + (k & 1) * 2 * XS;
-    if (own && col_ok) rb[DG_PS(i)] = rowv;
-    c.sync();
-    const double d = rb[DG_PS(k)];
-    if (!(d > 0.0)) return false;
-    const double inv = DG_RSQRT(d);
-    if (own && col_ok && i >= k) { W[i * ld + k] = rowv * inv; W[k * ld + i] = rowv * inv; }   // L and, mirrored, L' (tri_inverse_regs walks rows)
-    const double nci = col_ok ? -(rb[DG_PS(i)] * inv) * inv : 0.0;
-    const double* DG_RESTRICT xg = rb + g * XS;
-    DG_TRI_SWITCH(seg, (chol_sweep<RMAX, CB>(a, xg, nci)))
-  }
-  c.sync();
-#undef DG_PS
-  return true;
-}
-
 // ---- Cholesky and triangular inverse on 2D register tiles (256-thread CTAs, n <= 16*T <= 128) -------------------------
 // Same 16 x 16 thread grid and cyclic tiles as sym_tridiag_tiles: the column-per-thread forms above move ~n/2 doubles
 // per THREAD and step through shared memory (the LSU, not the FP64 pipe, bounds them); a tile needs the T entries of the
@@ -1265,88 +1040,8 @@ DG_DEV bool tri_inverse_tiles_dispatch(Cta& c, int n, const LinBuf& B) {
   return true;
 }
 
-// picks the instantiation whose scratch fits; false = not applicable (the caller runs cholesky_lower)
-template <bool SM>
-DG_DEV bool cholesky_regs_dispatch(Cta& c, int n, const LinBuf& B, bool& ok) {
-  if (c.nt() != 256) return false;
-  if (n >= 27 && n <= 40) { ok = cholesky_regs<20, SM>(c, n, B); return true; }
-  if (n >= 43 && n <= 64) { ok = cholesky_regs<32, SM>(c, n, B); return true; }
-  if (n >= 70 && n <= 104) { ok = cholesky_regs<52, SM>(c, n, B); return true; }
-  if (n >= 105 && n <= 128) { ok = cholesky_regs<64, SM>(c, n, B); return true; }
-  return false;
-}
 #endif
 
-#ifndef DG_HOSTSIM
-// ---- register-resident triangular inverse (256-thread CTAs, n <= 2*RMAX <= 128; pairs with cholesky_regs) ----------------
-// Y = L^-1 column by column: lanes (2c, 2c+1) of a warp own column c, the residual r of L y = e_c lives in their
-// registers in 4-row chunks that alternate between the two lanes (local index r <-> row 8 (r>>2) + 4 g + (r&3)).
-// Step k (the same k in every thread; columns c > k just carry zeros, which also zero-fills the upper triangle the
-// active-set solver expects):  y_k = r_k / L_kk is formed by the lane that holds row k and handed to its neighbour with
-// one shuffle, then r_j -= L[j][k] y_k over the thread's live chunks.  Column k of L is read as ROW k of the mirror L'
-// that cholesky_regs leaves in the upper triangle: the four rows of a chunk are contiguous, every lane of a parity reads
-// the same address (broadcast), 128-bit loads on even k.  No CTA barrier inside the sweep: the warps never exchange data.
-// The blocked shared-memory version this replaces (tri_inverse) costs 108 kcycles at n = 100.
-template <int RMAX, int CB>
-DG_DEV void trinv_sweep_vec(double (&a)[RMAX], const double* DG_RESTRICT row, int g, int n, double nx) {
-#pragma unroll
-  for (int cb = CB; cb < RMAX; cb += 4) {
-    if (2 * cb + 4 * g < n) {
-      const double2 x01 = *reinterpret_cast<const double2*>(row + 2 * cb), x23 = *reinterpret_cast<const double2*>(row + 2 * cb + 2);
-      a[cb + 0] = fma(x01.x, nx, a[cb + 0]); a[cb + 1] = fma(x01.y, nx, a[cb + 1]);
-      a[cb + 2] = fma(x23.x, nx, a[cb + 2]); a[cb + 3] = fma(x23.y, nx, a[cb + 3]);
-    }
-  }
-}
-template <int RMAX, int CB>
-DG_DEV void trinv_sweep_scl(double (&a)[RMAX], const double* DG_RESTRICT row, int g, int n, double nx) {
-#pragma unroll
-  for (int cb = CB; cb < RMAX; cb += 4) {
-    if (2 * cb + 4 * g < n) {
-      const double x0 = row[2 * cb], x1 = row[2 * cb + 1], x2 = row[2 * cb + 2], x3 = row[2 * cb + 3];
-      a[cb + 0] = fma(x0, nx, a[cb + 0]); a[cb + 1] = fma(x1, nx, a[cb + 1]);
-      a[cb + 2] = fma(x2, nx, a[cb + 2]); a[cb + 3] = fma(x3, nx, a[cb + 3]);
-    }
-  }
-}
-template <int RMAX, bool SM>
-DG_DEVN void tri_inverse_regs(Cta& c, int n, const LinBuf& B_) {
-  static_assert(RMAX % 4 == 0 && RMAX <= 64, "RMAX: multiple of the 4-row chunk, at most 64 rows per thread");
-  const LinBuf B = B_; DG_SH_LIN_T(B);
-  const double* DG_RESTRICT W = B.matA;
-  double* DG_RESTRICT Y = B.matB;
-  double* DG_RESTRICT rdiag = B.part;
-  const int ld = B.ld;
-  const int col = c.tid() >> 1, g = c.tid() & 1;
-  DG_FOR(k, n) rdiag[k] = 1.0 / W[k * ld + k];
-  double a[RMAX];
-#pragma unroll
-  for (int r = 0; r < RMAX; ++r) a[r] = (8 * (r >> 2) + 4 * g + (r & 3)) == col ? 1.0 : 0.0;
-  c.sync();
-  for (int k = 0; k < n; ++k) {
-    const int seg = k >> 3;                                        // CTA-uniform chunk offset CB = 4*seg
-    const bool own = g == ((k >> 2) & 1);
-    double rk = 0.0;
-    DG_TRI_SWITCH(seg, rk = tri_peel<RMAX, CB>(a, k & 3))
-    double x = own ? rk * rdiag[k] : 0.0;
-    const double other = __shfl_xor_sync(0xffffffffu, x, 1);
-    x = own ? x : other;
-    if (own && col < n) Y[k * ld + col] = x;
-    const double* DG_RESTRICT row = W + k * ld + 4 * g;
-    if (k & 1) { DG_TRI_SWITCH(seg, (trinv_sweep_scl<RMAX, CB>(a, row, g, n, -x))) }
-    else { DG_TRI_SWITCH(seg, (trinv_sweep_vec<RMAX, CB>(a, row, g, n, -x))) }
-  }
-}
-template <bool SM>
-DG_DEV bool tri_inverse_regs_dispatch(Cta& c, int n, const LinBuf& B) {
-  if (c.nt() != 256) return false;
-  if (n >= 27 && n <= 40) { tri_inverse_regs<20, SM>(c, n, B); return true; }
-  if (n >= 43 && n <= 64) { tri_inverse_regs<32, SM>(c, n, B); return true; }
-  if (n >= 70 && n <= 104) { tri_inverse_regs<52, SM>(c, n, B); return true; }
-  if (n >= 105 && n <= 128) { tri_inverse_regs<64, SM>(c, n, B); return true; }
-  return false;
-}
-#endif
 
 // Y = L^{-1} (lower triangular; L and Y row-major with leading dimension ld: Y[i][c]; the strict upper triangle of Y
 // is zero-filled because the active-set solver treats Y as dense).  Blocked by NB = 8 rows:

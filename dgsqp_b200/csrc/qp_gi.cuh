@@ -551,21 +551,17 @@ DG_DEVN bool qp_factor(Cta& c, const Dims& D_, const double* DG_RESTRICT qv, con
   const QpBuf Q = Q_; DG_SH_QP(Q); const LinBuf B = B_; DG_SH_LIN(B); const Dims D = D_;
   const int n = D.n, m = D.m, ld = B.ld;
   double* DG_RESTRICT Y = B.matB;
-  bool regs = false;
   {
     bool ok = false;
 #ifndef DG_HOSTSIM
-    if (!cholesky_tiles_dispatch<SM>(c, n, B, ok)) regs = cholesky_regs_dispatch<SM>(c, n, B, ok);
-    else regs = true;
-    if (!regs)
+    if (!cholesky_tiles_dispatch<SM>(c, n, B, ok))
 #endif
     ok = cholesky_lower<SM>(c, n, ld, B.matA, B.sp, B.part);
     if (!ok) return false;
   }
   c.lap(PH_CHOL);
 #ifndef DG_HOSTSIM
-  // (tri_inverse_regs reads the mirror L' that cholesky_regs leaves in the upper triangle; the tile forms need only L)
-  if (!tri_inverse_tiles_dispatch<SM>(c, n, B) && !(regs && tri_inverse_regs_dispatch<SM>(c, n, B)))
+  if (!tri_inverse_tiles_dispatch<SM>(c, n, B))
 #endif
   tri_inverse<SM>(c, n, ld, B.matA, Y, B.sp, B.part);
   c.sync();

@@ -52,3 +52,23 @@ def test_pid_rollout_on_device():
     # and the solver accepts them
     res = dg.DGSQP(game, dg.chicane_params(), print_method=None, mu_vio_thresh=1e-10).solve_batch(xd[:64], udv[:64])
     assert set(np.unique(res.status)) <= {0, 1, 2, 3, 4}
+
+
+def test_pid_rollout_against_the_oracle_rk45_sampler():
+    """The product roll-out (fixed-step RK4 x 4 per stage, the form the device kernel implements) against the ORACLE's
+    faithful restatement of the script's sampler (oracle/sampler.py: SciPy RK45 at its default rtol = 1e-3 / atol = 1e-6,
+    dynamics_models.py:161-186).  Same initial state bit for bit; the warm-start trajectories and inputs differ by the
+    reference integrator's own tolerance (measured on 40 starts: 1.1e-2 in position, 2.3e-2 in the inputs) -- they are
+    solver INPUTS, the parity fixtures draw theirs from the oracle sampler."""
+    from oracle import sampler as osamp
+    from oracle.racing_game import RacingGame
+    from oracle.track import chicane_track
+    og, game = RacingGame(chicane_track(), M=2, N=25), dg.chicane_game()
+    rng = np.random.default_rng(1)
+    K = 24
+    s0, xt0, v0 = np.maximum(0.1, rng.random(K) * 3.0), rng.random(K) * 2 - 1, rng.random(K) + 2
+    q0, xy, u = pid_rollout(game, s0, xt0, v0)
+    for i in range(K):
+        q0o, qws, uo = osamp.pid_rollout(og, s0[i], xt0[i], v0[i])
+        assert np.array_equal(q0o, q0[i])
+        assert np.abs(qws[:, :2] - xy[i]).max() < 3e-2 and np.abs(uo - u[i]).max() < 6e-2
