@@ -591,6 +591,217 @@ DG_DEV void negative_eigenvalues(Cta& c, int n, const LinBuf& B, int nneg, doubl
 }
 
 #ifndef DG_HOSTSIM
+// ---- eigenvector of the tridiagonal matrix by one warp: twisted factorisation (Fernando / Parlett-Dhillon) ---------------
+// With D+_i = p_i / p_{i-1} (leading minors of T - lam I) and D-_i = r_i / r_{i+1} (trailing minors),
+//   gamma_k = D+_k + D-_k - (d_k - lam),   twist index r = argmin |gamma_k|,
+//   z_r = 1,   z_i = -(e_i / D+_i) z_{i+1} (i < r),   z_i = -(e_{i-1} / D-_i) z_{i-1} (i > r)
+// solves (T - lam I) z = gamma_r e_r: one factorisation from each end instead of the LU + 2 x 2 substitutions of inverse
+// iteration, and every recurrence is a scan -- the minors through the 2x2 products of sturm_count_group16 (32 lanes), the
+// entries of z as running products kept as (mantissa, exponent) pairs so that no range is lost.  Lane l owns the rows
+// [l R, (l+1) R), R = ceil(n/32) <= 4.  The caller accepts the vector only if its residual |gamma_r| |z_r| / |z| is at
+// rounding level (returned) and falls back to inverse iteration otherwise; clusters always take the inverse iteration.
+struct MantExp { double f; int e; };                   // value = f * 2^e, f = 0 or |f| in [1, 2)
+DG_DEV MantExp me_norm(double v, int e) {
+  MantExp r; r.f = v; r.e = e;
+  const int eb = (__double2hiint(v) >> 20) & 0x7ff;
+  if (eb > 0 && eb < 0x7ff) { r.f = __hiloint2double((__double2hiint(v) & 0x800fffff) | 0x3ff00000, __double2loint(v)); r.e = e + eb - 1023; }
+  else if (eb == 0) { r.f = 0.0; r.e = -(1 << 28); }
+  return r;
+}
+DG_DEV MantExp me_mul(MantExp a, MantExp b) { return me_norm(a.f * b.f, a.e + b.e); }
+template <int R>
+DG_DEV double twisted_eigvec(Cta& c, int n, const double* DG_RESTRICT dg, const double* DG_RESTRICT od, const double* DG_RESTRICT od2,
+                             double lam, double pivmin, double* DG_RESTRICT z, double& rq_shift) {
+  const int l = c.lane(), i0 = l * R;
+  double dp[R], dm[R], a[R], e[R];                      // D+, D-, d_i - lam, e_i (couples i, i+1)
+#pragma unroll
+  for (int r = 0; r < R; ++r) { const int i = i0 + r; a[r] = i < n ? dg[i] - lam : 1.0; e[r] = i + 1 < n ? od[i] : 0.0; }
+  // forward minors
+  {
+    double p11 = 1.0, p12 = 0.0, p21 = 0.0, p22 = 1.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = i0 + r;
+      if (i < n) {
+        const double b = i > 0 ? od2[i - 1] : 0.0;
+        const double n11 = fma(a[r], p11, -b * p21), n12 = fma(a[r], p12, -b * p22);
+        p21 = p11; p22 = p12; p11 = n11; p12 = n12;
+      }
+    }
+    sturm_norm4(p11, p12, p21, p22);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t11 = __shfl_up_sync(0xffffffffu, p11, o), t12 = __shfl_up_sync(0xffffffffu, p12, o);
+      const double t21 = __shfl_up_sync(0xffffffffu, p21, o), t22 = __shfl_up_sync(0xffffffffu, p22, o);
+      if (l >= o) {
+        const double n11 = fma(p11, t11, p12 * t21), n12 = fma(p11, t12, p12 * t22);
+        const double n21 = fma(p21, t11, p22 * t21), n22 = fma(p21, t12, p22 * t22);
+        p11 = n11; p12 = n12; p21 = n21; p22 = n22;
+        sturm_norm4(p11, p12, p21, p22);
+      }
+    }
+    double pc = __shfl_up_sync(0xffffffffu, p11, 1), pm = __shfl_up_sync(0xffffffffu, p21, 1);
+    if (l == 0) { pc = 1.0; pm = 0.0; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = i0 + r;
+      dp[r] = 1.0;
+      if (i < n) {
+        const double t = (i > 0 ? od2[i - 1] : 0.0) * pm, lim = pivmin * fabs(pc);
+        double pn = fma(a[r], pc, -t);
+        pn = fabs(pn) < lim ? -pivmin * pc : pn;
+        dp[r] = pn / pc;
+        pm = pc; pc = pn;
+      }
+    }
+  }
+  // backward minors: (r_i, r_{i+1})' = [[d_i - lam, -e_i^2], [1, 0]] (r_{i+1}, r_{i+2})'
+  {
+    double p11 = 1.0, p12 = 0.0, p21 = 0.0, p22 = 1.0;
+#pragma unroll
+    for (int r = R - 1; r >= 0; --r) {
+      const int i = i0 + r;
+      if (i < n) {
+        const double b = e[r] * e[r];
+        const double n11 = fma(a[r], p11, -b * p21), n12 = fma(a[r], p12, -b * p22);
+        p21 = p11; p22 = p12; p11 = n11; p12 = n12;
+      }
+    }
+    sturm_norm4(p11, p12, p21, p22);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t11 = __shfl_down_sync(0xffffffffu, p11, o), t12 = __shfl_down_sync(0xffffffffu, p12, o);
+      const double t21 = __shfl_down_sync(0xffffffffu, p21, o), t22 = __shfl_down_sync(0xffffffffu, p22, o);
+      if (l + o < 32) {
+        const double n11 = fma(p11, t11, p12 * t21), n12 = fma(p11, t12, p12 * t22);
+        const double n21 = fma(p21, t11, p22 * t21), n22 = fma(p21, t12, p22 * t22);
+        p11 = n11; p12 = n12; p21 = n21; p22 = n22;
+        sturm_norm4(p11, p12, p21, p22);
+      }
+    }
+    double rc = __shfl_down_sync(0xffffffffu, p11, 1), rm = __shfl_down_sync(0xffffffffu, p21, 1);
+    if (l == 31) { rc = 1.0; rm = 0.0; }
+#pragma unroll
+    for (int r = R - 1; r >= 0; --r) {
+      const int i = i0 + r;
+      dm[r] = 1.0;
+      if (i < n) {
+        const double t = e[r] * e[r] * rm, lim = pivmin * fabs(rc);
+        double rn = fma(a[r], rc, -t);
+        rn = fabs(rn) < lim ? -pivmin * rc : rn;
+        dm[r] = rn / rc;
+        rm = rc; rc = rn;
+      }
+    }
+  }
+  // twist index
+  double gbest = 1e300; int kbest = 0x7fffffff;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = i0 + r;
+    if (i < n) { const double g = fabs(dp[r] + dm[r] - a[r]); if (g < gbest) { gbest = g; kbest = i; } }
+  }
+  double gmin = gbest; int kr = kbest;
+  c.warp_argmin(gmin, kr);
+  double gsig = 0.0;                                      // gamma_r with its sign
+#pragma unroll
+  for (int r = 0; r < R; ++r) if (i0 + r == kr) gsig = dp[r] + dm[r] - a[r];
+  gsig = c.warp_sum(gsig);
+  // multipliers: rows above the twist use D+ (z_i = mu_i z_{i+1}), rows below use D- (z_i = mu_i z_{i-1}); scans of running
+  // products in (mantissa, exponent) form.  up[r] = prod_{j=i}^{kr-1} mu_j for i < kr; dn[r] = prod_{j=kr+1}^{i} mu_j for i > kr
+  MantExp zr[R];
+  {
+    // upward part: suffix products of mu_j = -e_j / D+_j over j in [i, kr)
+    MantExp loc = {1.0, 0};
+    MantExp part[R];
+#pragma unroll
+    for (int r = R - 1; r >= 0; --r) {
+      const int i = i0 + r;
+      if (i < kr && i < n) loc = me_mul(loc, me_norm(-e[r] / dp[r], 0));
+      part[r] = loc;
+    }
+    MantExp tot = loc;                                     // product of this lane's rows that lie above the twist
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double tf = __shfl_down_sync(0xffffffffu, tot.f, o); const int te = __shfl_down_sync(0xffffffffu, tot.e, o);
+      if (l + o < 32) { MantExp t2 = {tf, te}; tot = me_mul(tot, t2); }
+    }
+    double cf = __shfl_down_sync(0xffffffffu, tot.f, 1); int ce = __shfl_down_sync(0xffffffffu, tot.e, 1);
+    if (l == 31) { cf = 1.0; ce = 0; }
+    MantExp carry = {cf, ce};                              // product over all later lanes
+#pragma unroll
+    for (int r = 0; r < R; ++r) zr[r] = me_mul(part[r], carry);
+  }
+  {
+    // downward part: prefix products of mu_j = -e_{j-1} / D-_j over j in (kr, i]
+    MantExp loc = {1.0, 0};
+    MantExp part[R];
+    const double eprev = __shfl_up_sync(0xffffffffu, e[R - 1], 1);      // e_{i0-1}: couples the previous lane's last row with this lane's first
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = i0 + r;
+      if (i > kr && i < n) {
+        const double em1 = r > 0 ? e[r - 1] : eprev;
+        loc = me_mul(loc, me_norm(-em1 / dm[r], 0));
+      }
+      part[r] = loc;
+    }
+    MantExp tot = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double tf = __shfl_up_sync(0xffffffffu, tot.f, o); const int te = __shfl_up_sync(0xffffffffu, tot.e, o);
+      if (l >= o) { MantExp t2 = {tf, te}; tot = me_mul(tot, t2); }
+    }
+    double cf = __shfl_up_sync(0xffffffffu, tot.f, 1); int ce = __shfl_up_sync(0xffffffffu, tot.e, 1);
+    if (l == 0) { cf = 1.0; ce = 0; }
+    MantExp carry = {cf, ce};
+#pragma unroll
+    for (int r = 0; r < R; ++r) { const int i = i0 + r; if (i > kr) zr[r] = me_mul(part[r], carry); }
+  }
+  // common scale, 2-norm, store
+  int emax = -(1 << 28);
+#pragma unroll
+  for (int r = 0; r < R; ++r) { const int i = i0 + r; if (i < n && zr[r].f != 0.0 && zr[r].e > emax) emax = zr[r].e; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, emax, o); emax = t > emax ? t : emax; }
+  double zv[R], nr = 0.0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = i0 + r;
+    const int de = zr[r].e - emax;
+    zv[r] = (i < n && zr[r].f != 0.0 && de > -1000) ? ldexp(zr[r].f, de) : 0.0;
+    nr = fma(zv[r], zv[r], nr);
+  }
+  nr = c.warp_sum(nr);
+  const double sc = DG_RSQRT(nr);
+#pragma unroll
+  for (int r = 0; r < R; ++r) { const int i = i0 + r; if (i < n) z[i] = zv[r] * sc; }
+  // residual of the unit vector: |gamma_r| |z_r|
+  double zk = 0.0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) if (i0 + r == kr) zk = fabs(zv[r]) * sc;
+  zk = c.warp_sum(zk);
+  rq_shift = gsig * zk * zk;                              // Rayleigh quotient of z minus lam ((T - lam I) z = gamma_r z_r e_r)
+  // TRUE residual |(T - lam I) z| of the stored unit vector: gamma_r z_r only bounds it when the pivots carry no growth
+  const double zprev = __shfl_up_sync(0xffffffffu, zv[R - 1], 1), znext = __shfl_down_sync(0xffffffffu, zv[0], 1);
+  const double eprev2 = __shfl_up_sync(0xffffffffu, e[R - 1], 1);
+  double rs = 0.0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = i0 + r;
+    if (i < n) {
+      const double zm = r > 0 ? zv[r - 1] : (l > 0 ? zprev : 0.0), zp = r + 1 < R ? zv[r + 1] : (l < 31 ? znext : 0.0);
+      const double em = r > 0 ? e[r - 1] : (l > 0 ? eprev2 : 0.0);
+      const double ri = (a[r] * zv[r] + em * zm + e[r] * zp) * sc;
+      rs = fma(ri, ri, rs);
+    }
+  }
+  rs = c.warp_sum(rs);
+  return sqrt(rs);
+}
+#endif
+
+#ifndef DG_HOSTSIM
 // The same multisection for up to 16 negative eigenvalues with half-warp probes (sturm_count_group16): 16 probes per round
 // instead of 256, each ~10x cheaper than a thread's chain; the brackets live in the registers of the half warps that refine
 // them (every probe group of an eigenvalue applies the same update), the winners go through three rotating arrays of
@@ -739,9 +950,31 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
 #endif
       negative_eigenvalues<SM>(c, n, B, nneg, tnorm, pivmin, B.pv, B.wv, cnts);
       c.lapf(PH_PD_EIGVAL);
-      // --- eigenvectors in chunks: inverse iteration (thread per vector), Gram-Schmidt inside clusters
+      // --- eigenvectors: without clusters one warp per vector by twisted factorisation (accepted when every residual is at
+      // rounding level); otherwise in chunks by inverse iteration (thread per vector) with Gram-Schmidt inside clusters
       const double tiny = fmax(tnorm, 1.0) * 1.1e-16;
-      for (int j0 = 0; j0 < nneg; j0 += CH) {
+      bool fast_ok = false;
+#ifndef DG_HOSTSIM
+      if (n >= 33 && n <= 128 && (c.nt() & 31) == 0 && pivmin < 2.2250738585072014e-308 * 1.3e36) {
+        bool sep = true;
+        for (int jj = 1; jj < nneg; ++jj) if (fabs(B.lam[jj] - B.lam[jj - 1]) <= 1e-3 * tnorm) sep = false;
+        if (sep) {
+          if (c.tid() == 0) cnts[0] = 0;
+          c.sync();
+          const double tol = 8e-15 * fmax(tnorm, 1.0);     // true residual of the unit vector: what inverse iteration reaches
+          for (int jv = c.warp(); jv < nneg; jv += c.nwarps()) {
+            double shift = 0.0;
+            const double res = n <= 64 ? twisted_eigvec<2>(c, n, B.dg, B.od, B.od2, B.lam[jv], pivmin, Z + (size_t)jv * n, shift)
+                                       : twisted_eigvec<4>(c, n, B.dg, B.od, B.od2, B.lam[jv], pivmin, Z + (size_t)jv * n, shift);
+            if (c.lane() == 0 && !(res <= tol)) cnts[0] = 1;
+          }
+          c.sync();
+          fast_ok = cnts[0] == 0;
+          c.sync();                              // (the flag word is scratch of the inverse iteration below)
+        }
+      }
+#endif
+      for (int j0 = 0; j0 < nneg && !fast_ok; j0 += CH) {
         const int kc = nneg - j0 < CH ? nneg - j0 : CH;
         bool cluster = false;
         for (int jj = 1; jj < kc; ++jj)
