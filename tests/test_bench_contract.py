@@ -57,7 +57,7 @@ def test_round2_bench_lines_follow_the_contract():
         d = _last_line(f"r2_close_bench_{wl}.json" if wl != "agents4" else "r2_final_bench_agents4.json")
         _check_line(d)
         assert d["config"]["workload"].startswith(wl[:5]) or wl.startswith("agents")
-    two = _last_line("r2_final_bench_2gpu.json")
+    two = _last_line("r2_close_bench_2gpu.json")
     assert two["n_gpus"] == 2 and 1.9 < two["value"] / head["value"] < 2.1
 
 
