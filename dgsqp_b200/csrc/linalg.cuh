@@ -845,30 +845,41 @@ DG_DEV void negative_eigenvalues_grp(Cta& c, int n, const LinBuf& B, int nneg, d
 template <int RPL>
 DG_DEV void backtransform_regs(Cta& c, int n, int ld, const double* DG_RESTRICT W, const double* DG_RESTRICT tau,
                                double* DG_RESTRICT Z, int nvec) {
+  // reflector k as a register vector: v_j = 0 (j <= k), 1 (j == k+1), W[j][k] (j > k+1)
+  auto load = [&](double (&v)[RPL], int k) {
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) { const int j = c.lane() + 32 * r; v[r] = (j > k + 1 && j < n) ? W[j * ld + k] : (j == k + 1 ? 1.0 : 0.0); }
+  };
   for (int jv = c.warp(); jv < nvec; jv += c.nwarps()) {
     double* DG_RESTRICT z = Z + (size_t)jv * n;
-    double zr[RPL], v[RPL], vn[RPL];
+    double zr[RPL], va[RPL], vb[RPL], na[RPL], nb[RPL];
 #pragma unroll
     for (int r = 0; r < RPL; ++r) { const int j = c.lane() + 32 * r; zr[r] = j < n ? z[j] : 0.0; }
-    // reflector k: v_j = 0 (j <= k), 1 (j == k+1), W[j][k] (j > k+1)
+    // two reflectors per pass: H_{k-1} H_k z = z - v_k a - v_{k-1} b with a = tau_k v_k'z, b = tau_{k-1} (v_{k-1}'z - (v_{k-1}'v_k) a):
+    // the three dot products of a pass share one shuffle-sum latency (half as many dependent chains as one reflector at a time)
     int k = n - 3;
+    if (k >= 1) { load(na, k); load(nb, k - 1); }
+    for (; k >= 1; k -= 2) {
+      const double ta = tau[k], tb = tau[k - 1];
 #pragma unroll
-    for (int r = 0; r < RPL; ++r) { const int j = c.lane() + 32 * r; vn[r] = (j > k + 1 && j < n) ? W[j * ld + k] : (j == k + 1 ? 1.0 : 0.0); }
-    for (; k >= 0; --k) {
-      const double tk = tau[k];
+      for (int r = 0; r < RPL; ++r) { va[r] = na[r]; vb[r] = nb[r]; }
+      if (k - 2 >= 1) { load(na, k - 2); load(nb, k - 3); }
+      double d[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-      for (int r = 0; r < RPL; ++r) v[r] = vn[r];
-      if (k > 0) {
+      for (int r = 0; r < RPL; ++r) { d[0] = fma(va[r], zr[r], d[0]); d[1] = fma(vb[r], zr[r], d[1]); d[2] = fma(va[r], vb[r], d[2]); }
+      c.warp_sum_n(d);
+      const double a = ta * d[0], b = tb * (d[1] - d[2] * a);
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) { const int j = c.lane() + 32 * r; vn[r] = (j > k && j < n) ? W[j * ld + k - 1] : (j == k ? 1.0 : 0.0); }
-      }
-      if (tk == 0.0) continue;
+      for (int r = 0; r < RPL; ++r) zr[r] = fma(-b, vb[r], fma(-a, va[r], zr[r]));
+    }
+    if (k == 0) {                                             // odd number of reflectors: the last one alone
+      load(va, 0);
       double pp = 0.0;
 #pragma unroll
-      for (int r = 0; r < RPL; ++r) pp = fma(v[r], zr[r], pp);
-      pp = c.warp_sum(pp) * tk;
+      for (int r = 0; r < RPL; ++r) pp = fma(va[r], zr[r], pp);
+      pp = c.warp_sum(pp) * tau[0];
 #pragma unroll
-      for (int r = 0; r < RPL; ++r) zr[r] = fma(-pp, v[r], zr[r]);
+      for (int r = 0; r < RPL; ++r) zr[r] = fma(-pp, va[r], zr[r]);
     }
 #pragma unroll
     for (int r = 0; r < RPL; ++r) { const int j = c.lane() + 32 * r; if (j < n) z[j] = zr[r]; }
