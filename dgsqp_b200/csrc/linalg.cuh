@@ -1102,11 +1102,13 @@ DG_DEVN int nearest_pd(Cta& c, int n, const double* DG_RESTRICT Qraw, const LinB
 // synchronisation only), then thread r solves its own panel row against it, then the trailing lower triangle is
 // updated by the whole CTA.  Four barriers per panel.  scr: NB + 1 doubles of scratch.
 // Returns false (uniformly) on a non-positive pivot.
+// kstop (a multiple of the panel width) < n: only the panels below kstop are factored; the lower triangle of the trailing
+// matrix is left updated for a register-tile continuation (qp_factor).
 template <bool SM>
-DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, double* DG_RESTRICT sp, double* DG_RESTRICT scr) {
+DG_DEVN bool cholesky_lower(Cta& c, int n, int ld, double* DG_RESTRICT Hm, double* DG_RESTRICT sp, double* DG_RESTRICT scr, int kstop) {
   DG_ASSUME_SHARED(Hm); DG_ASSUME_SHARED(sp); DG_ASSUME_SHARED(scr);
   constexpr int NB = DG_CHOL_NB;
-  for (int k0 = 0; k0 < n; k0 += NB) {
+  for (int k0 = 0; k0 < n && k0 < kstop; k0 += NB) {
     const int nb = n - k0 < NB ? n - k0 : NB;
     const int rows = n - k0;
     // stage panel rows k0.. : sp[(i-k0)*NB + t] = Hm[i][k0+t]
@@ -1243,8 +1245,9 @@ DG_DEV bool chol_tile_iter(Cta& c, int n, int k, int ld, double (&a)[T][T], doub
   return true;
 }
 #define DG_CHT_CASE(m) case m: if constexpr (m < T) ok = chol_tile_iter<T, m, SM>(c, n, k, ld, a, W, xs2, lrp, lcp); break;
+// lower_only: the matrix is valid in its lower triangle only (continuation of cholesky_lower): the tiles mirror it.
 template <int T, bool SM>
-DG_DEVN bool cholesky_tiles(Cta& c, int n, const LinBuf& B_) {
+DG_DEVN bool cholesky_tiles(Cta& c, int n, const LinBuf& B_, bool lower_only) {
   const LinBuf B = B_; DG_SH_LIN_T(B);
   double* DG_RESTRICT W = B.matA;
   const int ld = B.ld;
@@ -1257,7 +1260,7 @@ DG_DEVN bool cholesky_tiles(Cta& c, int n, const LinBuf& B_) {
 #pragma unroll
     for (int cb = 0; cb < T; ++cb) {
       const int j = ti + 16 * r, i = tj + 16 * cb;
-      a[r][cb] = (j < n && i < n) ? W[j * ld + i] : 0.0;
+      a[r][cb] = (j < n && i < n) ? ((lower_only && i > j) ? W[i * ld + j] : W[j * ld + i]) : 0.0;
     }
   }
   DG_FOR(t, 256) xs2[t] = 0.0;
@@ -1362,12 +1365,12 @@ template <bool SM>
 DG_DEV bool cholesky_tiles_dispatch(Cta& c, int n, const LinBuf& B, bool& ok) {
   if (c.nt() != 256 || n < 33 || n > 128) return false;
   switch ((n + 15) >> 4) {
-    case 3: ok = cholesky_tiles<3, SM>(c, n, B); break;
-    case 4: ok = cholesky_tiles<4, SM>(c, n, B); break;
-    case 5: ok = cholesky_tiles<5, SM>(c, n, B); break;
-    case 6: ok = cholesky_tiles<6, SM>(c, n, B); break;
-    case 7: ok = cholesky_tiles<7, SM>(c, n, B); break;
-    default: ok = cholesky_tiles<8, SM>(c, n, B); break;
+    case 3: ok = cholesky_tiles<3, SM>(c, n, B, false); break;
+    case 4: ok = cholesky_tiles<4, SM>(c, n, B, false); break;
+    case 5: ok = cholesky_tiles<5, SM>(c, n, B, false); break;
+    case 6: ok = cholesky_tiles<6, SM>(c, n, B, false); break;
+    case 7: ok = cholesky_tiles<7, SM>(c, n, B, false); break;
+    default: ok = cholesky_tiles<8, SM>(c, n, B, false); break;
   }
   return true;
 }

@@ -554,9 +554,20 @@ DG_DEVN bool qp_factor(Cta& c, const Dims& D_, const double* DG_RESTRICT qv, con
   {
     bool ok = false;
 #ifndef DG_HOSTSIM
-    if (!cholesky_tiles_dispatch<SM>(c, n, B, ok))
+    if (c.nt() == 256 && n > 128 && n <= 256) {
+      // larger games (3-4 agents): the blocked panels until at most 128 columns remain, then the register tiles on the
+      // trailing block (its lower triangle is what the panels leave updated)
+      const int base = (n - 128 + DG_CHOL_NB - 1) / DG_CHOL_NB * DG_CHOL_NB;
+      ok = cholesky_lower<SM>(c, n, ld, B.matA, B.sp, B.part, base);
+      if (ok) {
+        c.sync();
+        LinBuf Bt = B;
+        Bt.matA = B.matA + (size_t)base * ld + base;
+        ok = cholesky_tiles<8, SM>(c, n - base, Bt, true);
+      }
+    } else if (!cholesky_tiles_dispatch<SM>(c, n, B, ok))
 #endif
-    ok = cholesky_lower<SM>(c, n, ld, B.matA, B.sp, B.part);
+    ok = cholesky_lower<SM>(c, n, ld, B.matA, B.sp, B.part, n);
     if (!ok) return false;
   }
   c.lap(PH_CHOL);
